@@ -1,0 +1,71 @@
+"""Helpers shared by the golden-vector tests (loads tests/golden/*.npz)."""
+from __future__ import annotations
+
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import operators as oops
+from oracle.tiny_net import TinyEpsNet
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "dps_*.npz")))
+
+
+class Golden:
+    def __init__(self, name: str):
+        z = np.load(os.path.join(GOLDEN_DIR, f"dps_{name}.npz"))
+        self.meta = json.loads(bytes(z["meta"]).decode())
+        self.a = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+        self.name = name
+
+    def __getitem__(self, k):
+        return self.a[k]
+
+    @property
+    def K(self):
+        return len(self.meta["t"])
+
+    @property
+    def L(self):
+        return self.meta["L"]
+
+    @property
+    def shape(self):
+        return tuple(self.meta["shape"])
+
+    def net(self, device="cpu"):
+        net = TinyEpsNet(channels=self.shape[0])
+        net.load_state_dict({k[4:]: v for k, v in self.a.items() if k.startswith("net.")})
+        return net.to(device)
+
+    def y_flat(self):
+        """Observation shaped to broadcast against (L, *y_shape)."""
+        y = self.a["y"]
+        return y if len(self.meta["batch"]) else y.unsqueeze(0)
+
+    def oracle_op(self):
+        spec = self.meta["op"]
+        kind = spec[0]
+        if kind == "identity":
+            return oops.OracleIdentity(self.shape)
+        if kind == "mask":
+            return oops.OracleMaskGather(self.shape, self.a["mask"])
+        if kind == "gblur":
+            return oops.OracleSeparableBlur(self.shape, self.a["taps"])
+        if kind == "motion":
+            return oops.OracleConv2dBlur(self.shape, self.a["kernel2d"])
+        if kind == "box":
+            return oops.OracleBoxDownsample(self.shape, spec[1])
+        raise ValueError(kind)
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """Per-step state relative error: |a-b|_2 / |b|_2 (the 1e-5 metric)."""
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))

@@ -1,0 +1,58 @@
+"""Adjoint (dot-product) tests for the oracle operators -- the specification the
+CUDA operator kernels are held to.  CPU only."""
+import pytest
+import torch
+
+from oracle import operators as oops
+
+
+def _ops():
+    shape = (3, 20, 28)
+    g = torch.Generator().manual_seed(3)
+    mask = torch.rand(shape, generator=g) < 0.7
+    return {
+        "identity": oops.OracleIdentity(shape),
+        "identity_flat": oops.OracleIdentity(shape, flatten=True),
+        "mask": oops.OracleMaskGather(shape, mask),
+        "gblur9": oops.OracleGaussianBlur(shape, 9, 1.5),
+        "gblur61": oops.OracleGaussianBlur(shape, 61, 3.0),
+        "sep_asym": oops.OracleSeparableBlur(shape, torch.rand(7, generator=g), torch.rand(5, generator=g)),
+        "motion_line": oops.OracleConv2dBlur(shape, oops.motion_line_kernel(11, 30.0)),
+        "motion_walk": oops.OracleConv2dBlur(shape, oops.motion_walk_kernel(13, 0.5, seed=1)),
+        "box4": oops.OracleBoxDownsample(shape, 4),
+        "box2": oops.OracleBoxDownsample(shape, 2),
+    }
+
+
+@pytest.mark.parametrize("name", list(_ops().keys()))
+def test_adjoint_identity(name):
+    op = _ops()[name]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, *op.x_shape, generator=g, dtype=torch.float64)
+    y = torch.randn(2, *op.y_shape, generator=g, dtype=torch.float64)
+    if hasattr(op, "taps_h"):
+        op.taps_h, op.taps_v = op.taps_h.double(), op.taps_v.double()
+    if hasattr(op, "kernel2d"):
+        op.kernel2d = op.kernel2d.double()
+    lhs = (op.apply(x) * y).sum()
+    rhs = (x * op.adjoint(y)).sum()
+    assert abs(float(lhs - rhs)) < 1e-9 * max(1.0, abs(float(lhs)))
+
+
+def test_gaussian_taps_normalised_and_symmetric():
+    w = oops.gaussian_taps(61, 3.0)
+    assert w.numel() == 61 and abs(float(w.double().sum()) - 1) < 1e-6
+    assert torch.equal(w, w.flip(0))
+
+
+def test_separable_equals_outer_product_2d():
+    shape = (3, 24, 24)
+    sep = oops.OracleGaussianBlur(shape, 9, 1.5)
+    full = oops.OracleConv2dBlur(shape, torch.outer(sep.taps_v, sep.taps_h))
+    x = torch.randn(2, *shape, generator=torch.Generator().manual_seed(0))
+    assert torch.allclose(sep.apply(x), full.apply(x), atol=1e-6)
+
+
+def test_motion_kernels_sum_to_one():
+    assert abs(float(oops.motion_line_kernel(61, 45.0).sum()) - 1) < 1e-5
+    assert abs(float(oops.motion_walk_kernel(61, 0.5).sum()) - 1) < 1e-5
