@@ -1,0 +1,163 @@
+/*
+ * psx.h -- C ABI of libpsx, the sm_100a posterior-sampling step library.
+ *
+ * This is the drop-in boundary of samplers_b200.  The reference
+ * (thomashirtz/samplers) is pure Python and has no FFI of its own; each entry
+ * point below replaces the eager-torch arithmetic of the cited reference lines
+ * and is what a maintainer of the reference would bind with ctypes (see
+ * INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in any signature;
+ *   - every pointer named d_* is DEVICE memory owned by the caller (allocated by
+ *     torch in the host package); h_* is HOST memory read during the call only;
+ *   - all tensors are fp32, contiguous, "flat" layout (L, C, H, W) = (L, n);
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream); no entry point synchronises the device;
+ *   - return value: PSX_OK or an error code; psx_last_error() gives the text
+ *     (thread-local).  Nothing throws across the boundary.
+ *   - there is NO CPU implementation behind these calls: without a CUDA device
+ *     they fail with PSX_ERR_CUDA.
+ */
+#ifndef PSX_H_
+#define PSX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PSX_API __attribute__((visibility("default")))
+#else
+#define PSX_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSX_OK 0
+#define PSX_ERR_INVALID 1     /* bad argument (shape, null pointer, range)   */
+#define PSX_ERR_CUDA 2        /* CUDA runtime / launch failure               */
+#define PSX_ERR_UNSUPPORTED 3 /* valid request this build has no kernel for  */
+
+#define PSX_MAX_TAPS 127  /* longest 1-D tap vector of a separable blur       */
+#define PSX_ABI_VERSION 1
+
+/* Operator kinds (psx_op_kind). */
+#define PSX_OP_IDENTITY 0
+#define PSX_OP_MASK 1
+#define PSX_OP_BOX 2
+#define PSX_OP_SEPBLUR 3
+#define PSX_OP_CONV2D 4
+
+typedef struct psx_op psx_op; /* opaque host-side operator descriptor */
+
+PSX_API int psx_abi_version(void);
+PSX_API const char* psx_last_error(void);
+
+/* ---------------------------------------------------------------- operators
+ * Degradation operators A (forward) / A^T (adjoint).  Replaces
+ *   samplers/operators/identity.py:36-66      (identity)
+ *   samplers/operators/inpainting.py:98-131,141-187 + linear.py:141-165 (mask)
+ * and adds the operators BASELINE.json names that the reference lacks
+ * (box super-resolution, separable Gaussian blur, 2-D motion blur); their
+ * definition is oracle/operators.py.
+ */
+PSX_API int psx_op_create_identity(int64_t n, psx_op** out);
+/* d_keep: n bytes, 1 = pixel observed, 0 = missing (the reference's mask is the
+ * negation: True = missing, inpainting.py:27).  Dense form: y has n entries,
+ * zeros at missing pixels. */
+PSX_API int psx_op_create_mask(int64_t n, const uint8_t* d_keep, psx_op** out);
+/* mean over non-overlapping factor x factor blocks; y is (C, H/f, W/f). */
+PSX_API int psx_op_create_box(int C, int H, int W, int factor, psx_op** out);
+/* y = V(H(x)): zero-padded "same" cross-correlation of every row with
+ * h_taps_h (length kh, odd) then of every column with h_taps_v (length kv, odd). */
+PSX_API int psx_op_create_sepblur(int C, int H, int W, const float* h_taps_h, int kh,
+                          const float* h_taps_v, int kv, psx_op** out);
+/* depthwise 2-D zero-padded "same" cross-correlation with a kh x kw PSF (odd
+ * sizes, row-major host array); zero taps are skipped. */
+PSX_API int psx_op_create_conv2d(int C, int H, int W, const float* h_kernel, int kh, int kw,
+                         psx_op** out);
+PSX_API int psx_op_destroy(psx_op* op);
+
+PSX_API int psx_op_kind(const psx_op* op);
+PSX_API int64_t psx_op_x_numel(const psx_op* op); /* n   = elements of one x */
+PSX_API int64_t psx_op_y_numel(const psx_op* op); /* n_y = elements of one y */
+/* number of per-sample partial sums psx_dps_pre writes for this operator */
+PSX_API int psx_op_err_parts(const psx_op* op);
+/* bytes of device scratch psx_dps_pre / psx_op_apply / psx_op_adjoint need for L samples */
+PSX_API size_t psx_op_workspace_bytes(const psx_op* op, int64_t L);
+
+/* y = A x  (Operator.apply, operators/base.py:51-61)  */
+PSX_API int psx_op_apply(const psx_op* op, const float* d_x, float* d_y, int64_t L,
+                 void* d_workspace, size_t workspace_bytes, void* stream);
+/* x = A^T y  (Operator.apply_transpose, operators/base.py:63-75) */
+PSX_API int psx_op_adjoint(const psx_op* op, const float* d_y, float* d_x, int64_t L,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Gather / scatter form of the inpainting operator (flatten=True in the reference:
+ * inpainting.py:141-145 gather of the kept pixels, :178-187 scatter into zeros).
+ *   psx_gather : d_out[l, j] = d_in[l, d_idx[j]]           (L, n) -> (L, m)
+ *   psx_scatter: d_out = 0; d_out[l, d_idx[j]] = d_in[l, j] (L, m) -> (L, n)
+ * d_idx: m int64 indices in [0, n), strictly increasing (kept pixels). */
+PSX_API int psx_gather(const float* d_in, const int64_t* d_idx, float* d_out, int64_t L, int64_t n,
+                       int64_t m, void* stream);
+PSX_API int psx_scatter(const float* d_in, const int64_t* d_idx, float* d_out, int64_t L, int64_t n,
+                        int64_t m, void* stream);
+
+/* ------------------------------------------------------------------ K1
+ * psx_dps_pre -- everything between the network's eps output and the network
+ * VJP, in one pass.  Replaces
+ *   samplers/networks/base.py:41-43        Tweedie  x0 = (x_t - s1*eps)/sa
+ *   samplers/inverse_problem.py:17-21      r = y - A(x0)
+ *   samplers/noise.py:77-79 / 121-123      Gaussian / Poisson log-likelihood
+ *   the autograd mirror of those lines     (samplers/samplers/dps.py:102-103)
+ *   samplers/samplers/dps.py:117-120       per-sample |r|_2  (as partial sums)
+ *
+ *   d_cot[l]      = lik_weight * A^T r_l / sqrt_acp          (L, n)
+ *   d_err_part[l] = psx_op_err_parts(op) partial sums of |r_l|^2
+ *
+ * d_cot is d(sum log-lik)/d(x0)/sqrt_acp: the direct term of the gradient and,
+ * times -sqrt_1m_acp, the cotangent of eps.  The caller runs
+ * v = VJP_eps(d_cot) in torch and hands both to psx_dps_post.
+ *
+ * Observation indexing: sample l uses observation l / obs_repeat (so
+ * obs_repeat = L broadcasts one observation, obs_repeat = 1 gives one per
+ * sample) -- BatchView.repeat_observation, batch_view.py:128-137.
+ * lik_weight = 1/sigma^2 (Gaussian) or 2/(rate + 1e-3) (Poisson).
+ * d_x0_out may be NULL.
+ */
+PSX_API int psx_dps_pre(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y,
+                int64_t L, int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp,
+                float lik_weight, float* d_cot, float* d_err_part, float* d_x0_out,
+                void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K2
+ * psx_dps_post -- bridge (DDIM/DDPM ancestral) update fused with the guidance
+ * step and the injected noise.  Replaces
+ *   samplers/samplers/utils/bridge_kernels.py:41,44-45,59   mean + std * z
+ *   samplers/samplers/dps.py:116-122                        + gamma/(|r|+1e-9) * grad
+ * with grad = d_cot - sqrt_1m_acp * d_vjp  (dps.py:103 written out).
+ * c_ell, c_s, std are the fp64 bridge statistics of bridge_kernels.py:28-39
+ * rounded to fp32 by the caller.  d_z may be NULL when std == 0.
+ * d_err_out (L,) receives |r_l|_2 when not NULL.  d_x_next may alias d_x_t.
+ */
+PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_cot,
+                 const float* d_vjp, const float* d_z, const float* d_err_part, int err_parts,
+                 int64_t L, int64_t n, float sqrt_acp, float sqrt_1m_acp, float c_ell,
+                 float c_s, float std, float gamma, float* d_x_next, float* d_err_out,
+                 void* stream);
+
+/* ------------------------------------------------------------- final estimate
+ * psx_tweedie -- x0 = (x_t - s1*eps)/sa (dps.py:125-126), written straight into
+ * the caller's gather slot, optionally accumulating the per-pixel sum and sum
+ * of squares over the L local samples (posterior mean / variance send buffers).
+ * d_sum / d_sumsq (n,) may be NULL; when given they are OVERWRITTEN.
+ */
+PSX_API int psx_tweedie(const float* d_x_t, const float* d_eps, int64_t L, int64_t n, float sqrt_acp,
+                float sqrt_1m_acp, float* d_x0, float* d_sum, float* d_sumsq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSX_H_ */

@@ -1,0 +1,235 @@
+"""ctypes binding of libpsx.so (include/psx.h) -- the only way the host package
+reaches the GPU for the hot path.  There is deliberately no fallback: if the
+library is missing or no CUDA device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libpsx.so")
+
+PSX_OK, PSX_ERR_INVALID, PSX_ERR_CUDA, PSX_ERR_UNSUPPORTED = 0, 1, 2, 3
+OP_IDENTITY, OP_MASK, OP_BOX, OP_SEPBLUR, OP_CONV2D = range(5)
+ABI_VERSION = 1
+
+# name -> (restype, argtypes); must list every prototype of include/psx.h
+_f32p, _i64, _vp, _f = C.c_void_p, C.c_int64, C.c_void_p, C.c_float
+_opp = C.c_void_p
+PROTOTYPES = {
+    "psx_abi_version": (C.c_int, []),
+    "psx_last_error": (C.c_char_p, []),
+    "psx_op_create_identity": (C.c_int, [_i64, C.POINTER(_opp)]),
+    "psx_op_create_mask": (C.c_int, [_i64, _vp, C.POINTER(_opp)]),
+    "psx_op_create_box": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_opp)]),
+    "psx_op_create_sepblur": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
+                                        C.POINTER(C.c_float), C.c_int, C.POINTER(_opp)]),
+    "psx_op_create_conv2d": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int,
+                                       C.POINTER(_opp)]),
+    "psx_op_destroy": (C.c_int, [_opp]),
+    "psx_op_kind": (C.c_int, [_opp]),
+    "psx_op_x_numel": (_i64, [_opp]),
+    "psx_op_y_numel": (_i64, [_opp]),
+    "psx_op_err_parts": (C.c_int, [_opp]),
+    "psx_op_workspace_bytes": (C.c_size_t, [_opp, _i64]),
+    "psx_op_apply": (C.c_int, [_opp, _f32p, _f32p, _i64, _vp, C.c_size_t, _vp]),
+    "psx_op_adjoint": (C.c_int, [_opp, _f32p, _f32p, _i64, _vp, C.c_size_t, _vp]),
+    "psx_gather": (C.c_int, [_f32p, _vp, _f32p, _i64, _i64, _i64, _vp]),
+    "psx_scatter": (C.c_int, [_f32p, _vp, _f32p, _i64, _i64, _i64, _vp]),
+    "psx_dps_pre": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f, _f, _f, _f32p, _f32p, _f32p,
+                              _vp, C.c_size_t, _vp]),
+    "psx_dps_post": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64,
+                               _f, _f, _f, _f, _f, _f, _f32p, _f32p, _vp]),
+    "psx_tweedie": (C.c_int, [_f32p, _f32p, _i64, _i64, _f, _f, _f32p, _f32p, _f32p, _vp]),
+}
+
+
+class PsxError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libpsx error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0  # kernels-launching calls made through the ABI (bench.py reports it)
+
+
+def load() -> C.CDLL:
+    """Loads libpsx.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -m samplers_b200.build` "
+                    "(samplers_b200 has no non-CUDA implementation of the sampling step)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            if lib.psx_abi_version() != ABI_VERSION:
+                raise RuntimeError("libpsx.so ABI version mismatch; rebuild with `python -m samplers_b200.build --force`")
+            _lib = lib
+    return _lib
+
+
+def check(code: int) -> None:
+    if code == PSX_OK:
+        return
+    msg = load().psx_last_error().decode(errors="replace")
+    if code == PSX_ERR_INVALID:
+        raise ValueError(f"libpsx: {msg}")
+    if code == PSX_ERR_UNSUPPORTED:
+        raise NotImplementedError(f"libpsx: {msg}")
+    raise PsxError(code, msg)
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} must be a CUDA tensor: samplers_b200 runs the sampling step in sm_100a kernels only "
+            "(no CPU path)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype} (bf16 state is not implemented yet)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def ptr(t: torch.Tensor | None):
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class NativeOp:
+    """Owns one psx_op descriptor (host struct) and the device buffers it points to."""
+
+    def __init__(self, handle: int, keepalive=()):
+        self.handle = C.c_void_p(handle)
+        self._keepalive = keepalive
+        lib = load()
+        self.kind = lib.psx_op_kind(self.handle)
+        self.n = lib.psx_op_x_numel(self.handle)
+        self.n_y = lib.psx_op_y_numel(self.handle)
+        self.err_parts = lib.psx_op_err_parts(self.handle)
+
+    def workspace_bytes(self, L: int) -> int:
+        return load().psx_op_workspace_bytes(self.handle, L)
+
+    def __del__(self):
+        try:
+            if self.handle and _lib is not None:
+                _lib.psx_op_destroy(self.handle)
+        except Exception:
+            pass
+
+    # -- constructors ------------------------------------------------------
+    @staticmethod
+    def identity(n: int) -> "NativeOp":
+        h = _opp()
+        check(load().psx_op_create_identity(n, C.byref(h)))
+        return NativeOp(h.value)
+
+    @staticmethod
+    def mask(keep_u8: torch.Tensor) -> "NativeOp":
+        assert keep_u8.is_cuda and keep_u8.dtype == torch.uint8 and keep_u8.is_contiguous()
+        h = _opp()
+        check(load().psx_op_create_mask(keep_u8.numel(), keep_u8.data_ptr(), C.byref(h)))
+        return NativeOp(h.value, keepalive=(keep_u8,))
+
+    @staticmethod
+    def box(c: int, hh: int, w: int, factor: int) -> "NativeOp":
+        h = _opp()
+        check(load().psx_op_create_box(c, hh, w, factor, C.byref(h)))
+        return NativeOp(h.value)
+
+    @staticmethod
+    def sepblur(c: int, hh: int, w: int, taps_h, taps_v) -> "NativeOp":
+        th = (C.c_float * len(taps_h))(*[float(v) for v in taps_h])
+        tv = (C.c_float * len(taps_v))(*[float(v) for v in taps_v])
+        h = _opp()
+        check(load().psx_op_create_sepblur(c, hh, w, th, len(taps_h), tv, len(taps_v), C.byref(h)))
+        return NativeOp(h.value)
+
+    @staticmethod
+    def conv2d(c: int, hh: int, w: int, kernel2d: torch.Tensor) -> "NativeOp":
+        kh, kw = kernel2d.shape
+        flat = [float(v) for v in kernel2d.flatten().tolist()]
+        arr = (C.c_float * len(flat))(*flat)
+        h = _opp()
+        check(load().psx_op_create_conv2d(c, hh, w, arr, kh, kw, C.byref(h)))
+        return NativeOp(h.value)
+
+    # -- stand-alone A / A^T ------------------------------------------------
+    def _run(self, fn, src: torch.Tensor, dst_numel: int) -> torch.Tensor:
+        global launch_count
+        require_cuda(src, "operator input")
+        L = src.shape[0]
+        dst = torch.empty((L, dst_numel), device=src.device, dtype=torch.float32)
+        wsb = self.workspace_bytes(L)
+        ws = torch.empty(wsb // 4, device=src.device, dtype=torch.float32) if wsb else None
+        with torch.cuda.device(src.device):
+            check(fn(self.handle, src.data_ptr(), dst.data_ptr(), L, ptr(ws), wsb, stream_ptr(src.device)))
+        launch_count += 1
+        return dst
+
+    def apply(self, x_flat: torch.Tensor) -> torch.Tensor:  # (L, n) -> (L, n_y)
+        return self._run(load().psx_op_apply, x_flat, self.n_y)
+
+    def adjoint(self, y_flat: torch.Tensor) -> torch.Tensor:  # (L, n_y) -> (L, n)
+        return self._run(load().psx_op_adjoint, y_flat, self.n)
+
+
+def gather(src: torch.Tensor, idx: torch.Tensor, scatter: bool, n: int) -> torch.Tensor:
+    """(L, n) -> (L, m) gather of kept pixels, or its transpose (scatter into zeros)."""
+    global launch_count
+    require_cuda(src, "gather input")
+    assert idx.is_cuda and idx.dtype == torch.int64 and idx.is_contiguous()
+    L, m = src.shape[0], idx.numel()
+    out = torch.empty((L, n if scatter else m), device=src.device, dtype=torch.float32)
+    fn = load().psx_scatter if scatter else load().psx_gather
+    with torch.cuda.device(src.device):
+        check(fn(src.data_ptr(), idx.data_ptr(), out.data_ptr(), L, n, m, stream_ptr(src.device)))
+    launch_count += 1
+    return out
+
+
+def dps_pre(op: NativeOp, x_t, eps, y, obs_repeat: int, sa: float, s1: float, weight: float,
+            cot, err_part, ws, x0_out=None) -> None:
+    global launch_count
+    L = x_t.shape[0]
+    with torch.cuda.device(x_t.device):
+        check(load().psx_dps_pre(op.handle, x_t.data_ptr(), eps.data_ptr(), y.data_ptr(), L, obs_repeat,
+                                 sa, s1, weight, cot.data_ptr(), err_part.data_ptr(), ptr(x0_out),
+                                 ptr(ws), 0 if ws is None else ws.numel() * 4, stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def dps_post(x_t, eps, cot, vjp, z, err_part, err_parts: int, n: int, sa: float, s1: float,
+             c_ell: float, c_s: float, std: float, gamma: float, x_next, err_out=None) -> None:
+    global launch_count
+    L = x_t.shape[0]
+    with torch.cuda.device(x_t.device):
+        check(load().psx_dps_post(x_t.data_ptr(), eps.data_ptr(), cot.data_ptr(), vjp.data_ptr(), ptr(z),
+                                  err_part.data_ptr(), err_parts, L, n, sa, s1, c_ell, c_s, std, gamma,
+                                  x_next.data_ptr(), ptr(err_out), stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def tweedie(x_t, eps, sa: float, s1: float, x0, total=None, total_sq=None) -> None:
+    global launch_count
+    L = x_t.shape[0]
+    n = x_t.numel() // L
+    with torch.cuda.device(x_t.device):
+        check(load().psx_tweedie(x_t.data_ptr(), eps.data_ptr(), L, n, sa, s1, x0.data_ptr(),
+                                 ptr(total), ptr(total_sq), stream_ptr(x_t.device)))
+    launch_count += 1

@@ -1,0 +1,259 @@
+// psx_api.cu -- extern "C" entry points of libpsx (see include/psx.h).
+// Host-side validation, operator descriptors, tap preparation; all device work is asynchronous
+// on the caller's stream.  No CPU implementation exists behind these calls.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "psx_common.cuh"
+
+namespace psx {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return PSX_OK;
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return PSX_ERR_CUDA;
+}
+
+int pointwise_parts(int64_t n);
+int box_parts(int64_t ny);
+int launch_post(const float*, const float*, const float*, const float*, const float*, const float*, int,
+                int64_t, int64_t, float, float, float, float, float, float, float*, float*, cudaStream_t);
+int launch_tweedie(const float*, const float*, int64_t, int64_t, float, float, float*, float*, float*,
+                   cudaStream_t);
+int launch_gather(bool, const float*, const int64_t*, float*, int64_t, int64_t, int64_t, cudaStream_t);
+
+// Taps whose magnitude is below 2^-30 of the largest tap are dropped at the two ends: their total
+// contribution (<= k * 2^-30 * max|w| * max|x|) is far below half an fp32 ulp of the result.
+static int make_taps(const float* w, int k, bool flip, Taps* out) {
+  std::vector<float> v(w, w + k);
+  if (flip) for (int i = 0; i < k / 2; ++i) std::swap(v[i], v[k - 1 - i]);
+  float mx = 0.f;
+  for (float t : v) mx = std::fmax(mx, std::fabs(t));
+  int first = 0, last = k - 1;
+  const float thr = mx * 9.313225746154785e-10f;  // 2^-30
+  while (first < last && std::fabs(v[first]) <= thr) ++first;
+  while (last > first && std::fabs(v[last]) <= thr) --last;
+  int lo = first - k / 2;                       // offset of the first kept tap
+  int lo4 = (int)std::floor(lo / 4.0) * 4;      // rows kernel wants lo % 4 == 0
+  int front = lo - lo4;
+  int kept = last - first + 1;
+  int kk = (front + kept + 7) & ~7;
+  if (kk > PSX_MAX_TAPS + 9) return fail(PSX_ERR_INVALID, "too many taps");
+  std::memset(out, 0, sizeof(Taps));
+  out->k = kk;
+  out->lo = lo4;
+  for (int i = 0; i < kept; ++i) out->w[front + i] = v[first + i];
+  return PSX_OK;
+}
+
+}  // namespace psx
+
+using namespace psx;
+
+extern "C" {
+
+PSX_API int psx_abi_version(void) { return PSX_ABI_VERSION; }
+PSX_API const char* psx_last_error(void) { return g_last_error.c_str(); }
+
+static psx_op* new_op(int kind) {
+  psx_op* op = new (std::nothrow) psx_op();
+  if (op) {
+    std::memset(op, 0, sizeof(psx_op));
+    op->kind = kind;
+  }
+  return op;
+}
+
+PSX_API int psx_op_create_identity(int64_t n, psx_op** out) {
+  PSX_REQUIRE(out && n > 0, "psx_op_create_identity: n must be positive");
+  psx_op* op = new_op(PSX_OP_IDENTITY);
+  if (!op) return fail(PSX_ERR_INVALID, "out of host memory");
+  op->n = op->n_y = n;
+  op->err_parts = pointwise_parts(n);
+  *out = op;
+  return PSX_OK;
+}
+
+PSX_API int psx_op_create_mask(int64_t n, const uint8_t* d_keep, psx_op** out) {
+  PSX_REQUIRE(out && n > 0 && d_keep, "psx_op_create_mask: need n > 0 and a device keep-mask");
+  psx_op* op = new_op(PSX_OP_MASK);
+  if (!op) return fail(PSX_ERR_INVALID, "out of host memory");
+  op->n = op->n_y = n;
+  op->d_keep = d_keep;
+  op->err_parts = pointwise_parts(n);
+  *out = op;
+  return PSX_OK;
+}
+
+PSX_API int psx_op_create_box(int C, int H, int W, int factor, psx_op** out) {
+  PSX_REQUIRE(out && C > 0 && H > 0 && W > 0 && factor > 0, "psx_op_create_box: bad shape");
+  PSX_REQUIRE(H % factor == 0 && W % factor == 0, "psx_op_create_box: H and W must be multiples of factor");
+  psx_op* op = new_op(PSX_OP_BOX);
+  if (!op) return fail(PSX_ERR_INVALID, "out of host memory");
+  op->C = C; op->H = H; op->W = W; op->factor = factor;
+  op->n = (int64_t)C * H * W;
+  op->n_y = op->n / ((int64_t)factor * factor);
+  op->err_parts = box_parts(op->n_y);
+  *out = op;
+  return PSX_OK;
+}
+
+PSX_API int psx_op_create_sepblur(int C, int H, int W, const float* h_taps_h, int kh, const float* h_taps_v,
+                          int kv, psx_op** out) {
+  PSX_REQUIRE(out && C > 0 && H > 0 && W > 0, "psx_op_create_sepblur: bad shape");
+  PSX_REQUIRE(h_taps_h && h_taps_v, "psx_op_create_sepblur: null taps");
+  PSX_REQUIRE(kh > 0 && kv > 0 && (kh & 1) && (kv & 1) && kh <= PSX_MAX_TAPS && kv <= PSX_MAX_TAPS,
+              "psx_op_create_sepblur: tap counts must be odd and <= PSX_MAX_TAPS");
+  psx_op* op = new_op(PSX_OP_SEPBLUR);
+  if (!op) return fail(PSX_ERR_INVALID, "out of host memory");
+  op->C = C; op->H = H; op->W = W;
+  op->n = op->n_y = (int64_t)C * H * W;
+  int rc = make_taps(h_taps_h, kh, false, &op->fh);
+  if (!rc) rc = make_taps(h_taps_v, kv, false, &op->fv);
+  if (!rc) rc = make_taps(h_taps_h, kh, true, &op->ah);
+  if (!rc) rc = make_taps(h_taps_v, kv, true, &op->av);
+  if (!rc) rc = sepblur_plan(op);
+  if (rc) { delete op; return rc; }
+  *out = op;
+  return PSX_OK;
+}
+
+PSX_API int psx_op_create_conv2d(int C, int H, int W, const float* h_kernel, int kh, int kw, psx_op** out) {
+  PSX_REQUIRE(out && C > 0 && H > 0 && W > 0 && h_kernel, "psx_op_create_conv2d: bad arguments");
+  PSX_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && kh <= PSX_MAX_TAPS && kw <= PSX_MAX_TAPS,
+              "psx_op_create_conv2d: kernel sizes must be odd and <= PSX_MAX_TAPS");
+  std::vector<Tap2D> taps;
+  for (int jy = 0; jy < kh; ++jy)
+    for (int jx = 0; jx < kw; ++jx) {
+      const float w = h_kernel[jy * kw + jx];
+      if (w != 0.f) taps.push_back(Tap2D{(int16_t)(jy - kh / 2), (int16_t)(jx - kw / 2), w});
+    }
+  PSX_REQUIRE(!taps.empty(), "psx_op_create_conv2d: kernel is all zeros");
+  psx_op* op = new_op(PSX_OP_CONV2D);
+  if (!op) return fail(PSX_ERR_INVALID, "out of host memory");
+  op->C = C; op->H = H; op->W = W; op->kh = kh; op->kw = kw;
+  op->n = op->n_y = (int64_t)C * H * W;
+  op->n_taps2d = (int)taps.size();
+  int rc = check_cuda(cudaMalloc(&op->d_taps_f, taps.size() * sizeof(Tap2D)), "cudaMalloc taps");
+  if (!rc)
+    rc = check_cuda(cudaMemcpy(op->d_taps_f, taps.data(), taps.size() * sizeof(Tap2D), cudaMemcpyHostToDevice),
+                    "copy taps");
+  if (rc) { if (op->d_taps_f) cudaFree(op->d_taps_f); delete op; return rc; }
+  op->err_parts = conv2d_err_parts(op);
+  *out = op;
+  return PSX_OK;
+}
+
+PSX_API int psx_op_destroy(psx_op* op) {
+  if (!op) return PSX_OK;
+  if (op->d_taps_f) cudaFree(op->d_taps_f);
+  delete op;
+  return PSX_OK;
+}
+
+PSX_API int psx_op_kind(const psx_op* op) { return op ? op->kind : -1; }
+PSX_API int64_t psx_op_x_numel(const psx_op* op) { return op ? op->n : 0; }
+PSX_API int64_t psx_op_y_numel(const psx_op* op) { return op ? op->n_y : 0; }
+PSX_API int psx_op_err_parts(const psx_op* op) { return op ? op->err_parts : 0; }
+
+PSX_API size_t psx_op_workspace_bytes(const psx_op* op, int64_t L) {
+  if (!op || L <= 0) return 0;
+  if (op->kind == PSX_OP_SEPBLUR || op->kind == PSX_OP_CONV2D) return (size_t)L * op->n * sizeof(float);
+  return 0;
+}
+
+static int check_ws(const psx_op* op, int64_t L, void* ws, size_t bytes) {
+  const size_t need = psx_op_workspace_bytes(op, L);
+  if (need && (!ws || bytes < need)) return fail(PSX_ERR_INVALID, "workspace too small (see psx_op_workspace_bytes)");
+  return PSX_OK;
+}
+
+PSX_API int psx_op_apply(const psx_op* op, const float* d_x, float* d_y, int64_t L, void* ws, size_t ws_bytes,
+                 void* stream) {
+  PSX_REQUIRE(op && d_x && d_y && L > 0, "psx_op_apply: null argument or L <= 0");
+  if (int rc = check_ws(op, L, ws, ws_bytes)) return rc;
+  return launch_op(op, false, d_x, d_y, L, (float*)ws, (cudaStream_t)stream);
+}
+
+PSX_API int psx_op_adjoint(const psx_op* op, const float* d_y, float* d_x, int64_t L, void* ws, size_t ws_bytes,
+                   void* stream) {
+  PSX_REQUIRE(op && d_x && d_y && L > 0, "psx_op_adjoint: null argument or L <= 0");
+  if (int rc = check_ws(op, L, ws, ws_bytes)) return rc;
+  return launch_op(op, true, d_y, d_x, L, (float*)ws, (cudaStream_t)stream);
+}
+
+PSX_API int psx_gather(const float* d_in, const int64_t* d_idx, float* d_out, int64_t L, int64_t n, int64_t m,
+                       void* stream) {
+  PSX_REQUIRE(d_in && d_out && (d_idx || m == 0), "psx_gather: null pointer");
+  PSX_REQUIRE(L > 0 && n > 0 && m >= 0 && m <= n, "psx_gather: bad sizes");
+  return launch_gather(false, d_in, d_idx, d_out, L, n, m, (cudaStream_t)stream);
+}
+
+PSX_API int psx_scatter(const float* d_in, const int64_t* d_idx, float* d_out, int64_t L, int64_t n, int64_t m,
+                        void* stream) {
+  PSX_REQUIRE(d_out && ((d_in && d_idx) || m == 0), "psx_scatter: null pointer");
+  PSX_REQUIRE(L > 0 && n > 0 && m >= 0 && m <= n, "psx_scatter: bad sizes");
+  return launch_gather(true, d_in, d_idx, d_out, L, n, m, (cudaStream_t)stream);
+}
+
+PSX_API int psx_dps_pre(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y, int64_t L,
+                int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight, float* d_cot,
+                float* d_err_part, float* d_x0_out, void* ws, size_t ws_bytes, void* stream) {
+  PSX_REQUIRE(op && d_x_t && d_eps && d_y && d_cot && d_err_part, "psx_dps_pre: null pointer");
+  PSX_REQUIRE(L > 0 && L <= 65535, "psx_dps_pre: L must be in [1, 65535]");
+  PSX_REQUIRE(obs_repeat > 0, "psx_dps_pre: obs_repeat must be positive");
+  PSX_REQUIRE(sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(sqrt_1m_acp) && std::isfinite(lik_weight),
+              "psx_dps_pre: non-finite or non-positive schedule scalar");
+  if (int rc = check_ws(op, L, ws, ws_bytes)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (op->kind) {
+    case PSX_OP_IDENTITY:
+    case PSX_OP_MASK:
+      return launch_pre_pointwise(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight,
+                                  d_cot, d_err_part, d_x0_out, st);
+    case PSX_OP_BOX:
+      return launch_pre_box(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight, d_cot,
+                            d_err_part, d_x0_out, st);
+    case PSX_OP_SEPBLUR:
+      return launch_pre_sepblur(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight,
+                                d_cot, d_err_part, d_x0_out, (float*)ws, st);
+    case PSX_OP_CONV2D:
+      return launch_pre_conv2d(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight,
+                               d_cot, d_err_part, d_x0_out, (float*)ws, st);
+  }
+  return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: unknown operator kind");
+}
+
+PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
+                 const float* d_z, const float* d_err_part, int err_parts, int64_t L, int64_t n,
+                 float sqrt_acp, float sqrt_1m_acp, float c_ell, float c_s, float std_, float gamma,
+                 float* d_x_next, float* d_err_out, void* stream) {
+  PSX_REQUIRE(d_x_t && d_eps && d_cot && d_vjp && d_err_part && d_x_next, "psx_dps_post: null pointer");
+  PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts > 0, "psx_dps_post: bad sizes");
+  PSX_REQUIRE(d_z || std_ == 0.f, "psx_dps_post: d_z may be NULL only when std == 0");
+  PSX_REQUIRE(sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(c_ell) && std::isfinite(c_s) &&
+                  std::isfinite(std_) && std::isfinite(gamma),
+              "psx_dps_post: non-finite scalar");
+  return launch_post(d_x_t, d_eps, d_cot, d_vjp, std_ == 0.f ? nullptr : d_z, d_err_part, err_parts, L, n,
+                     sqrt_acp, sqrt_1m_acp, c_ell, c_s, std_, gamma, d_x_next, d_err_out,
+                     (cudaStream_t)stream);
+}
+
+PSX_API int psx_tweedie(const float* d_x_t, const float* d_eps, int64_t L, int64_t n, float sqrt_acp,
+                float sqrt_1m_acp, float* d_x0, float* d_sum, float* d_sumsq, void* stream) {
+  PSX_REQUIRE(d_x_t && d_eps && d_x0, "psx_tweedie: null pointer");
+  PSX_REQUIRE(L > 0 && n > 0, "psx_tweedie: bad sizes");
+  PSX_REQUIRE(sqrt_acp > 0.f && std::isfinite(sqrt_acp), "psx_tweedie: bad sqrt_acp");
+  return launch_tweedie(d_x_t, d_eps, L, n, sqrt_acp, sqrt_1m_acp, d_x0, d_sum, d_sumsq, (cudaStream_t)stream);
+}
+
+}  // extern "C"

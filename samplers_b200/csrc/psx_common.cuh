@@ -1,0 +1,132 @@
+// psx_common.cuh -- shared device helpers for libpsx (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "psx.h"
+
+namespace psx {
+
+constexpr int kThreads = 256;
+constexpr int kMaxParts = 64;  // upper bound on per-sample partial sums (pointwise kernels)
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int check_cuda(cudaError_t e, const char* what);
+
+#define PSX_REQUIRE(cond, msg) \
+  do {                         \
+    if (!(cond)) return ::psx::fail(PSX_ERR_INVALID, msg); \
+  } while (0)
+
+// ---------------------------------------------------------------- operator descriptor
+struct Taps {
+  int k;    // number of taps kept (after pruning), <= PSX_MAX_TAPS, padded to a multiple of 8 with zeros
+  int lo;   // offset of w[0]: out[p] = sum_i w[i] * in[p + lo + i]
+  float w[PSX_MAX_TAPS + 9];
+};
+
+struct Tap2D {
+  int16_t dy, dx;
+  float w;
+};
+
+}  // namespace psx
+
+struct psx_op {
+  int kind;
+  int64_t n, n_y;
+  int C, H, W;
+  int factor;                 // box
+  const uint8_t* d_keep;      // mask (caller-owned)
+  psx::Taps fh, fv, ah, av;   // separable blur: forward / adjoint taps (rows, cols)
+  psx::Tap2D* d_taps_f;       // conv2d: device tap lists (owned)
+  psx::Tap2D* d_taps_a;
+  int n_taps2d, kh, kw;
+  int err_parts;
+  int col_tc;                 // sepblur: column-strip width
+};
+
+namespace psx {
+
+// ---------------------------------------------------------------- memory access
+// Streaming 128-bit loads/stores: data is touched once per kernel, keep it out of L1.
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// ---------------------------------------------------------------- arithmetic with torch's roundings
+// networks/base.py:42-43 evaluates mul, sub, div as three separately rounded tensor ops;
+// the intrinsics stop nvcc from contracting them into an FMA / a reciprocal multiply.
+__device__ __forceinline__ float tweedie(float x, float e, float s1, float sa) {
+  return __fdiv_rn(__fsub_rn(x, __fmul_rn(s1, e)), sa);
+}
+
+// ---------------------------------------------------------------- reductions (fixed order => deterministic)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the CTA; result valid in thread 0.  `red` must hold >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = 0.f;
+  if (wid == 0) {
+    t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  return t;
+}
+
+// Per-sample |r|^2 from the partial sums K1 left behind; every thread gets the value.
+__device__ __forceinline__ float sum_parts(const float* part, int parts, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (wid == 0) {
+    float t = 0.f;
+    for (int i = lane; i < parts; i += 32) t += part[i];
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// launchers implemented in the .cu files ------------------------------------------------
+int launch_pre_pointwise(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
+                         int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                         float* x0_out, cudaStream_t st);
+int launch_pre_box(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
+                   int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                   float* x0_out, cudaStream_t st);
+int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
+                       int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                       float* x0_out, float* ws, cudaStream_t st);
+int launch_pre_conv2d(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
+                      int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                      float* x0_out, float* ws, cudaStream_t st);
+int launch_op(const psx_op* op, bool adjoint, const float* in, float* out, int64_t L, float* ws,
+              cudaStream_t st);
+int sepblur_plan(psx_op* op);
+int conv2d_err_parts(const psx_op* op);
+
+}  // namespace psx

@@ -1,0 +1,566 @@
+// psx_pointwise.cu -- HBM-bound kernels of the DPS step (sm_100a):
+//   K1 for identity / inpainting-mask / box super-resolution operators,
+//   K2 (bridge update + guidance + injected noise), the final Tweedie estimate,
+//   and the stand-alone forward / adjoint of those operators.
+// Every kernel streams each tensor exactly once with 128-bit accesses.
+#include "psx_common.cuh"
+
+namespace psx {
+
+// =========================================================================== K1: identity / mask
+// grid = (parts, L); CTA (p, l) owns the float4 range [p*chunk, (p+1)*chunk) of sample l.
+template <bool MASK, bool WRITE_X0>
+__global__ void __launch_bounds__(kThreads)
+k1_pointwise_v4(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
+                const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part,
+                float* __restrict__ x0_out, int64_t n, int64_t chunk4, int64_t obs_repeat, float sa,
+                float s1, float w) {
+  __shared__ float red[32];
+  const int64_t l = blockIdx.y;
+  const int64_t n4 = n >> 2;
+  const int64_t beg = (int64_t)blockIdx.x * chunk4;
+  const int64_t end = min(beg + chunk4, n4);
+  const float* xs = x + l * n;
+  const float* es = eps + l * n;
+  const float* ys = y + (l / obs_repeat) * n;
+  float* cs = cot + l * n;
+  float acc = 0.f;
+
+  constexpr int U = 4;
+  for (int64_t base = beg + threadIdx.x; base < end; base += (int64_t)kThreads * U) {
+    float4 xv[U], ev[U], yv[U];
+    uchar4 kv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * kThreads;
+      if (i < end) {
+        xv[u] = ld_stream4(xs + 4 * i);
+        ev[u] = ld_stream4(es + 4 * i);
+        yv[u] = __ldg(reinterpret_cast<const float4*>(ys) + i);
+        if (MASK) kv[u] = __ldg(reinterpret_cast<const uchar4*>(keep) + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * kThreads;
+      if (i < end) {
+        float4 x0, r, d;
+        x0.x = tweedie(xv[u].x, ev[u].x, s1, sa);
+        x0.y = tweedie(xv[u].y, ev[u].y, s1, sa);
+        x0.z = tweedie(xv[u].z, ev[u].z, s1, sa);
+        x0.w = tweedie(xv[u].w, ev[u].w, s1, sa);
+        r.x = __fsub_rn(yv[u].x, x0.x);
+        r.y = __fsub_rn(yv[u].y, x0.y);
+        r.z = __fsub_rn(yv[u].z, x0.z);
+        r.w = __fsub_rn(yv[u].w, x0.w);
+        if (MASK) {
+          r.x = kv[u].x ? r.x : 0.f;
+          r.y = kv[u].y ? r.y : 0.f;
+          r.z = kv[u].z ? r.z : 0.f;
+          r.w = kv[u].w ? r.w : 0.f;
+        }
+        acc = fmaf(r.x, r.x, acc);
+        acc = fmaf(r.y, r.y, acc);
+        acc = fmaf(r.z, r.z, acc);
+        acc = fmaf(r.w, r.w, acc);
+        d.x = __fdiv_rn(__fmul_rn(w, r.x), sa);
+        d.y = __fdiv_rn(__fmul_rn(w, r.y), sa);
+        d.z = __fdiv_rn(__fmul_rn(w, r.z), sa);
+        d.w = __fdiv_rn(__fmul_rn(w, r.w), sa);
+        st_stream4(cs + 4 * i, d);
+        if (WRITE_X0) st_stream4(x0_out + l * n + 4 * i, x0);
+      }
+    }
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) err_part[l * gridDim.x + blockIdx.x] = tot;
+}
+
+// scalar fallback for n % 4 != 0 (tiny / odd shapes)
+template <bool MASK>
+__global__ void __launch_bounds__(kThreads)
+k1_pointwise_s(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
+               const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part,
+               float* __restrict__ x0_out, int64_t n, int64_t chunk, int64_t obs_repeat, float sa,
+               float s1, float w) {
+  __shared__ float red[32];
+  const int64_t l = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, n);
+  float acc = 0.f;
+  for (int64_t i = beg + threadIdx.x; i < end; i += kThreads) {
+    const float x0 = tweedie(x[l * n + i], eps[l * n + i], s1, sa);
+    float r = __fsub_rn(y[(l / obs_repeat) * n + i], x0);
+    if (MASK) r = keep[i] ? r : 0.f;
+    acc = fmaf(r, r, acc);
+    cot[l * n + i] = __fdiv_rn(__fmul_rn(w, r), sa);
+    if (x0_out) x0_out[l * n + i] = x0;
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) err_part[l * gridDim.x + blockIdx.x] = tot;
+}
+
+int pointwise_parts(int64_t n) {
+  const int64_t units = (n % 4 == 0) ? n / 4 : n;
+  int parts = ceil_div(units, (int64_t)kThreads * 4);
+  return parts < 1 ? 1 : (parts > kMaxParts ? kMaxParts : parts);
+}
+
+int launch_pre_pointwise(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
+                         int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                         float* x0_out, cudaStream_t st) {
+  const int64_t n = op->n;
+  const int parts = op->err_parts;
+  const bool mask = op->kind == PSX_OP_MASK;
+  dim3 grid(parts, (unsigned)L);
+  if (n % 4 == 0) {
+    const int64_t chunk4 = (n / 4 + parts - 1) / parts;
+#define PSX_LAUNCH(M, X)                                                                             \
+  k1_pointwise_v4<M, X><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, x0_out, n, \
+                                                   chunk4, obs_repeat, sa, s1, w)
+    if (mask) {
+      if (x0_out) PSX_LAUNCH(true, true); else PSX_LAUNCH(true, false);
+    } else {
+      if (x0_out) PSX_LAUNCH(false, true); else PSX_LAUNCH(false, false);
+    }
+#undef PSX_LAUNCH
+  } else {
+    const int64_t chunk = (n + parts - 1) / parts;
+    if (mask)
+      k1_pointwise_s<true><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, x0_out, n,
+                                                      chunk, obs_repeat, sa, s1, w);
+    else
+      k1_pointwise_s<false><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, x0_out, n,
+                                                       chunk, obs_repeat, sa, s1, w);
+  }
+  return check_cuda(cudaGetLastError(), "k1_pointwise launch");
+}
+
+// =========================================================================== K1: box super-resolution
+// One thread per coarse pixel: F x F fine pixels of x_t / eps in, one y in, F x F cotangents out.
+// A warp covers 32 consecutive coarse pixels of a row => 32*F contiguous floats per fine row.
+template <int F>
+struct RowVec;
+template <> struct RowVec<2> { using T = float2; };
+template <> struct RowVec<4> { using T = float4; };
+
+template <int F>
+__global__ void __launch_bounds__(kThreads)
+k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
+       float* __restrict__ cot, float* __restrict__ err_part, float* __restrict__ x0_out, int planes,
+       int H, int W, int64_t chunk, int64_t obs_repeat, float sa, float s1, float w) {
+  __shared__ float red[32];
+  const int Hc = H / F, Wc = W / F;
+  const int64_t n = (int64_t)planes * H * W, ny = (int64_t)planes * Hc * Wc;
+  const int64_t l = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, ny);
+  const float inv = 1.0f / (float)(F * F);
+  float acc = 0.f;
+  for (int64_t q = beg + threadIdx.x; q < end; q += kThreads) {
+    const int cx = (int)(q % Wc);
+    const int64_t t = q / Wc;
+    const int cy = (int)(t % Hc);
+    const int pl = (int)(t / Hc);
+    const int64_t off = l * n + ((int64_t)pl * H + (int64_t)cy * F) * W + (int64_t)cx * F;
+    float x0[F][F];
+    float s = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < F; ++dy) {
+      float xv[F], ev[F];
+      if constexpr (F == 4) {
+        float4 a = ld_stream4(x + off + (int64_t)dy * W), b = ld_stream4(eps + off + (int64_t)dy * W);
+        xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+        ev[0] = b.x; ev[1] = b.y; ev[2] = b.z; ev[3] = b.w;
+      } else if constexpr (F == 2) {
+        float2 a = __ldg(reinterpret_cast<const float2*>(x + off + (int64_t)dy * W));
+        float2 b = __ldg(reinterpret_cast<const float2*>(eps + off + (int64_t)dy * W));
+        xv[0] = a.x; xv[1] = a.y; ev[0] = b.x; ev[1] = b.y;
+      } else {
+#pragma unroll
+        for (int dx = 0; dx < F; ++dx) {
+          xv[dx] = __ldg(x + off + (int64_t)dy * W + dx);
+          ev[dx] = __ldg(eps + off + (int64_t)dy * W + dx);
+        }
+      }
+#pragma unroll
+      for (int dx = 0; dx < F; ++dx) {
+        x0[dy][dx] = tweedie(xv[dx], ev[dx], s1, sa);
+        s = __fadd_rn(s, x0[dy][dx]);
+      }
+    }
+    const float avg = __fmul_rn(s, inv);  // F*F is a power of two for F = 2, 4, 8: exact scaling
+    const float r = __fsub_rn(__ldg(y + (l / obs_repeat) * ny + q), avg);
+    acc = fmaf(r, r, acc);
+    const float d = __fdiv_rn(__fmul_rn(w, __fmul_rn(r, inv)), sa);
+#pragma unroll
+    for (int dy = 0; dy < F; ++dy) {
+      if constexpr (F == 4) {
+        st_stream4(cot + off + (int64_t)dy * W, make_float4(d, d, d, d));
+        if (x0_out) st_stream4(x0_out + off + (int64_t)dy * W,
+                               make_float4(x0[dy][0], x0[dy][1], x0[dy][2], x0[dy][3]));
+      } else {
+#pragma unroll
+        for (int dx = 0; dx < F; ++dx) {
+          cot[off + (int64_t)dy * W + dx] = d;
+          if (x0_out) x0_out[off + (int64_t)dy * W + dx] = x0[dy][dx];
+        }
+      }
+    }
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) err_part[l * gridDim.x + blockIdx.x] = tot;
+}
+
+// generic factor (not a power of two): division by F*F as the oracle does
+__global__ void __launch_bounds__(kThreads)
+k1_box_any(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
+           float* __restrict__ cot, float* __restrict__ err_part, float* __restrict__ x0_out, int planes,
+           int H, int W, int F, int64_t chunk, int64_t obs_repeat, float sa, float s1, float w) {
+  __shared__ float red[32];
+  const int Hc = H / F, Wc = W / F;
+  const int64_t n = (int64_t)planes * H * W, ny = (int64_t)planes * Hc * Wc;
+  const int64_t l = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, ny);
+  const float ff = (float)(F * F);
+  float acc = 0.f;
+  for (int64_t q = beg + threadIdx.x; q < end; q += kThreads) {
+    const int cx = (int)(q % Wc);
+    const int64_t t = q / Wc;
+    const int cy = (int)(t % Hc);
+    const int pl = (int)(t / Hc);
+    const int64_t off = l * n + ((int64_t)pl * H + (int64_t)cy * F) * W + (int64_t)cx * F;
+    float s = 0.f;
+    for (int dy = 0; dy < F; ++dy)
+      for (int dx = 0; dx < F; ++dx) {
+        const float v = tweedie(x[off + (int64_t)dy * W + dx], eps[off + (int64_t)dy * W + dx], s1, sa);
+        if (x0_out) x0_out[off + (int64_t)dy * W + dx] = v;
+        s = __fadd_rn(s, v);
+      }
+    const float r = __fsub_rn(y[(l / obs_repeat) * ny + q], __fdiv_rn(s, ff));
+    acc = fmaf(r, r, acc);
+    const float d = __fdiv_rn(__fmul_rn(w, __fdiv_rn(r, ff)), sa);
+    for (int dy = 0; dy < F; ++dy)
+      for (int dx = 0; dx < F; ++dx) cot[off + (int64_t)dy * W + dx] = d;
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) err_part[l * gridDim.x + blockIdx.x] = tot;
+}
+
+int box_parts(int64_t ny) {
+  int parts = ceil_div(ny, (int64_t)kThreads);
+  return parts < 1 ? 1 : (parts > kMaxParts ? kMaxParts : parts);
+}
+
+int launch_pre_box(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
+                   int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                   float* x0_out, cudaStream_t st) {
+  const int parts = op->err_parts;
+  const int64_t chunk = (op->n_y + parts - 1) / parts;
+  dim3 grid(parts, (unsigned)L);
+  const int F = op->factor;
+  if (F == 4 && op->W % 4 == 0)
+    k1_box<4><<<grid, kThreads, 0, st>>>(x, eps, y, cot, err_part, x0_out, op->C, op->H, op->W, chunk,
+                                         obs_repeat, sa, s1, w);
+  else if (F == 2)
+    k1_box<2><<<grid, kThreads, 0, st>>>(x, eps, y, cot, err_part, x0_out, op->C, op->H, op->W, chunk,
+                                         obs_repeat, sa, s1, w);
+  else if (F == 8)
+    k1_box<8><<<grid, kThreads, 0, st>>>(x, eps, y, cot, err_part, x0_out, op->C, op->H, op->W, chunk,
+                                         obs_repeat, sa, s1, w);
+  else
+    k1_box_any<<<grid, kThreads, 0, st>>>(x, eps, y, cot, err_part, x0_out, op->C, op->H, op->W, F,
+                                          chunk, obs_repeat, sa, s1, w);
+  return check_cuda(cudaGetLastError(), "k1_box launch");
+}
+
+// =========================================================================== K2
+// x_next = c_ell*x_t + c_s*x0 + std*z + gamma/(|r|+1e-9) * (cot - s1*vjp)
+// Rounding order follows bridge_kernels.py:41 (mean), :59 (+ std*z), dps.py:121-122 (+ scale*grad).
+template <bool HAS_Z>
+__global__ void __launch_bounds__(kThreads)
+k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ cot,
+           const float* __restrict__ vjp, const float* __restrict__ z, const float* __restrict__ err_part,
+           int err_parts, int64_t n, int64_t chunk4, float sa, float s1, float c_ell, float c_s,
+           float sd, float gamma, float* __restrict__ x_next, float* __restrict__ err_out) {
+  __shared__ float red[32];
+  const int64_t l = blockIdx.y;
+  const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
+  const float err = sqrtf(e2);
+  const float scale = __fdiv_rn(gamma, __fadd_rn(err, 1e-9f));
+  if (err_out && blockIdx.x == 0 && threadIdx.x == 0) err_out[l] = err;
+
+  const int64_t n4 = n >> 2;
+  const int64_t beg = (int64_t)blockIdx.x * chunk4, end = min(beg + chunk4, n4);
+  const int64_t so = l * n;
+  constexpr int U = 2;
+  for (int64_t base = beg + threadIdx.x; base < end; base += (int64_t)kThreads * U) {
+    float4 xv[U], ev[U], dv[U], vv[U], zv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * kThreads;
+      if (i < end) {
+        xv[u] = ld_stream4(x + so + 4 * i);
+        ev[u] = ld_stream4(eps + so + 4 * i);
+        dv[u] = ld_stream4(cot + so + 4 * i);
+        vv[u] = ld_stream4(vjp + so + 4 * i);
+        if (HAS_Z) zv[u] = ld_stream4(z + so + 4 * i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * kThreads;
+      if (i < end) {
+        float4 o;
+#define PSX_K2_LANE(c)                                                                         \
+  {                                                                                            \
+    const float x0 = tweedie(xv[u].c, ev[u].c, s1, sa);                                        \
+    float m = __fadd_rn(__fmul_rn(c_ell, xv[u].c), __fmul_rn(c_s, x0));                        \
+    if (HAS_Z) m = __fadd_rn(m, __fmul_rn(sd, zv[u].c));                                       \
+    const float g = __fadd_rn(dv[u].c, __fmul_rn(-s1, vv[u].c));                               \
+    o.c = __fadd_rn(m, __fmul_rn(scale, g));                                                   \
+  }
+        PSX_K2_LANE(x) PSX_K2_LANE(y) PSX_K2_LANE(z) PSX_K2_LANE(w)
+#undef PSX_K2_LANE
+        st_stream4(x_next + so + 4 * i, o);
+      }
+    }
+  }
+}
+
+template <bool HAS_Z>
+__global__ void __launch_bounds__(kThreads)
+k2_post_s(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ cot,
+          const float* __restrict__ vjp, const float* __restrict__ z, const float* __restrict__ err_part,
+          int err_parts, int64_t n, int64_t chunk, float sa, float s1, float c_ell, float c_s, float sd,
+          float gamma, float* __restrict__ x_next, float* __restrict__ err_out) {
+  __shared__ float red[32];
+  const int64_t l = blockIdx.y;
+  const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
+  const float err = sqrtf(e2);
+  const float scale = __fdiv_rn(gamma, __fadd_rn(err, 1e-9f));
+  if (err_out && blockIdx.x == 0 && threadIdx.x == 0) err_out[l] = err;
+  const int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, n);
+  for (int64_t i = beg + threadIdx.x; i < end; i += kThreads) {
+    const int64_t j = l * n + i;
+    const float x0 = tweedie(x[j], eps[j], s1, sa);
+    float m = __fadd_rn(__fmul_rn(c_ell, x[j]), __fmul_rn(c_s, x0));
+    if (HAS_Z) m = __fadd_rn(m, __fmul_rn(sd, z[j]));
+    const float g = __fadd_rn(cot[j], __fmul_rn(-s1, vjp[j]));
+    x_next[j] = __fadd_rn(m, __fmul_rn(scale, g));
+  }
+}
+
+int launch_post(const float* x, const float* eps, const float* cot, const float* vjp, const float* z,
+                const float* err_part, int err_parts, int64_t L, int64_t n, float sa, float s1,
+                float c_ell, float c_s, float sd, float gamma, float* x_next, float* err_out,
+                cudaStream_t st) {
+  const bool has_z = z != nullptr;
+  if (n % 4 == 0) {
+    int parts = ceil_div(n / 4, (int64_t)kThreads * 4);
+    parts = parts < 1 ? 1 : parts;
+    const int64_t chunk4 = (n / 4 + parts - 1) / parts;
+    dim3 grid(parts, (unsigned)L);
+    if (has_z)
+      k2_post_v4<true><<<grid, kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, chunk4, sa,
+                                                  s1, c_ell, c_s, sd, gamma, x_next, err_out);
+    else
+      k2_post_v4<false><<<grid, kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, chunk4,
+                                                   sa, s1, c_ell, c_s, sd, gamma, x_next, err_out);
+  } else {
+    int parts = ceil_div(n, (int64_t)kThreads * 4);
+    parts = parts < 1 ? 1 : parts;
+    const int64_t chunk = (n + parts - 1) / parts;
+    dim3 grid(parts, (unsigned)L);
+    if (has_z)
+      k2_post_s<true><<<grid, kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, chunk, sa,
+                                                 s1, c_ell, c_s, sd, gamma, x_next, err_out);
+    else
+      k2_post_s<false><<<grid, kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, chunk, sa,
+                                                  s1, c_ell, c_s, sd, gamma, x_next, err_out);
+  }
+  return check_cuda(cudaGetLastError(), "k2_post launch");
+}
+
+// =========================================================================== final Tweedie (+ posterior moments)
+// One thread per pixel (quad), looping over the L local samples: x0 goes to the gather slot, the
+// per-pixel sum / sum of squares are the all-reduce send buffers for the posterior mean / variance.
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+k_tweedie_final(const float* __restrict__ x, const float* __restrict__ eps, int64_t L, int64_t n, float sa,
+                float s1, float* __restrict__ x0, float* __restrict__ sum, float* __restrict__ sumsq) {
+  const int64_t nv = n / V;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float s[V], q[V];
+#pragma unroll
+    for (int c = 0; c < V; ++c) s[c] = q[c] = 0.f;
+    for (int64_t l = 0; l < L; ++l) {
+      float xv[V], ev[V], o[V];
+      if constexpr (V == 4) {
+        float4 a = ld_stream4(x + l * n + 4 * i), b = ld_stream4(eps + l * n + 4 * i);
+        xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+        ev[0] = b.x; ev[1] = b.y; ev[2] = b.z; ev[3] = b.w;
+      } else {
+        xv[0] = x[l * n + i];
+        ev[0] = eps[l * n + i];
+      }
+#pragma unroll
+      for (int c = 0; c < V; ++c) {
+        o[c] = tweedie(xv[c], ev[c], s1, sa);
+        s[c] += o[c];
+        q[c] = fmaf(o[c], o[c], q[c]);
+      }
+      if constexpr (V == 4) st_stream4(x0 + l * n + 4 * i, make_float4(o[0], o[1], o[2], o[3]));
+      else x0[l * n + i] = o[0];
+    }
+    if (sum) {
+      if constexpr (V == 4) st_stream4(sum + 4 * i, make_float4(s[0], s[1], s[2], s[3]));
+      else sum[i] = s[0];
+    }
+    if (sumsq) {
+      if constexpr (V == 4) st_stream4(sumsq + 4 * i, make_float4(q[0], q[1], q[2], q[3]));
+      else sumsq[i] = q[0];
+    }
+  }
+}
+
+// When no moments are requested parallelise over samples as well (pure elementwise).
+__global__ void __launch_bounds__(kThreads)
+k_tweedie_flat(const float* __restrict__ x, const float* __restrict__ eps, int64_t total, float sa, float s1,
+               float* __restrict__ x0) {
+  const int64_t t4 = total >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = ld_stream4(x + 4 * i), b = ld_stream4(eps + 4 * i), o;
+    o.x = tweedie(a.x, b.x, s1, sa); o.y = tweedie(a.y, b.y, s1, sa);
+    o.z = tweedie(a.z, b.z, s1, sa); o.w = tweedie(a.w, b.w, s1, sa);
+    st_stream4(x0 + 4 * i, o);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (t4 << 2) + threadIdx.x; i < total; i += blockDim.x) x0[i] = tweedie(x[i], eps[i], s1, sa);
+}
+
+int launch_tweedie(const float* x, const float* eps, int64_t L, int64_t n, float sa, float s1, float* x0,
+                   float* sum, float* sumsq, cudaStream_t st) {
+  if (!sum && !sumsq) {
+    const int64_t total = L * n;
+    int blocks = ceil_div(total / 4 + 1, kThreads);
+    blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
+    k_tweedie_flat<<<blocks, kThreads, 0, st>>>(x, eps, total, sa, s1, x0);
+  } else if (n % 4 == 0) {
+    int blocks = ceil_div(n / 4, kThreads);
+    k_tweedie_final<4><<<blocks, kThreads, 0, st>>>(x, eps, L, n, sa, s1, x0, sum, sumsq);
+  } else {
+    int blocks = ceil_div(n, kThreads);
+    k_tweedie_final<1><<<blocks, kThreads, 0, st>>>(x, eps, L, n, sa, s1, x0, sum, sumsq);
+  }
+  return check_cuda(cudaGetLastError(), "tweedie launch");
+}
+
+// =========================================================================== stand-alone operators
+__global__ void __launch_bounds__(kThreads)
+k_mask_apply(const float* __restrict__ in, const uint8_t* __restrict__ keep, float* __restrict__ out,
+             int64_t n, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = keep[i % n] ? in[i] : 0.f;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_box_apply(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W, int F,
+            int64_t total_y) {
+  const int Hc = H / F, Wc = W / F;
+  const bool pow2 = (F & (F - 1)) == 0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_y;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(q % Wc);
+    const int64_t t = q / Wc;
+    const int cy = (int)(t % Hc);
+    const int64_t pl = t / Hc;  // plane index including the sample
+    const int64_t off = (pl * H + (int64_t)cy * F) * W + (int64_t)cx * F;
+    float s = 0.f;
+    for (int dy = 0; dy < F; ++dy)
+      for (int dx = 0; dx < F; ++dx) s = __fadd_rn(s, x[off + (int64_t)dy * W + dx]);
+    y[q] = pow2 ? __fmul_rn(s, 1.0f / (float)(F * F)) : __fdiv_rn(s, (float)(F * F));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_box_adjoint(const float* __restrict__ y, float* __restrict__ x, int planes, int H, int W, int F,
+              int64_t total_x) {
+  const int Hc = H / F, Wc = W / F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_x;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int px = (int)(i % W);
+    const int64_t t = i / W;
+    const int py = (int)(t % H);
+    const int64_t pl = t / H;
+    x[i] = __fdiv_rn(y[(pl * Hc + py / F) * Wc + px / F], (float)(F * F));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_gather(const float* __restrict__ in, const int64_t* __restrict__ idx, float* __restrict__ out, int64_t n,
+         int64_t m, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = i / m, j = i - l * m;
+    out[i] = in[l * n + __ldg(idx + j)];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_scatter(const float* __restrict__ in, const int64_t* __restrict__ idx, float* __restrict__ out, int64_t n,
+          int64_t m, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = i / m, j = i - l * m;
+    out[l * n + __ldg(idx + j)] = in[i];
+  }
+}
+
+int launch_gather(bool scatter, const float* in, const int64_t* idx, float* out, int64_t L, int64_t n,
+                  int64_t m, cudaStream_t st) {
+  const int64_t total = L * m;
+  int blocks = ceil_div(total, kThreads);
+  blocks = blocks > 148 * 16 ? 148 * 16 : (blocks < 1 ? 1 : blocks);
+  if (scatter) {
+    int rc = check_cuda(cudaMemsetAsync(out, 0, (size_t)L * n * sizeof(float), st), "scatter memset");
+    if (rc) return rc;
+    if (total > 0) k_scatter<<<blocks, kThreads, 0, st>>>(in, idx, out, n, m, total);
+  } else if (total > 0) {
+    k_gather<<<blocks, kThreads, 0, st>>>(in, idx, out, n, m, total);
+  }
+  return check_cuda(cudaGetLastError(), "gather/scatter launch");
+}
+
+int launch_op_pointwise(const psx_op* op, bool adjoint, const float* in, float* out, int64_t L,
+                        cudaStream_t st) {
+  const int64_t total_x = L * op->n, total_y = L * op->n_y;
+  auto blocks_for = [](int64_t t) {
+    int b = ceil_div(t, kThreads);
+    return b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b);
+  };
+  switch (op->kind) {
+    case PSX_OP_IDENTITY:
+      if (in != out)
+        return check_cuda(cudaMemcpyAsync(out, in, total_x * sizeof(float), cudaMemcpyDeviceToDevice, st),
+                          "identity copy");
+      return PSX_OK;
+    case PSX_OP_MASK:
+      k_mask_apply<<<blocks_for(total_x), kThreads, 0, st>>>(in, op->d_keep, out, op->n, total_x);
+      break;
+    case PSX_OP_BOX:
+      if (!adjoint)
+        k_box_apply<<<blocks_for(total_y), kThreads, 0, st>>>(in, out, op->C, op->H, op->W, op->factor,
+                                                              total_y);
+      else
+        k_box_adjoint<<<blocks_for(total_x), kThreads, 0, st>>>(in, out, op->C, op->H, op->W, op->factor,
+                                                                total_x);
+      break;
+    default:
+      return fail(PSX_ERR_INVALID, "launch_op_pointwise: wrong operator kind");
+  }
+  return check_cuda(cudaGetLastError(), "operator launch");
+}
+
+}  // namespace psx

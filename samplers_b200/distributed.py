@@ -1,0 +1,85 @@
+"""Multi-GPU posterior sampling: independent samples sharded across ranks, one
+process per GPU, no collective inside the sampling loop (DPS samples are
+independent: per-sample norm dps.py:118-120, per-sample log-prob noise.py:79).
+NCCL is used only at the end:
+
+  * all_gather of every rank's final x0 samples,
+  * all_reduce(SUM) of the per-pixel [sum, sum of squares] -> posterior mean / variance.
+
+The final Tweedie kernel (psx_tweedie) writes each rank's samples straight into
+its slot of the gather buffer and produces the two moment buffers in the same pass.
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def shard_count(total: int, rank: int, world: int) -> tuple[int, int]:
+    """(start, count) of the contiguous block of ``total`` items owned by ``rank``."""
+    if total < 0 or world < 1 or not (0 <= rank < world):
+        raise ValueError("bad shard request")
+    base, rem = divmod(total, world)
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+@dataclasses.dataclass
+class PosteriorSummary:
+    samples: Tensor   # (R_total, *x_shape) -- all ranks' reconstructions, rank-major
+    mean: Tensor      # (*x_shape)
+    variance: Tensor  # (*x_shape), unbiased (divides by R_total - 1)
+
+
+def combine_posterior(local_slot: Tensor, gathered: Tensor, total: Tensor, total_sq: Tensor, counts: list[int],
+                      group=None) -> PosteriorSummary:
+    """Terminal exchange.  ``gathered`` is (world * max_count, n); this rank already wrote its samples into
+    rows [rank * max_count, rank * max_count + counts[rank]) (``local_slot`` is that view).  ``total`` /
+    ``total_sq`` are this rank's per-pixel sum and sum of squares and are reduced in place."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    max_count = max(counts)
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, gathered.view(world, max_count, -1)[dist.get_rank(group)].contiguous(),
+                                    group=group)
+        moments = torch.stack([total, total_sq])
+        dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+        total, total_sq = moments[0], moments[1]
+    rows = [gathered.view(world, max_count, -1)[r, : counts[r]] for r in range(world)]
+    samples = torch.cat(rows, dim=0)
+    n_tot = float(sum(counts))
+    mean = total / n_tot
+    var = (total_sq - n_tot * mean * mean) / max(n_tot - 1.0, 1.0)
+    return PosteriorSummary(samples=samples, mean=mean, variance=var.clamp_min_(0))
+
+
+def sample_posterior(sampler, inverse_problem, *, num_reconstructions: int, num_sampling_steps: int = 50,
+                     gamma: float = 1.0, eta: float = 1.0, condition=None, group=None) -> PosteriorSummary:
+    """Draw ``num_reconstructions`` DPS samples of one observation across all ranks of ``group``
+    (or on this GPU alone when torch.distributed is not initialised)."""
+    if len(inverse_problem.batch_shape) != 0:
+        raise ValueError("sample_posterior shards the reconstructions of a single observation")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    counts = [shard_count(num_reconstructions, r, world)[1] for r in range(world)]
+    if min(counts) < 1:
+        raise ValueError("need at least one reconstruction per rank")
+    run = sampler.prepare(inverse_problem, num_sampling_steps, counts[rank], gamma, eta, condition)
+    try:
+        for k in range(run.num_steps):
+            run.step(k)
+        max_count = max(counts)
+        gathered = torch.zeros((world * max_count, run.n), device=run.device, dtype=torch.float32)
+        slot = gathered[rank * max_count: rank * max_count + counts[rank]]
+        total = torch.empty(run.n, device=run.device, dtype=torch.float32)
+        total_sq = torch.empty(run.n, device=run.device, dtype=torch.float32)
+        run.finalize(out=slot, total=total, total_sq=total_sq)
+    finally:
+        sampler.release()
+    out = combine_posterior(slot, gathered, total, total_sq, counts, group)
+    x_shape = tuple(inverse_problem.operator.x_shape)
+    return PosteriorSummary(samples=out.samples.view(-1, *x_shape), mean=out.mean.view(x_shape),
+                            variance=out.variance.view(x_shape))

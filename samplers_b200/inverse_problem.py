@@ -1,0 +1,45 @@
+"""InverseProblem(operator, observation, noise) -- same dataclass surface as the
+reference (samplers/inverse_problem.py:10-67): ``residual``, ``log_likelihood``,
+``score``, ``batch_shape``, ``from_observation``, ``from_clean_data``."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from .dtypes import RNG, Shape, Tensor
+from .noise import NoiseModel
+from .operators import Operator
+
+
+@dataclass
+class InverseProblem:
+    operator: Operator
+    observation: Tensor
+    noise: NoiseModel
+
+    def residual(self, x: Tensor) -> Tensor:
+        return self.observation - self.operator(x)
+
+    def log_likelihood(self, x: Tensor) -> Tensor:
+        return self.noise.log_prob(self.residual(x))
+
+    def score(self, x: Tensor) -> Tensor:
+        return self.noise.score(self.residual(x)) * (-1)
+
+    @property
+    def batch_shape(self) -> Shape:
+        return self.observation.shape[: self.observation.ndim - len(self.operator.y_shape)]
+
+    @classmethod
+    def from_observation(cls, obs: Tensor, *, operator: Operator, noise: NoiseModel) -> "InverseProblem":
+        return cls(operator=operator, observation=obs, noise=noise)
+
+    @classmethod
+    def from_clean_data(cls, x_true: Tensor, *, operator: Operator, noise: NoiseModel,
+                        rng: RNG = None) -> "InverseProblem":
+        """Simulate y = A(x_true) + eps, eps ~ noise.sample (rng makes the draw reproducible)."""
+        with torch.no_grad():
+            clean = operator(x_true)
+            y = clean + noise.sample(shape=clean.shape, device=clean.device, dtype=clean.dtype, generator=rng)
+        return cls(operator=operator, observation=y, noise=noise)

@@ -69,3 +69,57 @@ class Golden:
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """Per-step state relative error: |a-b|_2 / |b|_2 (the 1e-5 metric)."""
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def make_network(g: "Golden", device):
+    """Product-side EpsilonNetwork around the golden TinyEpsNet with the fixture's schedule."""
+    from samplers_b200.networks.base import EpsilonNetwork
+
+    class GoldenNetwork(EpsilonNetwork):
+        def __init__(self, core, acp, ts):
+            super().__init__(alphas_cumprod=acp)
+            self.core = core
+            self._ts = ts
+
+        def forward(self, x, t):
+            return self.core(x, int(t))
+
+        @classmethod
+        def from_pretrained(cls, *a, **k):
+            raise NotImplementedError
+
+        def set_sampling_parameters(self, num_sampling_steps, batch_size=1, num_reconstructions=1):
+            self._batch_size, self._num_sampling_steps = batch_size, num_sampling_steps
+            self._num_reconstructions = num_reconstructions
+            self.register_buffer("timesteps", self._ts.to(self.alphas_cumprod.device))
+
+        @property
+        def is_condition_initialized(self):
+            return True
+
+    return GoldenNetwork(g.net(), g["acp"].clone(), g["timesteps"].clone()).to(device)
+
+
+def make_problem(g: "Golden", device):
+    """Product-side InverseProblem equivalent to the fixture's."""
+    from samplers_b200 import operators as pops
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.noise import GaussianNoise, PoissonNoise
+
+    spec, shape = g.meta["op"], g.shape
+    kind = spec[0]
+    if kind == "identity":
+        op = pops.IdentityOperator(shape)
+    elif kind == "mask":
+        op = pops.InpaintingOperator(shape, g["mask"])
+    elif kind == "gblur":
+        op = pops.SeparableBlurOperator(shape, g["taps"])
+    elif kind == "motion":
+        op = pops.MotionBlurOperator(shape, kernel=g["kernel2d"])
+    elif kind == "box":
+        op = pops.BoxDownsampleOperator(shape, spec[1])
+    else:
+        raise ValueError(kind)
+    nk, nparam = g.meta["noise"]
+    noise = GaussianNoise(sigma=nparam) if nk == "gaussian" else PoissonNoise(rate=nparam)
+    return InverseProblem(operator=op.to(device), observation=g["y"].to(device), noise=noise)
