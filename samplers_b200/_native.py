@@ -56,7 +56,10 @@ class PsxError(RuntimeError):
 
 _lib = None
 _lock = threading.Lock()
-launch_count = 0  # kernels-launching calls made through the ABI (bench.py reports it)
+launch_count = 0  # kernel-launching calls made through the ABI (bench.py reports it)
+# CUDA kernels launched by one ABI call (psx_dps_pre depends on the operator kind)
+KERNELS_PER_CALL = {"pre_identity": 1, "pre_mask": 1, "pre_box": 1, "pre_sepblur": 3, "pre_conv2d": 2,
+                    "post": 1, "tweedie": 1}
 
 
 def load() -> C.CDLL:

@@ -51,7 +51,7 @@ static int make_taps(const float* w, int k, bool flip, Taps* out) {
   std::memset(out, 0, sizeof(Taps));
   out->k = kk;
   out->lo = lo4;
-  for (int i = 0; i < kept; ++i) out->w[front + i] = v[first + i];
+  for (int i = 0; i < kept; ++i) out->ww[front + i] = make_float2(v[first + i], v[first + i]);
   return PSX_OK;
 }
 

@@ -24,9 +24,11 @@ int check_cuda(cudaError_t e, const char* what);
 
 // ---------------------------------------------------------------- operator descriptor
 struct Taps {
-  int k;    // number of taps kept (after pruning), <= PSX_MAX_TAPS, padded to a multiple of 8 with zeros
-  int lo;   // offset of w[0]: out[p] = sum_i w[i] * in[p + lo + i]
-  float w[PSX_MAX_TAPS + 9];
+  int k;    // number of taps kept (after pruning), padded to a multiple of 8 with zeros
+  int lo;   // offset of tap 0: out[p] = sum_i w[i] * in[p + lo + i];  lo % 4 == 0
+  // every tap duplicated as (w, w): the packed FFMA2 (fma.rn.f32x2) takes the pair straight from the
+  // kernel-parameter constant bank through a uniform register (LDCU.64 + FFMA2 R, R, UR, R)
+  float2 ww[PSX_MAX_TAPS + 9];
 };
 
 struct Tap2D {

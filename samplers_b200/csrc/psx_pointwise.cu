@@ -13,8 +13,8 @@ template <bool MASK, bool WRITE_X0>
 __global__ void __launch_bounds__(kThreads)
 k1_pointwise_v4(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
                 const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part,
-                float* __restrict__ x0_out, int64_t n, int64_t chunk4, int64_t obs_repeat, float sa,
-                float s1, float w) {
+                int slots, float* __restrict__ x0_out, int64_t n, int64_t chunk4, int64_t obs_repeat, float sa,
+                float s1, float coef) {
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
   const int64_t n4 = n >> 2;
@@ -63,17 +63,19 @@ k1_pointwise_v4(const float* __restrict__ x, const float* __restrict__ eps, cons
         acc = fmaf(r.y, r.y, acc);
         acc = fmaf(r.z, r.z, acc);
         acc = fmaf(r.w, r.w, acc);
-        d.x = __fdiv_rn(__fmul_rn(w, r.x), sa);
-        d.y = __fdiv_rn(__fmul_rn(w, r.y), sa);
-        d.z = __fdiv_rn(__fmul_rn(w, r.z), sa);
-        d.w = __fdiv_rn(__fmul_rn(w, r.w), sa);
+        d.x = __fmul_rn(coef, r.x);
+        d.y = __fmul_rn(coef, r.y);
+        d.z = __fmul_rn(coef, r.z);
+        d.w = __fmul_rn(coef, r.w);
         st_stream4(cs + 4 * i, d);
         if (WRITE_X0) st_stream4(x0_out + l * n + 4 * i, x0);
       }
     }
   }
   const float tot = block_sum(acc, red);
-  if (threadIdx.x == 0) err_part[l * gridDim.x + blockIdx.x] = tot;
+  if (threadIdx.x == 0) err_part[l * slots + blockIdx.x] = tot;
+  if (blockIdx.x == 0)  // unused slots of this sample's row must read as zero in K2
+    for (int i = gridDim.x + threadIdx.x; i < slots; i += kThreads) err_part[l * slots + i] = 0.f;
 }
 
 // scalar fallback for n % 4 != 0 (tiny / odd shapes)
@@ -81,8 +83,8 @@ template <bool MASK>
 __global__ void __launch_bounds__(kThreads)
 k1_pointwise_s(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
                const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part,
-               float* __restrict__ x0_out, int64_t n, int64_t chunk, int64_t obs_repeat, float sa,
-               float s1, float w) {
+               int slots, float* __restrict__ x0_out, int64_t n, int64_t chunk, int64_t obs_repeat, float sa,
+               float s1, float coef) {
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
   const int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, n);
@@ -92,45 +94,82 @@ k1_pointwise_s(const float* __restrict__ x, const float* __restrict__ eps, const
     float r = __fsub_rn(y[(l / obs_repeat) * n + i], x0);
     if (MASK) r = keep[i] ? r : 0.f;
     acc = fmaf(r, r, acc);
-    cot[l * n + i] = __fdiv_rn(__fmul_rn(w, r), sa);
+    cot[l * n + i] = __fmul_rn(coef, r);
     if (x0_out) x0_out[l * n + i] = x0;
   }
   const float tot = block_sum(acc, red);
-  if (threadIdx.x == 0) err_part[l * gridDim.x + blockIdx.x] = tot;
+  if (threadIdx.x == 0) err_part[l * slots + blockIdx.x] = tot;
+  if (blockIdx.x == 0)  // unused slots of this sample's row must read as zero in K2
+    for (int i = gridDim.x + threadIdx.x; i < slots; i += kThreads) err_part[l * slots + i] = 0.f;
 }
 
-int pointwise_parts(int64_t n) {
-  const int64_t units = (n % 4 == 0) ? n / 4 : n;
-  int parts = ceil_div(units, (int64_t)kThreads * 4);
-  return parts < 1 ? 1 : (parts > kMaxParts ? kMaxParts : parts);
+// ---- grid sizing: ONE wave.  A kernel this short (tens of microseconds) loses 10-25 % to a partial
+// second wave, so the per-sample part count is chosen such that parts * L <= resident CTA slots.
+static int g_sm_count = 0;
+int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
 }
+template <typename K>
+int resident_slots(K kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 2;
+  return per_sm * sm_count();
+}
+// parts per sample.  Small launches (fewer than ~3 waves of 4-vectors-per-thread CTAs): exactly one wave,
+// every CTA resident and equally loaded.  Large launches: many short CTAs (measured faster at L = 64:
+// staggered CTA lifetimes keep more loads in flight than one long-lived wave).  Never more than `cap`
+// (slots in the partial-sum row) and never less than one vector per thread.
+int one_wave_parts(int slots, int64_t L, int64_t units_per_sample, int cap) {
+  const int64_t by_size = (units_per_sample + kThreads - 1) / kThreads;
+  int64_t fine = (units_per_sample + 4 * kThreads - 1) / (4 * kThreads);
+  int64_t parts = fine * L >= 3 * (int64_t)slots ? fine : slots / L;
+  if (parts > by_size) parts = by_size;
+  if (parts > cap) parts = cap;
+  return parts < 1 ? 1 : (int)parts;
+}
+
+int pointwise_parts(int64_t) { return kMaxParts; }  // size of the per-sample partial-sum row
 
 int launch_pre_pointwise(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                          int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
                          float* x0_out, cudaStream_t st) {
   const int64_t n = op->n;
-  const int parts = op->err_parts;
+  const int slots = op->err_parts;
   const bool mask = op->kind == PSX_OP_MASK;
-  dim3 grid(parts, (unsigned)L);
+  const float coef = (float)((double)w / (double)sa);  // cot = (w / sa) * r, one rounding
   if (n % 4 == 0) {
-    const int64_t chunk4 = (n / 4 + parts - 1) / parts;
-#define PSX_LAUNCH(M, X)                                                                             \
-  k1_pointwise_v4<M, X><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, x0_out, n, \
-                                                   chunk4, obs_repeat, sa, s1, w)
+#define PSX_LAUNCH(M, X)                                                                               \
+  {                                                                                                    \
+    static int rs = 0;                                                                                 \
+    if (!rs) rs = resident_slots(k1_pointwise_v4<M, X>);                                               \
+    const int parts = one_wave_parts(rs, L, n / 4, slots);                                             \
+    const int64_t chunk4 = (n / 4 + parts - 1) / parts;                                                \
+    k1_pointwise_v4<M, X><<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(                              \
+        x, eps, y, op->d_keep, cot, err_part, slots, x0_out, n, chunk4, obs_repeat, sa, s1, coef);     \
+  }
     if (mask) {
-      if (x0_out) PSX_LAUNCH(true, true); else PSX_LAUNCH(true, false);
+      if (x0_out) PSX_LAUNCH(true, true) else PSX_LAUNCH(true, false)
     } else {
-      if (x0_out) PSX_LAUNCH(false, true); else PSX_LAUNCH(false, false);
+      if (x0_out) PSX_LAUNCH(false, true) else PSX_LAUNCH(false, false)
     }
 #undef PSX_LAUNCH
   } else {
+    const int parts = one_wave_parts(2 * sm_count(), L, n, slots);
     const int64_t chunk = (n + parts - 1) / parts;
+    dim3 grid(parts, (unsigned)L);
     if (mask)
-      k1_pointwise_s<true><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, x0_out, n,
-                                                      chunk, obs_repeat, sa, s1, w);
+      k1_pointwise_s<true><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, slots, x0_out, n,
+                                                      chunk, obs_repeat, sa, s1, coef);
     else
-      k1_pointwise_s<false><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, x0_out, n,
-                                                       chunk, obs_repeat, sa, s1, w);
+      k1_pointwise_s<false><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, slots, x0_out, n,
+                                                       chunk, obs_repeat, sa, s1, coef);
   }
   return check_cuda(cudaGetLastError(), "k1_pointwise launch");
 }
@@ -146,8 +185,8 @@ template <> struct RowVec<4> { using T = float4; };
 template <int F>
 __global__ void __launch_bounds__(kThreads)
 k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
-       float* __restrict__ cot, float* __restrict__ err_part, float* __restrict__ x0_out, int planes,
-       int H, int W, int64_t chunk, int64_t obs_repeat, float sa, float s1, float w) {
+       float* __restrict__ cot, float* __restrict__ err_part, int slots, float* __restrict__ x0_out,
+       int planes, int H, int W, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef) {
   __shared__ float red[32];
   const int Hc = H / F, Wc = W / F;
   const int64_t n = (int64_t)planes * H * W, ny = (int64_t)planes * Hc * Wc;
@@ -190,7 +229,7 @@ k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* 
     const float avg = __fmul_rn(s, inv);  // F*F is a power of two for F = 2, 4, 8: exact scaling
     const float r = __fsub_rn(__ldg(y + (l / obs_repeat) * ny + q), avg);
     acc = fmaf(r, r, acc);
-    const float d = __fdiv_rn(__fmul_rn(w, __fmul_rn(r, inv)), sa);
+    const float d = __fmul_rn(coef, __fmul_rn(r, inv));
 #pragma unroll
     for (int dy = 0; dy < F; ++dy) {
       if constexpr (F == 4) {
@@ -207,14 +246,16 @@ k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* 
     }
   }
   const float tot = block_sum(acc, red);
-  if (threadIdx.x == 0) err_part[l * gridDim.x + blockIdx.x] = tot;
+  if (threadIdx.x == 0) err_part[l * slots + blockIdx.x] = tot;
+  if (blockIdx.x == 0)  // unused slots of this sample's row must read as zero in K2
+    for (int i = gridDim.x + threadIdx.x; i < slots; i += kThreads) err_part[l * slots + i] = 0.f;
 }
 
 // generic factor (not a power of two): division by F*F as the oracle does
 __global__ void __launch_bounds__(kThreads)
 k1_box_any(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
-           float* __restrict__ cot, float* __restrict__ err_part, float* __restrict__ x0_out, int planes,
-           int H, int W, int F, int64_t chunk, int64_t obs_repeat, float sa, float s1, float w) {
+           float* __restrict__ cot, float* __restrict__ err_part, int slots, float* __restrict__ x0_out,
+           int planes, int H, int W, int F, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef) {
   __shared__ float red[32];
   const int Hc = H / F, Wc = W / F;
   const int64_t n = (int64_t)planes * H * W, ny = (int64_t)planes * Hc * Wc;
@@ -237,38 +278,39 @@ k1_box_any(const float* __restrict__ x, const float* __restrict__ eps, const flo
       }
     const float r = __fsub_rn(y[(l / obs_repeat) * ny + q], __fdiv_rn(s, ff));
     acc = fmaf(r, r, acc);
-    const float d = __fdiv_rn(__fmul_rn(w, __fdiv_rn(r, ff)), sa);
+    const float d = __fmul_rn(coef, __fdiv_rn(r, ff));
     for (int dy = 0; dy < F; ++dy)
       for (int dx = 0; dx < F; ++dx) cot[off + (int64_t)dy * W + dx] = d;
   }
   const float tot = block_sum(acc, red);
-  if (threadIdx.x == 0) err_part[l * gridDim.x + blockIdx.x] = tot;
+  if (threadIdx.x == 0) err_part[l * slots + blockIdx.x] = tot;
+  if (blockIdx.x == 0)  // unused slots of this sample's row must read as zero in K2
+    for (int i = gridDim.x + threadIdx.x; i < slots; i += kThreads) err_part[l * slots + i] = 0.f;
 }
 
-int box_parts(int64_t ny) {
-  int parts = ceil_div(ny, (int64_t)kThreads);
-  return parts < 1 ? 1 : (parts > kMaxParts ? kMaxParts : parts);
-}
+int box_parts(int64_t) { return kMaxParts; }
 
 int launch_pre_box(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                    int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
                    float* x0_out, cudaStream_t st) {
-  const int parts = op->err_parts;
-  const int64_t chunk = (op->n_y + parts - 1) / parts;
-  dim3 grid(parts, (unsigned)L);
+  const int slots = op->err_parts;
   const int F = op->factor;
-  if (F == 4 && op->W % 4 == 0)
-    k1_box<4><<<grid, kThreads, 0, st>>>(x, eps, y, cot, err_part, x0_out, op->C, op->H, op->W, chunk,
-                                         obs_repeat, sa, s1, w);
-  else if (F == 2)
-    k1_box<2><<<grid, kThreads, 0, st>>>(x, eps, y, cot, err_part, x0_out, op->C, op->H, op->W, chunk,
-                                         obs_repeat, sa, s1, w);
-  else if (F == 8)
-    k1_box<8><<<grid, kThreads, 0, st>>>(x, eps, y, cot, err_part, x0_out, op->C, op->H, op->W, chunk,
-                                         obs_repeat, sa, s1, w);
-  else
-    k1_box_any<<<grid, kThreads, 0, st>>>(x, eps, y, cot, err_part, x0_out, op->C, op->H, op->W, F,
-                                          chunk, obs_repeat, sa, s1, w);
+  const float coef = (float)((double)w / (double)sa);
+#define PSX_BOX(KERNEL, ...)                                                                          \
+  {                                                                                                   \
+    static int rs = 0;                                                                                \
+    if (!rs) rs = resident_slots(KERNEL);                                                             \
+    const int parts = one_wave_parts(rs, L, op->n_y, slots);                                          \
+    const int64_t chunk = (op->n_y + parts - 1) / parts;                                              \
+    KERNEL<<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(x, eps, y, cot, err_part, slots, x0_out,    \
+                                                          op->C, op->H, op->W, __VA_ARGS__ chunk,     \
+                                                          obs_repeat, sa, s1, coef);                  \
+  }
+  if (F == 4 && op->W % 4 == 0) PSX_BOX(k1_box<4>, )
+  else if (F == 2) PSX_BOX(k1_box<2>, )
+  else if (F == 8) PSX_BOX(k1_box<8>, )
+  else PSX_BOX(k1_box_any, F, )
+#undef PSX_BOX
   return check_cuda(cudaGetLastError(), "k1_box launch");
 }
 
@@ -354,29 +396,22 @@ int launch_post(const float* x, const float* eps, const float* cot, const float*
                 float c_ell, float c_s, float sd, float gamma, float* x_next, float* err_out,
                 cudaStream_t st) {
   const bool has_z = z != nullptr;
-  if (n % 4 == 0) {
-    int parts = ceil_div(n / 4, (int64_t)kThreads * 4);
-    parts = parts < 1 ? 1 : parts;
-    const int64_t chunk4 = (n / 4 + parts - 1) / parts;
-    dim3 grid(parts, (unsigned)L);
-    if (has_z)
-      k2_post_v4<true><<<grid, kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, chunk4, sa,
-                                                  s1, c_ell, c_s, sd, gamma, x_next, err_out);
-    else
-      k2_post_v4<false><<<grid, kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, chunk4,
-                                                   sa, s1, c_ell, c_s, sd, gamma, x_next, err_out);
-  } else {
-    int parts = ceil_div(n, (int64_t)kThreads * 4);
-    parts = parts < 1 ? 1 : parts;
-    const int64_t chunk = (n + parts - 1) / parts;
-    dim3 grid(parts, (unsigned)L);
-    if (has_z)
-      k2_post_s<true><<<grid, kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, chunk, sa,
-                                                 s1, c_ell, c_s, sd, gamma, x_next, err_out);
-    else
-      k2_post_s<false><<<grid, kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, chunk, sa,
-                                                  s1, c_ell, c_s, sd, gamma, x_next, err_out);
+#define PSX_POST(KERNEL, UNITS)                                                                        \
+  {                                                                                                    \
+    static int rs = 0;                                                                                 \
+    if (!rs) rs = resident_slots(KERNEL);                                                              \
+    const int parts = one_wave_parts(rs, L, (UNITS), 1 << 20);                                         \
+    const int64_t chunk = ((UNITS) + parts - 1) / parts;                                               \
+    KERNEL<<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, \
+                                                          chunk, sa, s1, c_ell, c_s, sd, gamma, x_next, \
+                                                          err_out);                                    \
   }
+  if (n % 4 == 0) {
+    if (has_z) PSX_POST(k2_post_v4<true>, n / 4) else PSX_POST(k2_post_v4<false>, n / 4)
+  } else {
+    if (has_z) PSX_POST(k2_post_s<true>, n) else PSX_POST(k2_post_s<false>, n)
+  }
+#undef PSX_POST
   return check_cuda(cudaGetLastError(), "k2_post launch");
 }
 

@@ -131,6 +131,8 @@ def test_full_size_k1_consistent_with_standalone_kernels():
         x = torch.randn(L, nat.n, device=DEV, generator=gen)
         eps = torch.randn(L, nat.n, device=DEV, generator=gen)
         y = torch.randn(1, nat.n_y, device=DEV, generator=gen)
+        if isinstance(op, pops.InpaintingOperator):  # dense observations are zero at missing pixels
+            y = y * (~op.mask).flatten().float()
         sa, s1, w = 0.8, 0.6, 400.0
         cot = torch.empty_like(x)
         part = torch.empty(L, nat.err_parts, device=DEV)
