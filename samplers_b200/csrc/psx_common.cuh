@@ -72,8 +72,25 @@ __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
 // ---------------------------------------------------------------- arithmetic with torch's roundings
 // networks/base.py:42-43 evaluates mul, sub, div as three separately rounded tensor ops;
 // the intrinsics stop nvcc from contracting them into an FMA / a reciprocal multiply.
-__device__ __forceinline__ float tweedie(float x, float e, float s1, float sa) {
-  return __fdiv_rn(__fsub_rn(x, __fmul_rn(s1, e)), sa);
+// The division by the per-launch constant sa uses Markstein's correction instead of the generic IEEE
+// division sequence (~25 instructions incl. range checks): with rcp = RN(1/sa),
+//   q0 = RN(t*rcp);  rem = t - q0*sa (exact in one FMA);  q = RN(q0 + rem*rcp)
+// is the correctly rounded t/sa for normal operands (sa is in [1e-3, 1]) -- 3 instructions.
+struct TweedieC {
+  float s1, sa, rcp;
+};
+__device__ __forceinline__ TweedieC make_tc(float s1, float sa) {
+  TweedieC c;
+  c.s1 = s1;
+  c.sa = sa;
+  c.rcp = __frcp_rn(sa);
+  return c;
+}
+__device__ __forceinline__ float tweedie(float x, float e, const TweedieC& c) {
+  const float t = __fsub_rn(x, __fmul_rn(c.s1, e));
+  const float q0 = __fmul_rn(t, c.rcp);
+  const float rem = __fmaf_rn(-q0, c.sa, t);
+  return __fmaf_rn(rem, c.rcp, q0);
 }
 
 // ---------------------------------------------------------------- reductions (fixed order => deterministic)

@@ -6,6 +6,10 @@
 //     cols<RESIDUAL> : r = y - V h1, |r|^2 partials, h2 = V^T r  (strip-local) -> workspace (in place)
 //     rows<COT>      : cot = w * H^T h2 / sa                                   -> d_cot
 // All passes are zero-padded "same" cross-correlations; halos are zero-filled in shared memory.
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "psx_common.cuh"
 
 namespace psx {
@@ -26,7 +30,7 @@ __device__ __forceinline__ void fma2_block(float2 (&acc)[8], const float2 (&win)
 
 __device__ __forceinline__ float4 load_row4(const float* __restrict__ in, const float* __restrict__ eps,
                                             int64_t plane, int gr, int gc, int H, int W, bool vec_ok,
-                                            bool tw, float s1, float sa) {
+                                            bool tw, const TweedieC& tc) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (gr >= H) return v;
   const int64_t g = plane + (int64_t)gr * W + gc;
@@ -34,8 +38,8 @@ __device__ __forceinline__ float4 load_row4(const float* __restrict__ in, const 
     v = ld_stream4(in + g);
     if (tw) {
       const float4 e = ld_stream4(eps + g);
-      v.x = tweedie(v.x, e.x, s1, sa); v.y = tweedie(v.y, e.y, s1, sa);
-      v.z = tweedie(v.z, e.z, s1, sa); v.w = tweedie(v.w, e.w, s1, sa);
+      v.x = tweedie(v.x, e.x, tc); v.y = tweedie(v.y, e.y, tc);
+      v.z = tweedie(v.z, e.z, tc); v.w = tweedie(v.w, e.w, tc);
     }
   } else {
     float t[4];
@@ -44,7 +48,7 @@ __device__ __forceinline__ float4 load_row4(const float* __restrict__ in, const 
       t[c] = 0.f;
       if (gc + c >= 0 && gc + c < W) {
         t[c] = in[g + c];
-        if (tw) t[c] = tweedie(t[c], eps[g + c], s1, sa);
+        if (tw) t[c] = tweedie(t[c], eps[g + c], tc);
       }
     }
     v = make_float4(t[0], t[1], t[2], t[3]);
@@ -62,6 +66,7 @@ __global__ void __launch_bounds__(kThreads)
 conv_rows(const float* __restrict__ in, const float* __restrict__ eps, float* __restrict__ out, int H, int W,
           int TW, int pitch2, const __grid_constant__ Taps taps, float sa, float s1, float coef) {
   extern __shared__ __align__(16) float2 smem2[];
+  const TweedieC tc = make_tc(s1, sa);
   const int c0 = blockIdx.x * TW;
   const int r0 = blockIdx.y * kRowTH;
   const int64_t plane = (int64_t)blockIdx.z * H * W;
@@ -71,8 +76,8 @@ conv_rows(const float* __restrict__ in, const float* __restrict__ eps, float* __
   for (int idx = threadIdx.x; idx < (kRowTH / 2) * in_w4; idx += kThreads) {
     const int rp = idx / in_w4, c4 = idx - rp * in_w4;
     const int gc = c0 + taps.lo + 4 * c4, gr = r0 + 2 * rp;
-    const float4 a = load_row4(in, eps, plane, gr, gc, H, W, vec_ok, MODE == ROWS_TWEEDIE, s1, sa);
-    const float4 b = load_row4(in, eps, plane, gr + 1, gc, H, W, vec_ok, MODE == ROWS_TWEEDIE, s1, sa);
+    const float4 a = load_row4(in, eps, plane, gr, gc, H, W, vec_ok, MODE == ROWS_TWEEDIE, tc);
+    const float4 b = load_row4(in, eps, plane, gr + 1, gc, H, W, vec_ok, MODE == ROWS_TWEEDIE, tc);
     float2* dst = smem2 + rp * pitch2 + 4 * c4;
     *reinterpret_cast<float4*>(dst) = make_float4(a.x, b.x, a.y, b.y);
     *reinterpret_cast<float4*>(dst + 2) = make_float4(a.z, b.z, a.w, b.w);
@@ -294,6 +299,361 @@ conv_cols(const float* in, const float* __restrict__ y, float* out,  // in may a
   }
 }
 
+// ========================================================================================== pipelined fast path
+// Persistent CTAs walk over tiles.  While tile i is computed, tile i+1 is already being copied into the
+// other shared-memory stage by the bulk-copy engine (cp.async.bulk global->shared, one instruction per
+// row segment, completion signalled on an mbarrier with complete_tx) -- no per-element copy instructions,
+// no register staging, and the global-load latency that dominated the one-tile-per-CTA kernels (ncu:
+// >30 % of stall samples on the first use of a loaded value) hides behind the FFMA2 work.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// The vote makes the loop condition warp-uniform *for the compiler*: code after the wait stays eligible
+// for the uniform datapath (LDCU + FFMA2 with a UR operand), which is what keeps FFMA2 at 2 cycles
+// (3 vector register pairs per FFMA2 cost 3 register-file cycles; 2 pairs + 1 uniform pair cost 2).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!__all_sync(0xffffffffu, ok));
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+
+constexpr int kPipeRows = 16;   // rows per tile of the pipelined row pass: 8 row pairs (rho, rho + 8)
+constexpr int kPipeHdr = 128;   // bytes reserved at the start of dynamic smem for the two mbarriers
+
+// NOTE on loop shapes in the two kernels below: every per-thread loop ahead of an FFMA2 block is fully
+// unrolled (compile-time trip count, guards inside) or has a runtime trip count with no thread-dependent
+// branch.  Otherwise ptxas treats the warp as possibly divergent from there on, stops using the uniform
+// datapath, and FFMA2 with three vector-register pairs costs 3 register-file cycles instead of the 2 of
+// FFMA2 R, R, UR, R.
+
+// ---- rows.  The batch is one tall matrix of total_rows = planes * H rows x W columns (the padding is
+// horizontal only, so tiles may straddle planes).  A tile is 16 full rows = ONE contiguous 16*W*4-byte
+// block per input array: the producer is a single cp.async.bulk per array and tile.  Per CTA: 2 raw
+// stages + one compute tile in the row-pair-interleaved float2 layout of conv_rows (pairs (rho, rho+8);
+// pitch2 % 16 == 2 => conflict-free LDS.128) whose halo columns are zeroed once.  A conversion pass
+// (Tweedie or plain copy) moves a landed stage into the compute tile.  Needs W % 8 == 0, W <= 512.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, float* __restrict__ out,
+               int64_t total_rows, int W, int pitch2, int64_t num_tiles, const __grid_constant__ Taps taps,
+               float sa, float s1, float coef) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const TweedieC tc = make_tc(s1, sa);
+  constexpr int kArrays = MODE == ROWS_TWEEDIE ? 2 : 1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float2* comp = reinterpret_cast<float2*>(smem_raw + kPipeHdr);              // 8 x pitch2 float2
+  float* raw = reinterpret_cast<float*>(comp + (kPipeRows / 2) * pitch2);       // 2 stages x kArrays x 16 x W
+  const int tile_floats = kPipeRows * W;
+  const int w4 = W >> 2;
+
+  {  // zero the compute tile once: its halo columns are never written again
+    const int n4 = ((kPipeRows / 2) * pitch2) >> 1;
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {  // 8 x (512 + 136 + 14) float2 / 2 <= 11 * 256
+      const int i = threadIdx.x + t * kThreads;
+      if (i < n4) reinterpret_cast<float4*>(comp)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int stage) {
+    if (threadIdx.x == 0) {
+      const int64_t r0 = tile * kPipeRows;
+      const int64_t left = total_rows - r0;
+      const uint32_t nb = (uint32_t)(left < kPipeRows ? left : kPipeRows) * (uint32_t)W * 4u;
+      float* xs = raw + (size_t)stage * kArrays * tile_floats;
+      mbar_expect_tx(&bars[stage], nb * kArrays);
+      bulk_g2s(xs, in + r0 * W, nb, &bars[stage]);
+      if (kArrays == 2) bulk_g2s(xs + tile_floats, eps + r0 * W, nb, &bars[stage]);
+    }
+  };
+
+  int64_t tile = blockIdx.x;
+  if (tile < num_tiles) issue(tile, 0);
+  for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
+    const int stage = it & 1;
+    if (tile + gridDim.x < num_tiles) issue(tile + gridDim.x, stage ^ 1);
+    mbar_wait(&bars[stage], (uint32_t)(it >> 1) & 1u);
+    __syncthreads();  // B1: previous tile's compute is done with `comp`
+    const float* xs = raw + (size_t)stage * kArrays * tile_floats;
+    const int64_t r0 = tile * kPipeRows;
+    const int64_t left = total_rows - r0;
+    const int rows_valid = left < kPipeRows ? (int)left : kPipeRows;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {  // 8 row pairs x W/4 column quads <= 4 * 256 for W <= 512
+      const int idx = threadIdx.x + t * kThreads;
+      const int rp = idx / w4, c4 = idx - rp * w4;
+      if (rp < kPipeRows / 2) {
+        const bool va = rp < rows_valid, vb = rp + 8 < rows_valid;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (va) a = *reinterpret_cast<const float4*>(xs + rp * W + 4 * c4);
+        if (vb) b = *reinterpret_cast<const float4*>(xs + (rp + 8) * W + 4 * c4);
+        if (MODE == ROWS_TWEEDIE) {
+          float4 ea = make_float4(0.f, 0.f, 0.f, 0.f), eb = ea;
+          if (va) ea = *reinterpret_cast<const float4*>(xs + tile_floats + rp * W + 4 * c4);
+          if (vb) eb = *reinterpret_cast<const float4*>(xs + tile_floats + (rp + 8) * W + 4 * c4);
+          a.x = tweedie(a.x, ea.x, tc); a.y = tweedie(a.y, ea.y, tc);
+          a.z = tweedie(a.z, ea.z, tc); a.w = tweedie(a.w, ea.w, tc);
+          b.x = tweedie(b.x, eb.x, tc); b.y = tweedie(b.y, eb.y, tc);
+          b.z = tweedie(b.z, eb.z, tc); b.w = tweedie(b.w, eb.w, tc);
+        }
+        float2* dst = comp + rp * pitch2 - taps.lo + 4 * c4;  // smem column s <-> image column s + lo
+        *reinterpret_cast<float4*>(dst) = make_float4(a.x, b.x, a.y, b.y);
+        *reinterpret_cast<float4*>(dst + 2) = make_float4(a.z, b.z, a.w, b.w);
+      }
+    }
+    __syncthreads();  // B2: `comp` complete; raw[stage] fully consumed (may be refilled from now on)
+
+    const int ncg = W >> 3;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {  // W/8 column groups x 8 row pairs <= 2 * 256 tasks
+      const int q_raw = threadIdx.x + t * kThreads;
+      const bool q_ok = q_raw < 8 * ncg;
+      const int q = q_ok ? q_raw : 8 * ncg - 1;  // every thread computes (uniform control flow); stores are guarded
+      const int rp = q & 7, cg = q >> 3;
+      const float2* row = comp + rp * pitch2 + 8 * cg;
+      float2 acc[8], win[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(row + 2 * m);
+        win[2 * m] = make_float2(v.x, v.y); win[2 * m + 1] = make_float2(v.z, v.w);
+      }
+      for (int c = 0; c < taps.k; c += 8) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float4 v = *reinterpret_cast<const float4*>(row + c + 8 + 2 * m);
+          win[8 + 2 * m] = make_float2(v.x, v.y); win[9 + 2 * m] = make_float2(v.z, v.w);
+        }
+        fma2_block(acc, win, taps.ww + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool ok = q_ok && rp + 8 * h < rows_valid;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = h ? acc[j].y : acc[j].x;
+          if (MODE == ROWS_COT) o[j] = __fmul_rn(coef, o[j]);
+        }
+        float* dst = out + (r0 + rp + 8 * h) * W + 8 * cg;
+        if (ok) {
+          st_stream4(dst, make_float4(o[0], o[1], o[2], o[3]));
+          st_stream4(dst + 4, make_float4(o[4], o[5], o[6], o[7]));
+        }
+      }
+      if (W <= 256) break;  // uniform: one round covers all tasks
+    }
+    // no trailing barrier: B1 of the next iteration orders this compute before the next conversion pass,
+    // and the stage refilled next (this one) was fully read before B2.
+  }
+}
+
+// ---- columns.  Tile = one 32-column strip (all H rows) of one plane, fetched by ONE 2-D TMA box load
+// (cp.async.bulk.tensor.2d, box = 32 x H) into a stage whose zero halo rows persist across tiles; a
+// lane owns a column pair and 8 output rows.  r lives in one extra buffer; y is prefetched straight from
+// global (it is shared by all samples: L2 hits).  Needs W % 32 == 0, H % 8 == 0, H <= 256.
+constexpr int kColTC = 32;
+
+template <bool RESIDUAL, int ROUNDS>  // ROUNDS = H / 8 * 16 / kThreads: tasks per thread and pass (1 or 2)
+__global__ void __launch_bounds__(kThreads, 2)
+conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ y, float* out,
+               float* __restrict__ err_part, int C, int H, int W, int strips, int64_t num_tiles,
+               int64_t obs_repeat, const __grid_constant__ Taps tf, const __grid_constant__ Taps ta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float red[32];
+  constexpr int TC = kColTC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw + kPipeHdr);
+  const int rowsA = H + tf.k, rowsB = H + ta.k;
+  const int stage_floats = rowsA * TC;
+  float* bufB = smem + 2 * (size_t)stage_floats;  // RESIDUAL only
+
+  {  // zero the halo rows once (8 float4 per row): stage rows outside [-lo, -lo + H), same for bufB
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {  // (136 + 8) halo rows * 8 float4 <= 5 * 256
+      const int i = threadIdx.x + t * kThreads;
+      const int r = i >> 3, c4 = i & 7;
+      if (r < tf.k) {
+        const int row = r < -tf.lo ? r : r + H;
+        *reinterpret_cast<float4*>(smem + (size_t)row * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(smem + stage_floats + (size_t)row * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (RESIDUAL && r < ta.k) {
+        const int row = r < -ta.lo ? r : r + H;
+        *reinterpret_cast<float4*>(bufB + (size_t)row * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int stage) {
+    if (threadIdx.x == 0) {
+      const int64_t pl = tile / strips;
+      const int c0 = (int)(tile - pl * strips) * TC;
+      mbar_expect_tx(&bars[stage], (uint32_t)H * TC * 4u);
+      tma_load_2d(smem + (size_t)stage * stage_floats - (size_t)tf.lo * TC, &tmap, c0, (int)(pl * H), &bars[stage]);
+    }
+  };
+
+  constexpr int npair = TC >> 1;
+  int64_t tile = blockIdx.x;
+  if (tile < num_tiles) issue(tile, 0);
+  for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
+    const int stage = it & 1;
+    if (tile + gridDim.x < num_tiles) issue(tile + gridDim.x, stage ^ 1);
+    mbar_wait(&bars[stage], (uint32_t)(it >> 1) & 1u);
+    __syncthreads();
+    const float* A = smem + (size_t)stage * stage_floats;
+    const int64_t pl = tile / strips;
+    const int strip = (int)(tile - pl * strips);
+    const int c0 = strip * TC;
+    const int64_t plane = pl * H * W;
+    const int64_t yplane = RESIDUAL ? ((pl / C) / obs_repeat * C + pl % C) * (int64_t)H * W : 0;
+    float e2 = 0.f;
+
+#pragma unroll
+    for (int t = 0; t < ROUNDS; ++t) {  // H/8 * 16 tasks = ROUNDS * 256 exactly
+      const int q = threadIdx.x + t * kThreads;
+      const int cp = q % npair, g = q / npair;
+      const int gc = c0 + 2 * cp;
+      float2 yv[8];
+      if (RESIDUAL) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          yv[j] = __ldg(reinterpret_cast<const float2*>(y + yplane + (int64_t)(8 * g + j) * W + gc));
+      }
+      const float* col = A + (size_t)(8 * g) * TC + 2 * cp;
+      float2 acc[8], win[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = make_float2(0.f, 0.f);
+        win[j] = *reinterpret_cast<const float2*>(col + j * TC);
+      }
+      for (int k = 0; k < tf.k; k += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[8 + j] = *reinterpret_cast<const float2*>(col + (k + 8 + j) * TC);
+        fma2_block(acc, win, tf.ww + k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int gr = 8 * g + j;
+        if (RESIDUAL) {
+          float2 r;
+          r.x = __fsub_rn(yv[j].x, acc[j].x);
+          r.y = __fsub_rn(yv[j].y, acc[j].y);
+          e2 = fmaf(r.x, r.x, e2);
+          e2 = fmaf(r.y, r.y, e2);
+          *reinterpret_cast<float2*>(bufB + (size_t)(gr - ta.lo) * TC + 2 * cp) = r;
+        } else {
+          *reinterpret_cast<float2*>(out + plane + (int64_t)gr * W + gc) = acc[j];
+        }
+      }
+    }
+    if (RESIDUAL) {
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < ROUNDS; ++t) {
+        const int q = threadIdx.x + t * kThreads;
+        const int cp = q % npair, g = q / npair;
+        const float* col = bufB + (size_t)(8 * g) * TC + 2 * cp;
+        float2 acc[8], win[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = make_float2(0.f, 0.f);
+          win[j] = *reinterpret_cast<const float2*>(col + j * TC);
+        }
+        for (int k = 0; k < ta.k; k += 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) win[8 + j] = *reinterpret_cast<const float2*>(col + (k + 8 + j) * TC);
+          fma2_block(acc, win, ta.ww + k);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
+        }
+        const int gc = c0 + 2 * cp;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float2*>(out + plane + (int64_t)(8 * g + j) * W + gc) = acc[j];
+      }
+      const float tot = block_sum(e2, red);  // contains a __syncthreads
+      if (threadIdx.x == 0) {
+        const int64_t l = pl / C;
+        const int ch = (int)(pl % C);
+        err_part[l * (int64_t)(C * strips) + ch * strips + strip] = tot;
+      }
+    }
+    __syncthreads();  // stage + bufB + red fully consumed
+  }
+}
+
+// host: 2-D tensor map over the tall (planes*H) x W fp32 matrix, box = 32 columns x H rows
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+static bool make_strip_map(CUtensorMap* map, const float* base, int64_t rows, int W, int H) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)W * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kColTC, (cuuint32_t)H};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ------------------------------------------------------------------------------------------ planning
 static int row_tw(int W) {
   int tw = (W + 31) & ~31;
@@ -322,9 +682,34 @@ int sepblur_plan(psx_op* op) {
   return PSX_OK;
 }
 
+int sm_count();
+
 template <int MODE>
 static int run_rows(const psx_op* op, const Taps& t, const float* in, const float* eps, float* out,
                     int64_t planes, float sa, float s1, float w, cudaStream_t st) {
+  if ((op->W & 7) == 0 && op->W <= 512 && !getenv("PSX_NO_PIPE")) {
+    const int pitch2 = row_pitch2(op->W + t.k);
+    const int arrays = MODE == ROWS_TWEEDIE ? 2 : 1;
+    const size_t smem = kPipeHdr + (size_t)(kPipeRows / 2) * pitch2 * sizeof(float2) +
+                        (size_t)2 * arrays * kPipeRows * op->W * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(conv_rows_pipe<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_rows_pipe<MODE>, kThreads, smem) != cudaSuccess ||
+        occ < 1)
+      occ = 1;
+    const int64_t total_rows = planes * op->H;
+    const int64_t num_tiles = (total_rows + kPipeRows - 1) / kPipeRows;
+    int64_t grid = (int64_t)occ * sm_count();
+    if (grid > num_tiles) grid = num_tiles;
+    const float coef = (float)((double)w / (double)sa);
+    conv_rows_pipe<MODE><<<(unsigned)grid, kThreads, smem, st>>>(in, eps, out, total_rows, op->W, pitch2,
+                                                                 num_tiles, t, sa, s1, coef);
+    return check_cuda(cudaGetLastError(), "conv_rows_pipe launch");
+  }
   const int TW = row_tw(op->W);
   const int pitch = row_pitch2(TW + t.k);
   const size_t smem = (size_t)(kRowTH / 2) * pitch * sizeof(float2);
@@ -342,6 +727,35 @@ static int run_rows(const psx_op* op, const Taps& t, const float* in, const floa
 template <bool RESIDUAL>
 static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const float* in, const float* y,
                     float* out, float* err_part, int64_t planes, int64_t obs_repeat, cudaStream_t st) {
+  {
+    const size_t stage = ((size_t)op->H + tf.k) * kColTC * sizeof(float);
+    const size_t smem_pipe = kPipeHdr + 2 * stage + (RESIDUAL ? ((size_t)op->H + ta.k) * kColTC * sizeof(float) : 0);
+    CUtensorMap map;
+    if ((op->W % kColTC) == 0 && (op->H % 16) == 0 && op->H <= 256 && !getenv("PSX_NO_PIPE") &&
+        make_strip_map(&map, in, planes * op->H, op->W, op->H)) {
+      const int rounds = (op->H >> 3) * (kColTC >> 1) / kThreads;  // H % 16 == 0  =>  exact
+      const int strips = op->W / kColTC;
+      const int64_t num_tiles = planes * strips;
+#define PSX_COLS(R)                                                                                          \
+  {                                                                                                          \
+    static int occ = 0;                                                                                      \
+    if (!occ) {                                                                                              \
+      cudaFuncSetAttribute(conv_cols_pipe<RESIDUAL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                           200 * 1024);                                                                      \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_cols_pipe<RESIDUAL, R>, kThreads,         \
+                                                        smem_pipe) != cudaSuccess || occ < 1)                \
+        occ = 1;                                                                                             \
+    }                                                                                                        \
+    int64_t grid = (int64_t)occ * sm_count();                                                                \
+    if (grid > num_tiles) grid = num_tiles;                                                                  \
+    conv_cols_pipe<RESIDUAL, R><<<(unsigned)grid, kThreads, smem_pipe, st>>>(                                \
+        map, y, out, err_part, op->C, op->H, op->W, strips, num_tiles, obs_repeat, tf, ta);                  \
+  }
+      if (rounds == 2) PSX_COLS(2) else if (rounds == 1) PSX_COLS(1)
+      if (rounds == 1 || rounds == 2) return check_cuda(cudaGetLastError(), "conv_cols_pipe launch");
+#undef PSX_COLS
+    }
+  }
   const int TC = op->col_tc;
   const size_t smem = cols_smem(op, TC, RESIDUAL, tf, ta);
   static bool attr_done = false;
@@ -380,6 +794,7 @@ conv2d_sparse(const float* __restrict__ in, const float* __restrict__ eps, const
               float* __restrict__ out, float* __restrict__ err_part, const Tap2D* __restrict__ taps,
               int ntaps, int C, int H, int W, int kh, int kw, int64_t obs_repeat, float sa, float s1,
               float wgt) {
+  const TweedieC tc = make_tc(s1, sa);
   extern __shared__ __align__(16) float smem[];
   __shared__ Tap2D stap[kC2Chunk];
   __shared__ float red[32];
@@ -395,7 +810,7 @@ conv2d_sparse(const float* __restrict__ in, const float* __restrict__ eps, const
     float v = 0.f;
     if (gr >= 0 && gr < H && gc >= 0 && gc < W) {
       v = in[plane + (int64_t)gr * W + gc];
-      if (MODE == C2_RESIDUAL) v = tweedie(v, eps[plane + (int64_t)gr * W + gc], s1, sa);
+      if (MODE == C2_RESIDUAL) v = tweedie(v, eps[plane + (int64_t)gr * W + gc], tc);
     }
     smem[idx] = v;
   }

@@ -15,6 +15,7 @@ k1_pointwise_v4(const float* __restrict__ x, const float* __restrict__ eps, cons
                 const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part,
                 int slots, float* __restrict__ x0_out, int64_t n, int64_t chunk4, int64_t obs_repeat, float sa,
                 float s1, float coef) {
+  const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
   const int64_t n4 = n >> 2;
@@ -45,10 +46,10 @@ k1_pointwise_v4(const float* __restrict__ x, const float* __restrict__ eps, cons
       const int64_t i = base + (int64_t)u * kThreads;
       if (i < end) {
         float4 x0, r, d;
-        x0.x = tweedie(xv[u].x, ev[u].x, s1, sa);
-        x0.y = tweedie(xv[u].y, ev[u].y, s1, sa);
-        x0.z = tweedie(xv[u].z, ev[u].z, s1, sa);
-        x0.w = tweedie(xv[u].w, ev[u].w, s1, sa);
+        x0.x = tweedie(xv[u].x, ev[u].x, tc);
+        x0.y = tweedie(xv[u].y, ev[u].y, tc);
+        x0.z = tweedie(xv[u].z, ev[u].z, tc);
+        x0.w = tweedie(xv[u].w, ev[u].w, tc);
         r.x = __fsub_rn(yv[u].x, x0.x);
         r.y = __fsub_rn(yv[u].y, x0.y);
         r.z = __fsub_rn(yv[u].z, x0.z);
@@ -85,12 +86,13 @@ k1_pointwise_s(const float* __restrict__ x, const float* __restrict__ eps, const
                const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part,
                int slots, float* __restrict__ x0_out, int64_t n, int64_t chunk, int64_t obs_repeat, float sa,
                float s1, float coef) {
+  const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
   const int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, n);
   float acc = 0.f;
   for (int64_t i = beg + threadIdx.x; i < end; i += kThreads) {
-    const float x0 = tweedie(x[l * n + i], eps[l * n + i], s1, sa);
+    const float x0 = tweedie(x[l * n + i], eps[l * n + i], tc);
     float r = __fsub_rn(y[(l / obs_repeat) * n + i], x0);
     if (MASK) r = keep[i] ? r : 0.f;
     acc = fmaf(r, r, acc);
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(kThreads)
 k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
        float* __restrict__ cot, float* __restrict__ err_part, int slots, float* __restrict__ x0_out,
        int planes, int H, int W, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef) {
+  const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int Hc = H / F, Wc = W / F;
   const int64_t n = (int64_t)planes * H * W, ny = (int64_t)planes * Hc * Wc;
@@ -222,7 +225,7 @@ k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* 
       }
 #pragma unroll
       for (int dx = 0; dx < F; ++dx) {
-        x0[dy][dx] = tweedie(xv[dx], ev[dx], s1, sa);
+        x0[dy][dx] = tweedie(xv[dx], ev[dx], tc);
         s = __fadd_rn(s, x0[dy][dx]);
       }
     }
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(kThreads)
 k1_box_any(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
            float* __restrict__ cot, float* __restrict__ err_part, int slots, float* __restrict__ x0_out,
            int planes, int H, int W, int F, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef) {
+  const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int Hc = H / F, Wc = W / F;
   const int64_t n = (int64_t)planes * H * W, ny = (int64_t)planes * Hc * Wc;
@@ -272,7 +276,7 @@ k1_box_any(const float* __restrict__ x, const float* __restrict__ eps, const flo
     float s = 0.f;
     for (int dy = 0; dy < F; ++dy)
       for (int dx = 0; dx < F; ++dx) {
-        const float v = tweedie(x[off + (int64_t)dy * W + dx], eps[off + (int64_t)dy * W + dx], s1, sa);
+        const float v = tweedie(x[off + (int64_t)dy * W + dx], eps[off + (int64_t)dy * W + dx], tc);
         if (x0_out) x0_out[off + (int64_t)dy * W + dx] = v;
         s = __fadd_rn(s, v);
       }
@@ -323,6 +327,7 @@ k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const flo
            const float* __restrict__ vjp, const float* __restrict__ z, const float* __restrict__ err_part,
            int err_parts, int64_t n, int64_t chunk4, float sa, float s1, float c_ell, float c_s,
            float sd, float gamma, float* __restrict__ x_next, float* __restrict__ err_out) {
+  const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
   const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
@@ -354,7 +359,7 @@ k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const flo
         float4 o;
 #define PSX_K2_LANE(c)                                                                         \
   {                                                                                            \
-    const float x0 = tweedie(xv[u].c, ev[u].c, s1, sa);                                        \
+    const float x0 = tweedie(xv[u].c, ev[u].c, tc);                                        \
     float m = __fadd_rn(__fmul_rn(c_ell, xv[u].c), __fmul_rn(c_s, x0));                        \
     if (HAS_Z) m = __fadd_rn(m, __fmul_rn(sd, zv[u].c));                                       \
     const float g = __fadd_rn(dv[u].c, __fmul_rn(-s1, vv[u].c));                               \
@@ -374,6 +379,7 @@ k2_post_s(const float* __restrict__ x, const float* __restrict__ eps, const floa
           const float* __restrict__ vjp, const float* __restrict__ z, const float* __restrict__ err_part,
           int err_parts, int64_t n, int64_t chunk, float sa, float s1, float c_ell, float c_s, float sd,
           float gamma, float* __restrict__ x_next, float* __restrict__ err_out) {
+  const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
   const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
@@ -383,7 +389,7 @@ k2_post_s(const float* __restrict__ x, const float* __restrict__ eps, const floa
   const int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, n);
   for (int64_t i = beg + threadIdx.x; i < end; i += kThreads) {
     const int64_t j = l * n + i;
-    const float x0 = tweedie(x[j], eps[j], s1, sa);
+    const float x0 = tweedie(x[j], eps[j], tc);
     float m = __fadd_rn(__fmul_rn(c_ell, x[j]), __fmul_rn(c_s, x0));
     if (HAS_Z) m = __fadd_rn(m, __fmul_rn(sd, z[j]));
     const float g = __fadd_rn(cot[j], __fmul_rn(-s1, vjp[j]));
@@ -422,6 +428,7 @@ template <int V>
 __global__ void __launch_bounds__(kThreads)
 k_tweedie_final(const float* __restrict__ x, const float* __restrict__ eps, int64_t L, int64_t n, float sa,
                 float s1, float* __restrict__ x0, float* __restrict__ sum, float* __restrict__ sumsq) {
+  const TweedieC tc = make_tc(s1, sa);
   const int64_t nv = n / V;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -440,7 +447,7 @@ k_tweedie_final(const float* __restrict__ x, const float* __restrict__ eps, int6
       }
 #pragma unroll
       for (int c = 0; c < V; ++c) {
-        o[c] = tweedie(xv[c], ev[c], s1, sa);
+        o[c] = tweedie(xv[c], ev[c], tc);
         s[c] += o[c];
         q[c] = fmaf(o[c], o[c], q[c]);
       }
@@ -462,16 +469,17 @@ k_tweedie_final(const float* __restrict__ x, const float* __restrict__ eps, int6
 __global__ void __launch_bounds__(kThreads)
 k_tweedie_flat(const float* __restrict__ x, const float* __restrict__ eps, int64_t total, float sa, float s1,
                float* __restrict__ x0) {
+  const TweedieC tc = make_tc(s1, sa);
   const int64_t t4 = total >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t4;
        i += (int64_t)gridDim.x * blockDim.x) {
     float4 a = ld_stream4(x + 4 * i), b = ld_stream4(eps + 4 * i), o;
-    o.x = tweedie(a.x, b.x, s1, sa); o.y = tweedie(a.y, b.y, s1, sa);
-    o.z = tweedie(a.z, b.z, s1, sa); o.w = tweedie(a.w, b.w, s1, sa);
+    o.x = tweedie(a.x, b.x, tc); o.y = tweedie(a.y, b.y, tc);
+    o.z = tweedie(a.z, b.z, tc); o.w = tweedie(a.w, b.w, tc);
     st_stream4(x0 + 4 * i, o);
   }
   if (blockIdx.x == 0)
-    for (int64_t i = (t4 << 2) + threadIdx.x; i < total; i += blockDim.x) x0[i] = tweedie(x[i], eps[i], s1, sa);
+    for (int64_t i = (t4 << 2) + threadIdx.x; i < total; i += blockDim.x) x0[i] = tweedie(x[i], eps[i], tc);
 }
 
 int launch_tweedie(const float* x, const float* eps, int64_t L, int64_t n, float sa, float s1, float* x0,
