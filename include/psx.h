@@ -148,6 +148,22 @@ PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_
                  float c_s, float std, float gamma, float* d_x_next, float* d_err_out,
                  void* stream);
 
+/* ------------------------------------------------------------- latent samplers (PSLD)
+ * psx_bridge_update -- bridge (DDIM/DDPM) update with an additive correction, the tail of a PSLD step:
+ *   x_next = c_ell*x + c_s*x0 + std*z + grad_scale*grad,   x0 = (x - s1*eps)/sa
+ * Replaces samplers/samplers/psld.py:144-153 (ddim_step(..., e_t=z0) followed by `z_t - gradient`:
+ * grad_scale = -1) and bridge_kernels.py:41,44-45,59.  d_z may be NULL when std == 0; d_grad may be
+ * NULL when grad_scale == 0 (plain ddim_step).  d_x_next may alias d_x.
+ */
+PSX_API int psx_bridge_update(const float* d_x, const float* d_eps, const float* d_z, const float* d_grad,
+                              int64_t numel, float sqrt_acp, float sqrt_1m_acp, float c_ell, float c_s,
+                              float std, float grad_scale, float* d_x_next, void* stream);
+
+/* psx_lincomb3 -- out = ca*a + cb*b + cc*c elementwise (c may be NULL).  Glue of the PSLD pixel-space
+ * block around psx_dps_pre: x_eff = x0 + A^T(y - A x0) (psld.py:132-136) and its cotangent. */
+PSX_API int psx_lincomb3(const float* d_a, float ca, const float* d_b, float cb, const float* d_c, float cc,
+                         float* d_out, int64_t numel, void* stream);
+
 /* ------------------------------------------------------------- final estimate
  * psx_tweedie -- x0 = (x_t - s1*eps)/sa (dps.py:125-126), written straight into
  * the caller's gather slot, optionally accumulating the per-pixel sum and sum

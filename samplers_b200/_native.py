@@ -45,6 +45,8 @@ PROTOTYPES = {
     "psx_dps_post": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64,
                                _f, _f, _f, _f, _f, _f, _f32p, _f32p, _vp]),
     "psx_tweedie": (C.c_int, [_f32p, _f32p, _i64, _i64, _f, _f, _f32p, _f32p, _f32p, _vp]),
+    "psx_bridge_update": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, _f, _f32p, _vp]),
+    "psx_lincomb3": (C.c_int, [_f32p, _f, _f32p, _f, _f32p, _f, _f32p, _i64, _vp]),
 }
 
 
@@ -235,4 +237,21 @@ def tweedie(x_t, eps, sa: float, s1: float, x0, total=None, total_sq=None) -> No
     with torch.cuda.device(x_t.device):
         check(load().psx_tweedie(x_t.data_ptr(), eps.data_ptr(), L, n, sa, s1, x0.data_ptr(),
                                  ptr(total), ptr(total_sq), stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def bridge_update(x, eps, z, grad, sa: float, s1: float, c_ell: float, c_s: float, std: float,
+                  grad_scale: float, x_next) -> None:
+    global launch_count
+    with torch.cuda.device(x.device):
+        check(load().psx_bridge_update(x.data_ptr(), eps.data_ptr(), ptr(z), ptr(grad), x.numel(), sa, s1, c_ell,
+                                       c_s, std, grad_scale, x_next.data_ptr(), stream_ptr(x.device)))
+    launch_count += 1
+
+
+def lincomb3(a, ca: float, b, cb: float, c, cc: float, out) -> None:
+    global launch_count
+    with torch.cuda.device(a.device):
+        check(load().psx_lincomb3(a.data_ptr(), ca, b.data_ptr(), cb, ptr(c), cc, out.data_ptr(), a.numel(),
+                                  stream_ptr(a.device)))
     launch_count += 1

@@ -30,6 +30,9 @@ int launch_post(const float*, const float*, const float*, const float*, const fl
 int launch_tweedie(const float*, const float*, int64_t, int64_t, float, float, float*, float*, float*,
                    cudaStream_t);
 int launch_gather(bool, const float*, const int64_t*, float*, int64_t, int64_t, int64_t, cudaStream_t);
+int launch_bridge_update(const float*, const float*, const float*, const float*, int64_t, float, float, float,
+                         float, float, float, float*, cudaStream_t);
+int launch_lincomb3(const float*, float, const float*, float, const float*, float, float*, int64_t, cudaStream_t);
 
 // Taps whose magnitude is below 2^-30 of the largest tap are dropped at the two ends: their total
 // contribution (<= k * 2^-30 * max|w| * max|x|) is far below half an fp32 ulp of the result.
@@ -246,6 +249,26 @@ PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_
   return launch_post(d_x_t, d_eps, d_cot, d_vjp, std_ == 0.f ? nullptr : d_z, d_err_part, err_parts, L, n,
                      sqrt_acp, sqrt_1m_acp, c_ell, c_s, std_, gamma, d_x_next, d_err_out,
                      (cudaStream_t)stream);
+}
+
+PSX_API int psx_bridge_update(const float* d_x, const float* d_eps, const float* d_z, const float* d_grad,
+                              int64_t numel, float sqrt_acp, float sqrt_1m_acp, float c_ell, float c_s,
+                              float std_, float grad_scale, float* d_x_next, void* stream) {
+  PSX_REQUIRE(d_x && d_eps && d_x_next && numel > 0, "psx_bridge_update: null pointer or empty tensor");
+  PSX_REQUIRE(d_z || std_ == 0.f, "psx_bridge_update: d_z may be NULL only when std == 0");
+  PSX_REQUIRE(d_grad || grad_scale == 0.f, "psx_bridge_update: d_grad may be NULL only when grad_scale == 0");
+  PSX_REQUIRE(sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(c_ell) && std::isfinite(c_s) &&
+                  std::isfinite(std_) && std::isfinite(grad_scale),
+              "psx_bridge_update: non-finite scalar");
+  return launch_bridge_update(d_x, d_eps, std_ == 0.f ? nullptr : d_z, grad_scale == 0.f ? nullptr : d_grad,
+                              numel, sqrt_acp, sqrt_1m_acp, c_ell, c_s, std_, grad_scale, d_x_next,
+                              (cudaStream_t)stream);
+}
+
+PSX_API int psx_lincomb3(const float* d_a, float ca, const float* d_b, float cb, const float* d_c, float cc,
+                         float* d_out, int64_t numel, void* stream) {
+  PSX_REQUIRE(d_a && d_b && d_out && numel > 0, "psx_lincomb3: null pointer or empty tensor");
+  return launch_lincomb3(d_a, ca, d_b, cb, d_c, cc, d_out, numel, (cudaStream_t)stream);
 }
 
 PSX_API int psx_tweedie(const float* d_x_t, const float* d_eps, int64_t L, int64_t n, float sqrt_acp,

@@ -449,12 +449,19 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
         const float4 v = *reinterpret_cast<const float4*>(row + 2 * m);
         win[2 * m] = make_float2(v.x, v.y); win[2 * m + 1] = make_float2(v.z, v.w);
       }
+      // software pipeline: the window of chunk c+1 is fetched before the 64 FFMA2 of chunk c issue
+      // (comp has >= 8 zero columns of slack beyond the last chunk: pitch2 >= W + k + 2, reads stay in the row)
+      float4 nx[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) nx[m] = *reinterpret_cast<const float4*>(row + 8 + 2 * m);
       for (int c = 0; c < taps.k; c += 8) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const float4 v = *reinterpret_cast<const float4*>(row + c + 8 + 2 * m);
-          win[8 + 2 * m] = make_float2(v.x, v.y); win[9 + 2 * m] = make_float2(v.z, v.w);
+          win[8 + 2 * m] = make_float2(nx[m].x, nx[m].y); win[9 + 2 * m] = make_float2(nx[m].z, nx[m].w);
         }
+#pragma unroll
+        for (int m = 0; m < 4; ++m)  // unconditional (a guard here would cost the uniform datapath); the
+          nx[m] = *reinterpret_cast<const float4*>(row + c + 16 + 2 * m);  // last fetch is unused slack
         fma2_block(acc, win, taps.ww + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
@@ -497,9 +504,9 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
   constexpr int TC = kColTC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw + kPipeHdr);
-  const int rowsA = H + tf.k, rowsB = H + ta.k;
+  const int rowsA = H + tf.k;
   const int stage_floats = rowsA * TC;
-  float* bufB = smem + 2 * (size_t)stage_floats;  // RESIDUAL only
+  float* bufB = smem + 2 * (size_t)stage_floats;  // RESIDUAL only, (H + ta.k) rows
 
   {  // zero the halo rows once (8 float4 per row): stage rows outside [-lo, -lo + H), same for bufB
 #pragma unroll
@@ -567,9 +574,15 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
         acc[j] = make_float2(0.f, 0.f);
         win[j] = *reinterpret_cast<const float2*>(col + j * TC);
       }
+      float2 nx[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) nx[j] = *reinterpret_cast<const float2*>(col + (8 + j) * TC);
       for (int k = 0; k < tf.k; k += 8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) win[8 + j] = *reinterpret_cast<const float2*>(col + (k + 8 + j) * TC);
+        for (int j = 0; j < 8; ++j) win[8 + j] = nx[j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // unconditional; the last fetch lands in the 8 slack rows, unused
+          nx[j] = *reinterpret_cast<const float2*>(col + (k + 16 + j) * TC);
         fma2_block(acc, win, tf.ww + k);
 #pragma unroll
         for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
@@ -602,9 +615,14 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
           acc[j] = make_float2(0.f, 0.f);
           win[j] = *reinterpret_cast<const float2*>(col + j * TC);
         }
+        float2 nx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nx[j] = *reinterpret_cast<const float2*>(col + (8 + j) * TC);
         for (int k = 0; k < ta.k; k += 8) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) win[8 + j] = *reinterpret_cast<const float2*>(col + (k + 8 + j) * TC);
+          for (int j = 0; j < 8; ++j) win[8 + j] = nx[j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) nx[j] = *reinterpret_cast<const float2*>(col + (k + 16 + j) * TC);
           fma2_block(acc, win, ta.ww + k);
 #pragma unroll
           for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
@@ -691,7 +709,7 @@ static int run_rows(const psx_op* op, const Taps& t, const float* in, const floa
     const int pitch2 = row_pitch2(op->W + t.k);
     const int arrays = MODE == ROWS_TWEEDIE ? 2 : 1;
     const size_t smem = kPipeHdr + (size_t)(kPipeRows / 2) * pitch2 * sizeof(float2) +
-                        (size_t)2 * arrays * kPipeRows * op->W * sizeof(float);
+                        (size_t)2 * arrays * kPipeRows * op->W * sizeof(float);  // raw stages double as read slack
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(conv_rows_pipe<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -729,7 +747,8 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
                     float* out, float* err_part, int64_t planes, int64_t obs_repeat, cudaStream_t st) {
   {
     const size_t stage = ((size_t)op->H + tf.k) * kColTC * sizeof(float);
-    const size_t smem_pipe = kPipeHdr + 2 * stage + (RESIDUAL ? ((size_t)op->H + ta.k) * kColTC * sizeof(float) : 0);
+    const size_t smem_pipe = kPipeHdr + 2 * stage + (RESIDUAL ? ((size_t)op->H + ta.k) * kColTC * sizeof(float) : 0) +
+                             8 * kColTC * sizeof(float);  // 8 slack rows for the unconditional window prefetch
     CUtensorMap map;
     if ((op->W % kColTC) == 0 && (op->H % 16) == 0 && op->H <= 256 && !getenv("PSX_NO_PIPE") &&
         make_strip_map(&map, in, planes * op->H, op->W, op->H)) {

@@ -499,6 +499,89 @@ int launch_tweedie(const float* x, const float* eps, int64_t L, int64_t n, float
   return check_cuda(cudaGetLastError(), "tweedie launch");
 }
 
+// =========================================================================== PSLD tail + glue
+template <bool HAS_Z, bool HAS_G>
+__global__ void __launch_bounds__(kThreads)
+k_bridge_update(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z,
+                const float* __restrict__ grad, int64_t total, float sa, float s1, float c_ell, float c_s,
+                float sd, float gs, float* __restrict__ x_next) {
+  const TweedieC tc = make_tc(s1, sa);
+  const int64_t t4 = total >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 xv = ld_stream4(x + 4 * i), ev = ld_stream4(eps + 4 * i);
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), gv = zv, o;
+    if (HAS_Z) zv = ld_stream4(z + 4 * i);
+    if (HAS_G) gv = ld_stream4(grad + 4 * i);
+#define PSX_BU(c)                                                                       \
+  {                                                                                     \
+    const float x0 = tweedie(xv.c, ev.c, tc);                                           \
+    float m = __fadd_rn(__fmul_rn(c_ell, xv.c), __fmul_rn(c_s, x0));                    \
+    if (HAS_Z) m = __fadd_rn(m, __fmul_rn(sd, zv.c));                                   \
+    if (HAS_G) m = __fadd_rn(m, __fmul_rn(gs, gv.c));                                   \
+    o.c = m;                                                                            \
+  }
+    PSX_BU(x) PSX_BU(y) PSX_BU(z) PSX_BU(w)
+    st_stream4(x_next + 4 * i, o);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (t4 << 2) + threadIdx.x; i < total; i += blockDim.x) {
+      const float x0 = tweedie(x[i], eps[i], tc);
+      float m = __fadd_rn(__fmul_rn(c_ell, x[i]), __fmul_rn(c_s, x0));
+      if (HAS_Z) m = __fadd_rn(m, __fmul_rn(sd, z[i]));
+      if (HAS_G) m = __fadd_rn(m, __fmul_rn(gs, grad[i]));
+      x_next[i] = m;
+    }
+#undef PSX_BU
+}
+
+int launch_bridge_update(const float* x, const float* eps, const float* z, const float* grad, int64_t total,
+                         float sa, float s1, float c_ell, float c_s, float sd, float gs, float* x_next,
+                         cudaStream_t st) {
+  int blocks = ceil_div(total / 4 + 1, kThreads);
+  blocks = blocks > sm_count() * 8 ? sm_count() * 8 : blocks;
+  const bool hz = z != nullptr, hg = grad != nullptr;
+#define PSX_GO(Z, G) \
+  k_bridge_update<Z, G><<<blocks, kThreads, 0, st>>>(x, eps, z, grad, total, sa, s1, c_ell, c_s, sd, gs, x_next)
+  if (hz && hg) PSX_GO(true, true); else if (hz) PSX_GO(true, false); else if (hg) PSX_GO(false, true);
+  else PSX_GO(false, false);
+#undef PSX_GO
+  return check_cuda(cudaGetLastError(), "bridge_update launch");
+}
+
+template <bool HAS_C>
+__global__ void __launch_bounds__(kThreads)
+k_lincomb3(const float* __restrict__ a, float ca, const float* __restrict__ b, float cb,
+           const float* __restrict__ c, float cc, float* __restrict__ out, int64_t total) {
+  const int64_t t4 = total >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 av = ld_stream4(a + 4 * i), bv = ld_stream4(b + 4 * i);
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(ca, av.x), __fmul_rn(cb, bv.x)); o.y = __fadd_rn(__fmul_rn(ca, av.y), __fmul_rn(cb, bv.y));
+    o.z = __fadd_rn(__fmul_rn(ca, av.z), __fmul_rn(cb, bv.z)); o.w = __fadd_rn(__fmul_rn(ca, av.w), __fmul_rn(cb, bv.w));
+    if (HAS_C) {
+      const float4 cv = ld_stream4(c + 4 * i);
+      o.x = __fadd_rn(o.x, __fmul_rn(cc, cv.x)); o.y = __fadd_rn(o.y, __fmul_rn(cc, cv.y));
+      o.z = __fadd_rn(o.z, __fmul_rn(cc, cv.z)); o.w = __fadd_rn(o.w, __fmul_rn(cc, cv.w));
+    }
+    st_stream4(out + 4 * i, o);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (t4 << 2) + threadIdx.x; i < total; i += blockDim.x) {
+      float o = __fadd_rn(__fmul_rn(ca, a[i]), __fmul_rn(cb, b[i]));
+      if (HAS_C) o = __fadd_rn(o, __fmul_rn(cc, c[i]));
+      out[i] = o;
+    }
+}
+
+int launch_lincomb3(const float* a, float ca, const float* b, float cb, const float* c, float cc, float* out,
+                    int64_t total, cudaStream_t st) {
+  int blocks = ceil_div(total / 4 + 1, kThreads);
+  blocks = blocks > sm_count() * 8 ? sm_count() * 8 : blocks;
+  if (c) k_lincomb3<true><<<blocks, kThreads, 0, st>>>(a, ca, b, cb, c, cc, out, total);
+  else k_lincomb3<false><<<blocks, kThreads, 0, st>>>(a, ca, b, cb, c, cc, out, total);
+  return check_cuda(cudaGetLastError(), "lincomb3 launch");
+}
+
 // =========================================================================== stand-alone operators
 __global__ void __launch_bounds__(kThreads)
 k_mask_apply(const float* __restrict__ in, const uint8_t* __restrict__ keep, float* __restrict__ out,

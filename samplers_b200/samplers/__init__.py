@@ -1,4 +1,5 @@
 from .base import PosteriorSampler
 from .dps import DPSRun, DPSSampler
+from .psld import PSLDSampler
 
-__all__ = ["PosteriorSampler", "DPSSampler", "DPSRun"]
+__all__ = ["PosteriorSampler", "DPSSampler", "PSLDSampler", "DPSRun"]

@@ -123,3 +123,103 @@ def make_problem(g: "Golden", device):
     nk, nparam = g.meta["noise"]
     noise = GaussianNoise(sigma=nparam) if nk == "gaussian" else PoissonNoise(rate=nparam)
     return InverseProblem(operator=op.to(device), observation=g["y"].to(device), noise=noise)
+
+
+# --------------------------------------------------------------------------- PSLD fixtures
+def psld_names():
+    return sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "psld_*.npz")))
+
+
+class PsldGolden:
+    def __init__(self, name: str):
+        z = np.load(os.path.join(GOLDEN_DIR, f"psld_{name}.npz"))
+        self.meta = json.loads(bytes(z["meta"]).decode())
+        self.a = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+
+    def __getitem__(self, k):
+        return self.a[k]
+
+    @property
+    def K(self):
+        return len(self.meta["t"])
+
+    @property
+    def L(self):
+        return self.meta["L"]
+
+    @property
+    def shape(self):
+        return tuple(self.meta["shape"])
+
+    def core(self, device="cpu"):
+        from oracle.tiny_latent_net import TinyLatentCore
+        core = TinyLatentCore(channels=self.shape[0])
+        core.load_state_dict({k[4:]: v for k, v in self.a.items() if k.startswith("net.")})
+        return core.to(device)
+
+    def oracle_op(self):
+        spec = self.meta["op"]
+        if spec[0] == "identity":
+            return oops.OracleIdentity(self.shape)
+        if spec[0] == "gblur":
+            return oops.OracleSeparableBlur(self.shape, self.a["taps"])
+        if spec[0] == "box":
+            return oops.OracleBoxDownsample(self.shape, spec[1])
+        raise ValueError(spec)
+
+    def y_flat(self, op):
+        """psld.py:111 -- observation tiled over reconstructions, flat."""
+        y, R = self.a["y"], self.meta["R"]
+        nb = len(self.meta["batch"])
+        y = y.reshape(-1, *op.y_shape) if nb else y.unsqueeze(0)
+        return y.repeat_interleave(R, dim=0)
+
+
+def make_latent_network(g: "PsldGolden", device):
+    from samplers_b200.networks.base import LatentEpsilonNetwork
+
+    class GoldenLatentNetwork(LatentEpsilonNetwork):
+        def __init__(self, core, acp, ts):
+            super().__init__(alphas_cumprod=acp)
+            self.core, self._ts = core, ts
+
+        def forward(self, x, t):
+            return self.core.eps(x, int(t))
+
+        @classmethod
+        def from_pretrained(cls, *a, **k):
+            raise NotImplementedError
+
+        def set_sampling_parameters(self, num_sampling_steps, batch_size=1, num_reconstructions=1):
+            self._batch_size, self._num_sampling_steps = batch_size, num_sampling_steps
+            self._num_reconstructions = num_reconstructions
+            self.register_buffer("timesteps", self._ts.to(self.alphas_cumprod.device))
+
+        @property
+        def is_condition_initialized(self):
+            return True
+
+        def get_latent_shape(self, x_shape):
+            return (4, x_shape[1] // 2, x_shape[2] // 2)
+
+        def _decode(self, z, *, differentiable=False):
+            return self.core.decode(z)
+
+        def _encode(self, x, *, differentiable=False):
+            return self.core.encode(x)
+
+    return GoldenLatentNetwork(g.core(), g["acp"].clone(), g["timesteps"].clone()).to(device)
+
+
+def make_psld_problem(g: "PsldGolden", device):
+    from samplers_b200 import operators as pops
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.noise import GaussianNoise
+    spec, shape = g.meta["op"], g.shape
+    if spec[0] == "identity":
+        op = pops.IdentityOperator(shape)
+    elif spec[0] == "gblur":
+        op = pops.SeparableBlurOperator(shape, g["taps"])
+    else:
+        op = pops.BoxDownsampleOperator(shape, spec[1])
+    return InverseProblem(operator=op.to(device), observation=g["y"].to(device), noise=GaussianNoise(sigma=g.meta["sigma"]))

@@ -1,0 +1,94 @@
+"""PSLD on the CUDA path vs recordings of the unmodified reference PSLDSampler (tests/golden/psld_*.npz)."""
+import pytest
+import torch
+
+from tests._golden import PsldGolden, make_latent_network, make_psld_problem, psld_names, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("name", psld_names())
+def test_psld_full_run_matches_reference(name):
+    from samplers_b200.samplers import PSLDSampler
+    g = PsldGolden(name)
+    m = g.meta
+    net, prob = make_latent_network(g, DEV), make_psld_problem(g, DEV)
+    draws = iter([g["z_init"]] + [g["noise"][k] for k in range(g.K)])
+    s = PSLDSampler(net)
+    s.draw = lambda shape, device, dtype: next(draws).to(device)
+    out = s(prob, num_sampling_steps=m["steps"], num_reconstructions=m["R"], gamma=m["gamma"], omega=m["omega"],
+            eta=m["eta"]).cpu()
+    assert out.shape == g["x_out"].shape
+    assert rel_err(out, g["x_out"]) < 1e-4
+    assert not net.are_sampling_parameters_initialized
+    lat = PSLDSampler(net)
+    lat.draw = lambda shape, device, dtype: torch.zeros(shape, device=device, dtype=dtype)
+    z = lat(prob, num_sampling_steps=4, decode_output=False)
+    assert z.shape == (*m["batch"], 1, *m["latent_shape"])
+
+
+@pytest.mark.parametrize("name", psld_names())
+def test_psld_data_term_forward_backward(name):
+    """The fused pixel-space block (K1-based autograd node) vs the oracle's torch expression."""
+    from samplers_b200.samplers.psld import _PsldDataTerm
+    g = PsldGolden(name)
+    op_o = g.oracle_op()
+    prob = make_psld_problem(g, DEV)
+    nat = prob.operator._native_cached(torch.device(DEV))
+    L = g.L
+    y_flat = g.y_flat(op_o)
+    y_dev = prob.operator._dense_observation(prob.observation.float())
+    obs_repeat = g.meta["R"] if len(g.meta["batch"]) else L
+    gen = torch.Generator().manual_seed(0)
+    x0 = torch.randn(L, *g.shape, generator=gen)
+    c_x = torch.randn(L, *g.shape, generator=gen)
+    # oracle
+    xo = x0.clone().requires_grad_()
+    hx = op_o.apply(xo)
+    lik_o = torch.norm(y_flat - hx)
+    xeff_o = op_o.adjoint(y_flat) + xo - op_o.adjoint(hx)
+    (go,) = torch.autograd.grad(0.3 * lik_o + (xeff_o * c_x).sum(), xo)
+    # product
+    xd = x0.reshape(L, -1).to(DEV).requires_grad_()
+    wsb = nat.workspace_bytes(L)
+    ws = torch.empty(wsb // 4, device=DEV) if wsb else None
+    zeros_y = torch.zeros(1, nat.n_y, device=DEV)
+    lik, xeff = _PsldDataTerm.apply(xd, nat, y_dev, obs_repeat, ws, zeros_y)
+    (gd,) = torch.autograd.grad(0.3 * lik + (xeff * c_x.reshape(L, -1).to(DEV)).sum(), xd)
+    assert abs(float(lik) - float(lik_o)) < 1e-5 * float(lik_o)
+    assert rel_err(xeff.detach().cpu(), xeff_o.detach().reshape(L, -1)) < 2e-6
+    assert rel_err(gd.cpu(), go.reshape(L, -1)) < 1e-5
+
+
+def test_psld_requires_latent_network():
+    from samplers_b200.samplers import PSLDSampler
+    from tests._golden import Golden, make_network
+    with pytest.raises(TypeError):
+        PSLDSampler(make_network(Golden("identity_gauss"), DEV))
+
+
+def test_bridge_update_and_lincomb_kernels():
+    from oracle import dps as odps
+    from samplers_b200 import _native
+    gen = torch.Generator().manual_seed(1)
+    x, e, z, g = (torch.randn(3, 1001, generator=gen) for _ in range(4))
+    acp = torch.tensor([1.0, 0.9, 0.6, 0.3])
+    c_ell, c_s, std = odps.bridge_coefficients(acp, 3, 2, 0, 0.7)
+    ref = (c_ell * x + c_s * odps.tweedie_x0(x, e, acp[3])).float() + std.float() * z - g
+    out = torch.empty(3, 1001, device=DEV)
+    _native.bridge_update(x.to(DEV), e.to(DEV), z.to(DEV), g.to(DEV), float(acp[3] ** 0.5), float((1 - acp[3]) ** 0.5),
+                          float(c_ell.float()), float(c_s.float()), float(std.float()), -1.0, out)
+    assert rel_err(out.cpu(), ref) < 1e-6
+    out2 = torch.empty(3, 1001, device=DEV)
+    _native.lincomb3(x.to(DEV), 2.0, e.to(DEV), -0.5, z.to(DEV), 0.25, out2)
+    assert torch.allclose(out2.cpu(), 2.0 * x - 0.5 * e + 0.25 * z, atol=1e-6)
