@@ -164,6 +164,40 @@ PSX_API int psx_bridge_update(const float* d_x, const float* d_eps, const float*
 PSX_API int psx_lincomb3(const float* d_a, float ca, const float* d_b, float cb, const float* d_c, float cc,
                          float* d_out, int64_t numel, void* stream);
 
+/* ------------------------------------------------------------- ReSample
+ * psx_ddim_eps_step -- DDIM update in the eps parameterisation (bridge_kernels.py:82-115), three outputs:
+ *   pred_x0   = (x - sqrt_oma*eps) / sqrt_a_t
+ *   pseudo_x0 = (x - oma*eps)      / sqrt_a_t            (oma = 1 - acp_t)
+ *   x_prev    = sqrt_a_p*pred_x0 + dir*eps + sigma_t*z
+ * The six scalars are evaluated by the caller in fp32 exactly as the reference does (0-dim tensor ops).
+ * d_z may be NULL when sigma_t == 0; d_pred_x0 / d_pseudo_x0 may be NULL.
+ */
+PSX_API int psx_ddim_eps_step(const float* d_x, const float* d_eps, const float* d_z, int64_t numel,
+                              float sqrt_a_t, float sqrt_oma, float oma, float sqrt_a_p, float dir,
+                              float sigma_t, float* d_x_prev, float* d_pred_x0, float* d_pseudo_x0,
+                              void* stream);
+
+/* psx_stochastic_resample (resample_kernels.py:96-107):
+ *   out = (c_p*pseudo_x0 + c_x*x_t) / den + k_n*noise
+ * with c_p = sigma*sqrt(a), c_x = 1 - a, den = sigma + 1 - a, k_n = sqrt(1/(1/sigma + 1/(1-a))). */
+PSX_API int psx_stochastic_resample(const float* d_pseudo_x0, const float* d_x_t, const float* d_noise,
+                                    int64_t numel, float c_p, float c_x, float den, float k_n, float* d_out,
+                                    void* stream);
+
+/* psx_adamw_step -- one fused AdamW update (torch.optim.AdamW defaults' arithmetic: decoupled weight
+ * decay, lerp first moment, bias-corrected step), used by the hard-consistency optimisers
+ * (resample_kernels.py:32-54 pixel space, :57-93 latent space).  `step` is 1-based.
+ * Optional on-device early stop for the pixel-space loop (no host sync per iteration):
+ *   d_flags: int32[2] or NULL.  If d_flags[flag_in] != 0 the call is a no-op and sets d_flags[1-flag_in];
+ *   otherwise the update is applied and d_flags[1-flag_in] = (sum(d_loss_parts[0..n_loss_parts)) *
+ *   loss_scale < loss_threshold)  -- the reference's `if loss.item() < eps**2: break` evaluated after
+ *   the step of the same iteration.
+ */
+PSX_API int psx_adamw_step(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t numel, float lr,
+                           float beta1, float beta2, float adam_eps, float weight_decay, int step,
+                           int* d_flags, int flag_in, const float* d_loss_parts, int64_t n_loss_parts,
+                           float loss_scale, float loss_threshold, void* stream);
+
 /* ------------------------------------------------------------- final estimate
  * psx_tweedie -- x0 = (x_t - s1*eps)/sa (dps.py:125-126), written straight into
  * the caller's gather slot, optionally accumulating the per-pixel sum and sum

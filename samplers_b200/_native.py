@@ -47,6 +47,10 @@ PROTOTYPES = {
     "psx_tweedie": (C.c_int, [_f32p, _f32p, _i64, _i64, _f, _f, _f32p, _f32p, _f32p, _vp]),
     "psx_bridge_update": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, _f, _f32p, _vp]),
     "psx_lincomb3": (C.c_int, [_f32p, _f, _f32p, _f, _f32p, _f, _f32p, _i64, _vp]),
+    "psx_ddim_eps_step": (C.c_int, [_f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, _f, _f32p, _f32p, _f32p, _vp]),
+    "psx_stochastic_resample": (C.c_int, [_f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f32p, _vp]),
+    "psx_adamw_step": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, C.c_int, _vp, C.c_int,
+                                 _f32p, _i64, _f, _f, _vp]),
 }
 
 
@@ -254,4 +258,32 @@ def lincomb3(a, ca: float, b, cb: float, c, cc: float, out) -> None:
     with torch.cuda.device(a.device):
         check(load().psx_lincomb3(a.data_ptr(), ca, b.data_ptr(), cb, ptr(c), cc, out.data_ptr(), a.numel(),
                                   stream_ptr(a.device)))
+    launch_count += 1
+
+
+def ddim_eps_step(x, eps, z, sc: dict, x_prev, pred_x0=None, pseudo_x0=None) -> None:
+    global launch_count
+    with torch.cuda.device(x.device):
+        check(load().psx_ddim_eps_step(x.data_ptr(), eps.data_ptr(), ptr(z), x.numel(), sc["sqrt_a_t"], sc["sqrt_oma"],
+                                       sc["oma"], sc["sqrt_a_p"], sc["dir"], sc["sigma_t"], x_prev.data_ptr(),
+                                       ptr(pred_x0), ptr(pseudo_x0), stream_ptr(x.device)))
+    launch_count += 1
+
+
+def stochastic_resample(pseudo_x0, x_t, noise, c_p: float, c_x: float, den: float, k_n: float, out) -> None:
+    global launch_count
+    with torch.cuda.device(x_t.device):
+        check(load().psx_stochastic_resample(pseudo_x0.data_ptr(), x_t.data_ptr(), noise.data_ptr(), x_t.numel(),
+                                             c_p, c_x, den, k_n, out.data_ptr(), stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def adamw_step(param, grad, m, v, lr: float, step: int, *, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2,
+               flags=None, flag_in=0, loss_parts=None, loss_scale=0.0, loss_threshold=0.0) -> None:
+    global launch_count
+    with torch.cuda.device(param.device):
+        check(load().psx_adamw_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(), lr,
+                                    beta1, beta2, eps, weight_decay, step, ptr(flags), flag_in, ptr(loss_parts),
+                                    0 if loss_parts is None else loss_parts.numel(), loss_scale, loss_threshold,
+                                    stream_ptr(param.device)))
     launch_count += 1

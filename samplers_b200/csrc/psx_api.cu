@@ -33,6 +33,12 @@ int launch_gather(bool, const float*, const int64_t*, float*, int64_t, int64_t, 
 int launch_bridge_update(const float*, const float*, const float*, const float*, int64_t, float, float, float,
                          float, float, float, float*, cudaStream_t);
 int launch_lincomb3(const float*, float, const float*, float, const float*, float, float*, int64_t, cudaStream_t);
+int launch_ddim_eps(const float*, const float*, const float*, int64_t, float, float, float, float, float, float,
+                    float*, float*, float*, cudaStream_t);
+int launch_stoch_resample(const float*, const float*, const float*, int64_t, float, float, float, float, float*,
+                          cudaStream_t);
+int launch_adamw(float*, const float*, float*, float*, int64_t, float, float, float, float, float, int, int*, int,
+                 const float*, int64_t, float, float, cudaStream_t);
 
 // Taps whose magnitude is below 2^-30 of the largest tap are dropped at the two ends: their total
 // contribution (<= k * 2^-30 * max|w| * max|x|) is far below half an fp32 ulp of the result.
@@ -269,6 +275,41 @@ PSX_API int psx_lincomb3(const float* d_a, float ca, const float* d_b, float cb,
                          float* d_out, int64_t numel, void* stream) {
   PSX_REQUIRE(d_a && d_b && d_out && numel > 0, "psx_lincomb3: null pointer or empty tensor");
   return launch_lincomb3(d_a, ca, d_b, cb, d_c, cc, d_out, numel, (cudaStream_t)stream);
+}
+
+PSX_API int psx_ddim_eps_step(const float* d_x, const float* d_eps, const float* d_z, int64_t numel,
+                              float sqrt_a_t, float sqrt_oma, float oma, float sqrt_a_p, float dir,
+                              float sigma_t, float* d_x_prev, float* d_pred_x0, float* d_pseudo_x0,
+                              void* stream) {
+  PSX_REQUIRE(d_x && d_eps && d_x_prev && numel > 0, "psx_ddim_eps_step: null pointer or empty tensor");
+  PSX_REQUIRE(d_z || sigma_t == 0.f, "psx_ddim_eps_step: d_z may be NULL only when sigma_t == 0");
+  PSX_REQUIRE(sqrt_a_t > 0.f && std::isfinite(sqrt_a_t) && std::isfinite(sqrt_oma) && std::isfinite(oma) &&
+                  std::isfinite(sqrt_a_p) && std::isfinite(dir) && std::isfinite(sigma_t),
+              "psx_ddim_eps_step: non-finite scalar");
+  return launch_ddim_eps(d_x, d_eps, sigma_t == 0.f ? nullptr : d_z, numel, sqrt_a_t, sqrt_oma, oma, sqrt_a_p, dir,
+                         sigma_t, d_x_prev, d_pred_x0, d_pseudo_x0, (cudaStream_t)stream);
+}
+
+PSX_API int psx_stochastic_resample(const float* d_pseudo_x0, const float* d_x_t, const float* d_noise,
+                                    int64_t numel, float c_p, float c_x, float den, float k_n, float* d_out,
+                                    void* stream) {
+  PSX_REQUIRE(d_pseudo_x0 && d_x_t && d_noise && d_out && numel > 0, "psx_stochastic_resample: null pointer");
+  PSX_REQUIRE(den != 0.f && std::isfinite(den) && std::isfinite(c_p) && std::isfinite(c_x) && std::isfinite(k_n),
+              "psx_stochastic_resample: bad scalar");
+  return launch_stoch_resample(d_pseudo_x0, d_x_t, d_noise, numel, c_p, c_x, den, k_n, d_out, (cudaStream_t)stream);
+}
+
+PSX_API int psx_adamw_step(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t numel, float lr,
+                           float beta1, float beta2, float adam_eps, float weight_decay, int step,
+                           int* d_flags, int flag_in, const float* d_loss_parts, int64_t n_loss_parts,
+                           float loss_scale, float loss_threshold, void* stream) {
+  PSX_REQUIRE(d_param && d_grad && d_m && d_v && numel > 0, "psx_adamw_step: null pointer or empty tensor");
+  PSX_REQUIRE(step >= 1 && lr > 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f,
+              "psx_adamw_step: bad hyper-parameter");
+  PSX_REQUIRE(!d_flags || ((flag_in == 0 || flag_in == 1) && d_loss_parts && n_loss_parts > 0),
+              "psx_adamw_step: early-stop flags need loss partials");
+  return launch_adamw(d_param, d_grad, d_m, d_v, numel, lr, beta1, beta2, adam_eps, weight_decay, step, d_flags,
+                      flag_in, d_loss_parts, n_loss_parts, loss_scale, loss_threshold, (cudaStream_t)stream);
 }
 
 PSX_API int psx_tweedie(const float* d_x_t, const float* d_eps, int64_t L, int64_t n, float sqrt_acp,

@@ -3,6 +3,8 @@
 //   K2 (bridge update + guidance + injected noise), the final Tweedie estimate,
 //   and the stand-alone forward / adjoint of those operators.
 // Every kernel streams each tensor exactly once with 128-bit accesses.
+#include <cmath>
+
 #include "psx_common.cuh"
 
 namespace psx {
@@ -580,6 +582,104 @@ int launch_lincomb3(const float* a, float ca, const float* b, float cb, const fl
   if (c) k_lincomb3<true><<<blocks, kThreads, 0, st>>>(a, ca, b, cb, c, cc, out, total);
   else k_lincomb3<false><<<blocks, kThreads, 0, st>>>(a, ca, b, cb, c, cc, out, total);
   return check_cuda(cudaGetLastError(), "lincomb3 launch");
+}
+
+// =========================================================================== ReSample kernels
+__device__ __forceinline__ float div_const(float t, float d, float rcp) {  // correctly rounded t / d (see TweedieC)
+  const float q0 = __fmul_rn(t, rcp);
+  return __fmaf_rn(__fmaf_rn(-q0, d, t), rcp, q0);
+}
+
+template <bool HAS_Z>
+__global__ void __launch_bounds__(kThreads)
+k_ddim_eps(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z, int64_t total,
+           float sat, float soma, float oma, float sap, float dir, float sig, float* __restrict__ x_prev,
+           float* __restrict__ pred, float* __restrict__ pseudo) {
+  const float rcp = __frcp_rn(sat);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xv = x[i], ev = eps[i];
+    const float p0 = div_const(__fsub_rn(xv, __fmul_rn(soma, ev)), sat, rcp);
+    const float ps = div_const(__fsub_rn(xv, __fmul_rn(oma, ev)), sat, rcp);
+    float o = __fadd_rn(__fmul_rn(sap, p0), __fmul_rn(dir, ev));
+    if (HAS_Z) o = __fadd_rn(o, __fmul_rn(sig, z[i]));
+    x_prev[i] = o;
+    if (pred) pred[i] = p0;
+    if (pseudo) pseudo[i] = ps;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_stoch_resample(const float* __restrict__ p, const float* __restrict__ xt, const float* __restrict__ nz,
+                 int64_t total, float cp, float cx, float den, float kn, float* __restrict__ out) {
+  const float rcp = __frcp_rn(den);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float num = __fadd_rn(__fmul_rn(cp, p[i]), __fmul_rn(cx, xt[i]));
+    out[i] = __fadd_rn(div_const(num, den, rcp), __fmul_rn(nz[i], kn));
+  }
+}
+
+// AdamW with torch's operation order (torch/optim/adamw.py, single-tensor path):
+//   p *= 1 - lr*wd;  m += (g - m)*(1 - b1);  v = v*b2 + (1 - b2)*g*g
+//   p += -(lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void __launch_bounds__(kThreads)
+k_adamw(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+        int64_t total, float decay, float w1, float b2, float w2, float step_size, float bc2_sqrt, float aeps,
+        int* __restrict__ flags, int flag_in, const float* __restrict__ loss_parts, int64_t n_parts,
+        float loss_scale, float loss_thr) {
+  __shared__ float red[32];
+  if (flags) {
+    if (flags[flag_in]) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) flags[1 - flag_in] = 1;
+      return;
+    }
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    float pi = __fmul_rn(p[i], decay);
+    const float mi = __fadd_rn(m[i], __fmul_rn(__fsub_rn(gi, m[i]), w1));
+    const float vi = __fadd_rn(__fmul_rn(v[i], b2), __fmul_rn(__fmul_rn(w2, gi), gi));
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), aeps);
+    pi = __fadd_rn(pi, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+  if (flags && blockIdx.x == 0) {  // fixed-order sum of the loss partials of THIS iteration
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < n_parts; i += kThreads) acc += loss_parts[i];
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) flags[1 - flag_in] = (__fmul_rn(tot, loss_scale) < loss_thr) ? 1 : 0;
+  }
+}
+
+static int ew_blocks(int64_t total) {
+  int b = ceil_div(total, kThreads);
+  return b > sm_count() * 8 ? sm_count() * 8 : (b < 1 ? 1 : b);
+}
+
+int launch_ddim_eps(const float* x, const float* eps, const float* z, int64_t total, float sat, float soma,
+                    float oma, float sap, float dir, float sig, float* x_prev, float* pred, float* pseudo,
+                    cudaStream_t st) {
+  if (z) k_ddim_eps<true><<<ew_blocks(total), kThreads, 0, st>>>(x, eps, z, total, sat, soma, oma, sap, dir, sig, x_prev, pred, pseudo);
+  else k_ddim_eps<false><<<ew_blocks(total), kThreads, 0, st>>>(x, eps, z, total, sat, soma, oma, sap, dir, sig, x_prev, pred, pseudo);
+  return check_cuda(cudaGetLastError(), "ddim_eps launch");
+}
+
+int launch_stoch_resample(const float* p, const float* xt, const float* nz, int64_t total, float cp, float cx,
+                          float den, float kn, float* out, cudaStream_t st) {
+  k_stoch_resample<<<ew_blocks(total), kThreads, 0, st>>>(p, xt, nz, total, cp, cx, den, kn, out);
+  return check_cuda(cudaGetLastError(), "stochastic_resample launch");
+}
+
+int launch_adamw(float* p, const float* g, float* m, float* v, int64_t total, float lr, float b1, float b2,
+                 float aeps, float wd, int step, int* flags, int flag_in, const float* loss_parts, int64_t n_parts,
+                 float loss_scale, float loss_thr, cudaStream_t st) {
+  // scalar prep in double like Python floats, then rounded once to fp32
+  const double bc1 = 1.0 - std::pow((double)b1, step), bc2 = 1.0 - std::pow((double)b2, step);
+  const float decay = (float)(1.0 - (double)lr * (double)wd);
+  const float w1 = (float)(1.0 - (double)b1), w2 = (float)(1.0 - (double)b2);
+  const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)std::sqrt(bc2);
+  k_adamw<<<ew_blocks(total), kThreads, 0, st>>>(p, g, m, v, total, decay, w1, b2, w2, step_size, bc2_sqrt, aeps,
+                                                 flags, flag_in, loss_parts, n_parts, loss_scale, loss_thr);
+  return check_cuda(cudaGetLastError(), "adamw launch");
 }
 
 // =========================================================================== stand-alone operators

@@ -223,3 +223,39 @@ def make_psld_problem(g: "PsldGolden", device):
     else:
         op = pops.BoxDownsampleOperator(shape, spec[1])
     return InverseProblem(operator=op.to(device), observation=g["y"].to(device), noise=GaussianNoise(sigma=g.meta["sigma"]))
+
+
+# --------------------------------------------------------------------------- ReSample fixtures
+def resample_names():
+    return sorted(os.path.basename(p)[9:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "resample_*.npz")))
+
+
+class ResampleGolden(PsldGolden):
+    def __init__(self, name: str):
+        z = np.load(os.path.join(GOLDEN_DIR, f"resample_{name}.npz"))
+        self.meta = json.loads(bytes(z["meta"]).decode())
+        self.a = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+
+    def eps_threshold(self) -> float:
+        nk, p = self.meta["noise"]
+        return float(torch.tensor(p, dtype=torch.float32)) if nk == "gaussian" else 1e-3
+
+
+def make_resample_problem(g: "ResampleGolden", device):
+    from samplers_b200.noise import GaussianNoise, PoissonNoise
+    prob = make_psld_problem(_SigmaShim(g), device)
+    nk, p = g.meta["noise"]
+    prob.noise = GaussianNoise(sigma=p) if nk == "gaussian" else PoissonNoise(rate=p)
+    return prob
+
+
+class _SigmaShim:
+    """make_psld_problem reads meta['sigma']; ReSample fixtures store the noise as [kind, param]."""
+
+    def __init__(self, g):
+        self._g = g
+        self.meta = dict(g.meta, sigma=0.05)
+        self.shape = g.shape
+
+    def __getitem__(self, k):
+        return self._g[k]
