@@ -141,6 +141,9 @@ PSX_API int psx_dps_pre(const psx_op* op, const float* d_x_t, const float* d_eps
  * c_ell, c_s, std are the fp64 bridge statistics of bridge_kernels.py:28-39
  * rounded to fp32 by the caller.  d_z may be NULL when std == 0.
  * d_err_out (L,) receives |r_l|_2 when not NULL.  d_x_next may alias d_x_t.
+ * Fixed-scale mode (d_err_part = NULL, err_parts = 0): the guidance term is gamma * grad, which is the
+ * PGDM update samplers/samplers/pgdm.py:130-135 with gamma = guidance_weight * sqrt(1 - acp_t) and
+ * d_cot = 2c A^T r / sqrt_acp (c = the operator's pseudo-inverse gain, A^+ = c A^T).
  */
 PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_cot,
                  const float* d_vjp, const float* d_z, const float* d_err_part, int err_parts,

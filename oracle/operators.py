@@ -40,6 +40,9 @@ class OracleOperator:
     def adjoint(self, y: Tensor) -> Tensor:  # (L, *y_shape) -> (L, *x_shape)
         raise NotImplementedError
 
+    def pinv(self, y: Tensor) -> Tensor:  # Moore-Penrose pseudo-inverse, where it has a closed form
+        raise NotImplementedError
+
 
 class OracleIdentity(OracleOperator):
     def __init__(self, x_shape, flatten: bool = False):
@@ -52,6 +55,8 @@ class OracleIdentity(OracleOperator):
 
     def adjoint(self, y):
         return y.reshape(y.shape[0], *self.x_shape)
+
+    pinv = adjoint
 
 
 class OracleMaskGather(OracleOperator):
@@ -74,6 +79,8 @@ class OracleMaskGather(OracleOperator):
         out = torch.zeros(y.shape[0], self.n, dtype=y.dtype, device=y.device)
         out[:, self.kept] = y * 1.0
         return out.reshape(y.shape[0], *self.x_shape)
+
+    pinv = adjoint  # unit singular values (inpainting.py:130)
 
 
 def gaussian_taps(kernel_size: int = 61, sigma: float = 3.0) -> Tensor:
@@ -205,3 +212,7 @@ class OracleBoxDownsample(OracleOperator):
         f = self.factor
         up = y.repeat_interleave(f, dim=-2).repeat_interleave(f, dim=-1)
         return up / float(f * f)
+
+    def pinv(self, y):  # A A^T = I / f^2  =>  A^+ = f^2 A^T = replicate
+        f = self.factor
+        return y.repeat_interleave(f, dim=-2).repeat_interleave(f, dim=-1)

@@ -229,7 +229,8 @@ def dps_post(x_t, eps, cot, vjp, z, err_part, err_parts: int, n: int, sa: float,
     L = x_t.shape[0]
     with torch.cuda.device(x_t.device):
         check(load().psx_dps_post(x_t.data_ptr(), eps.data_ptr(), cot.data_ptr(), vjp.data_ptr(), ptr(z),
-                                  err_part.data_ptr(), err_parts, L, n, sa, s1, c_ell, c_s, std, gamma,
+                                  ptr(err_part), err_parts if err_part is not None else 0, L, n, sa, s1, c_ell,
+                                  c_s, std, gamma,
                                   x_next.data_ptr(), ptr(err_out), stream_ptr(x_t.device)))
     launch_count += 1
 

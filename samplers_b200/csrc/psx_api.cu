@@ -246,8 +246,9 @@ PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_
                  const float* d_z, const float* d_err_part, int err_parts, int64_t L, int64_t n,
                  float sqrt_acp, float sqrt_1m_acp, float c_ell, float c_s, float std_, float gamma,
                  float* d_x_next, float* d_err_out, void* stream) {
-  PSX_REQUIRE(d_x_t && d_eps && d_cot && d_vjp && d_err_part && d_x_next, "psx_dps_post: null pointer");
-  PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts > 0, "psx_dps_post: bad sizes");
+  PSX_REQUIRE(d_x_t && d_eps && d_cot && d_vjp && d_x_next, "psx_dps_post: null pointer");
+  PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts >= 0, "psx_dps_post: bad sizes");
+  PSX_REQUIRE((err_parts > 0) == (d_err_part != nullptr), "psx_dps_post: d_err_part and err_parts must agree");
   PSX_REQUIRE(d_z || std_ == 0.f, "psx_dps_post: d_z may be NULL only when std == 0");
   PSX_REQUIRE(sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(c_ell) && std::isfinite(c_s) &&
                   std::isfinite(std_) && std::isfinite(gamma),

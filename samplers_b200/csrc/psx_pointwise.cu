@@ -332,10 +332,13 @@ k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const flo
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
-  const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
-  const float err = sqrtf(e2);
-  const float scale = __fdiv_rn(gamma, __fadd_rn(err, 1e-9f));
-  if (err_out && blockIdx.x == 0 && threadIdx.x == 0) err_out[l] = err;
+  float scale = gamma;  // err_parts == 0: fixed guidance scale (PGDM); otherwise DPS: gamma / (|r| + 1e-9)
+  if (err_parts > 0) {
+    const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
+    const float err = sqrtf(e2);
+    scale = __fdiv_rn(gamma, __fadd_rn(err, 1e-9f));
+    if (err_out && blockIdx.x == 0 && threadIdx.x == 0) err_out[l] = err;
+  }
 
   const int64_t n4 = n >> 2;
   const int64_t beg = (int64_t)blockIdx.x * chunk4, end = min(beg + chunk4, n4);
@@ -384,10 +387,13 @@ k2_post_s(const float* __restrict__ x, const float* __restrict__ eps, const floa
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
-  const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
-  const float err = sqrtf(e2);
-  const float scale = __fdiv_rn(gamma, __fadd_rn(err, 1e-9f));
-  if (err_out && blockIdx.x == 0 && threadIdx.x == 0) err_out[l] = err;
+  float scale = gamma;  // err_parts == 0: fixed guidance scale (PGDM); otherwise DPS: gamma / (|r| + 1e-9)
+  if (err_parts > 0) {
+    const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
+    const float err = sqrtf(e2);
+    scale = __fdiv_rn(gamma, __fadd_rn(err, 1e-9f));
+    if (err_out && blockIdx.x == 0 && threadIdx.x == 0) err_out[l] = err;
+  }
   const int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, n);
   for (int64_t i = beg + threadIdx.x; i < end; i += kThreads) {
     const int64_t j = l * n + i;

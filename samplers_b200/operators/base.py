@@ -66,6 +66,11 @@ class Operator(torch.nn.Module, ABC):
             self._native_cache[key] = op
         return op
 
+    def _pinv_gain(self) -> float:
+        """c with A^+ = c A^T and A A^T = I / c (identity, inpainting: 1; f x f box: f^2).  Operators
+        without such a pseudo-inverse cannot be used by PGDM."""
+        raise NotImplementedError("Pseudo-inverse not defined for this operator")
+
     def _dense_observation(self, y: Tensor) -> Tensor:
         """Observation as the kernels index it: (num_obs, n_y) contiguous fp32."""
         return y.reshape(-1, _numel(self.y_shape)).contiguous()

@@ -33,5 +33,8 @@ class IdentityOperator(LinearOperator):
 
     apply_pseudo_inverse = apply_transpose
 
+    def _pinv_gain(self) -> float:
+        return 1.0
+
     def _native(self, device):
         return _native.NativeOp.identity(_numel(self.x_shape))

@@ -85,6 +85,9 @@ class InpaintingOperator(LinearOperator):
     def _idx(self, device) -> Tensor:
         return self._kept_indices.to(device).contiguous()
 
+    def _pinv_gain(self) -> float:
+        return 1.0
+
     def _native(self, device):
         keep = (~self.mask).flatten().to(device=device, dtype=torch.uint8).contiguous()
         return _native.NativeOp.mask(keep)

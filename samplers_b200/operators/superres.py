@@ -35,6 +35,9 @@ class BoxDownsampleOperator(LinearOperator):
     def apply_pseudo_inverse(self, y: Tensor) -> Tensor:
         return self.apply_transpose(y) * float(self.factor * self.factor)
 
+    def _pinv_gain(self) -> float:
+        return float(self.factor * self.factor)
+
     def _native(self, device):
         c, h, w = self.x_shape
         return _native.NativeOp.box(c, h, w, self.factor)

@@ -52,7 +52,7 @@ class DPSRun:
     """
 
     def __init__(self, network, inverse_problem: InverseProblem, view: BatchView, gamma: float, eta: float,
-                 draw: Draw):
+                 draw: Draw, weight: float | None = None, fixed_scale=None):
         op, noise = inverse_problem.operator, inverse_problem.noise
         if not isinstance(noise, NoiseModel):
             raise NotImplementedError(f"no fused likelihood for noise model {type(noise).__name__}")
@@ -64,7 +64,9 @@ class DPSRun:
         if self.dtype != torch.float32:
             raise TypeError(f"DPSSampler state is float32; network dtype {self.dtype} is not supported yet")
         self.op = op._native_cached(self.device)
-        self.weight = float(noise._likelihood_weight())
+        # `weight` / `fixed_scale` turn the same two kernels into the PGDM update (see samplers/pgdm.py)
+        self.weight = float(noise._likelihood_weight()) if weight is None else float(weight)
+        self._fixed_scale = fixed_scale
         y = inverse_problem.observation.to(device=self.device, dtype=torch.float32)
         self.y = op._dense_observation(y)                      # (num_obs, n_y)
         self.L, self.n = view.leading_size, self.op.n
@@ -103,8 +105,12 @@ class DPSRun:
             z = self.draw(self.view.flat_shape, self.device, self.dtype)
         if z is not None:
             z = z.reshape(self.L, self.n)
-        _native.dps_post(self.x, eps_flat, self.cot, v, z, self.err_part, self.op.err_parts, self.n,
-                         sc.sqrt_acp, sc.sqrt_1m_acp, sc.c_ell, sc.c_s, sc.std, self.gamma, self.x_next, self.err)
+        if self._fixed_scale is None:
+            _native.dps_post(self.x, eps_flat, self.cot, v, z, self.err_part, self.op.err_parts, self.n,
+                             sc.sqrt_acp, sc.sqrt_1m_acp, sc.c_ell, sc.c_s, sc.std, self.gamma, self.x_next, self.err)
+        else:
+            _native.dps_post(self.x, eps_flat, self.cot, v, z, None, 0, self.n, sc.sqrt_acp, sc.sqrt_1m_acp,
+                             sc.c_ell, sc.c_s, sc.std, self._fixed_scale(sc), self.x_next, None)
         self.x, self.x_next = self.x_next, self.x
 
     def finalize(self, out: Tensor | None = None, total: Tensor | None = None,

@@ -259,3 +259,51 @@ class _SigmaShim:
 
     def __getitem__(self, k):
         return self._g[k]
+
+
+# --------------------------------------------------------------------------- PGDM fixtures
+def pgdm_names():
+    return sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "pgdm_*.npz")))
+
+
+class PgdmGolden(Golden):
+    def __init__(self, name: str):
+        z = np.load(os.path.join(GOLDEN_DIR, f"pgdm_{name}.npz"))
+        self.meta = json.loads(bytes(z["meta"]).decode())
+        self.a = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+        self.name = name
+
+    def oracle_op(self):
+        spec = self.meta["op"]
+        if spec[0] == "mask":  # dense form: y has the shape of x, zeros at the missing pixels
+            keep = (~self.a["mask"]).float()
+
+            class Dense(oops.OracleOperator):
+                x_shape = y_shape = self.shape
+
+                def apply(self, x):
+                    return x * keep
+
+                adjoint = pinv = apply
+            return Dense()
+        return super().oracle_op()
+
+    def y_flat(self):
+        y, R = self.a["y"], self.meta["R"]
+        op = self.oracle_op()
+        y = y.reshape(-1, *op.y_shape) if len(self.meta["batch"]) else y.unsqueeze(0)
+        return y.repeat_interleave(R, dim=0) if len(self.meta["batch"]) else y
+
+
+def make_pgdm_problem(g: "PgdmGolden", device):
+    from samplers_b200 import operators as pops
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.noise import GaussianNoise
+    spec, shape = g.meta["op"], g.shape
+    if spec[0] == "identity":
+        op = pops.IdentityOperator(shape)
+    elif spec[0] == "mask":
+        op = pops.InpaintingOperator(shape, g["mask"], flatten=False)
+    else:
+        op = pops.BoxDownsampleOperator(shape, spec[1])
+    return InverseProblem(operator=op.to(device), observation=g["y"].to(device), noise=GaussianNoise(sigma=0.05))
