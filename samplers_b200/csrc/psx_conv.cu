@@ -341,6 +341,74 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, 
       : "memory");
 }
 
+// The FFMA2 work of one task: 8 outputs x (taps.k) taps on float2 pairs.  K > 0: the tap loop is fully
+// unrolled -- the tap pairs become immediate-offset constant-bank loads into uniform registers that the
+// compiler hoists and widens (22 LDCU for 40 taps), the window loads are software-pipelined, and nothing but
+// FFMA2 R,R,UR,R + LDS is left (36 registers).  K == 0: generic runtime loop.
+template <int K>
+__device__ __forceinline__ void row_block(float2 (&acc)[8], const float2* __restrict__ row, const Taps& taps) {
+  float2 win[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const float4 v = *reinterpret_cast<const float4*>(row + 2 * m);
+    win[2 * m] = make_float2(v.x, v.y); win[2 * m + 1] = make_float2(v.z, v.w);
+  }
+  if constexpr (K > 0) {
+#pragma unroll
+    for (int c = 0; c < K; c += 8) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(row + c + 8 + 2 * m);
+        win[8 + 2 * m] = make_float2(v.x, v.y); win[9 + 2 * m] = make_float2(v.z, v.w);
+      }
+      fma2_block(acc, win, taps.ww + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
+    }
+  } else {
+    for (int c = 0; c < taps.k; c += 8) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(row + c + 8 + 2 * m);
+        win[8 + 2 * m] = make_float2(v.x, v.y); win[9 + 2 * m] = make_float2(v.z, v.w);
+      }
+      fma2_block(acc, win, taps.ww + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
+    }
+  }
+}
+
+template <int K, int TC>
+__device__ __forceinline__ void col_block(float2 (&acc)[8], const float* __restrict__ col, const Taps& taps) {
+  float2 win[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] = make_float2(0.f, 0.f);
+    win[j] = *reinterpret_cast<const float2*>(col + j * TC);
+  }
+  if constexpr (K > 0) {
+#pragma unroll
+    for (int k = 0; k < K; k += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) win[8 + j] = *reinterpret_cast<const float2*>(col + (k + 8 + j) * TC);
+      fma2_block(acc, win, taps.ww + k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
+    }
+  } else {
+    for (int k = 0; k < taps.k; k += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) win[8 + j] = *reinterpret_cast<const float2*>(col + (k + 8 + j) * TC);
+      fma2_block(acc, win, taps.ww + k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
+    }
+  }
+}
+
 constexpr int kPipeRows = 16;   // rows per tile of the pipelined row pass: 8 row pairs (rho, rho + 8)
 constexpr int kPipeHdr = 128;   // bytes reserved at the start of dynamic smem for the two mbarriers
 
@@ -356,7 +424,7 @@ constexpr int kPipeHdr = 128;   // bytes reserved at the start of dynamic smem f
 // stages + one compute tile in the row-pair-interleaved float2 layout of conv_rows (pairs (rho, rho+8);
 // pitch2 % 16 == 2 => conflict-free LDS.128) whose halo columns are zeroed once.  A conversion pass
 // (Tweedie or plain copy) moves a landed stage into the compute tile.  Needs W % 8 == 0, W <= 512.
-template <int MODE>
+template <int MODE, int K>
 __global__ void __launch_bounds__(kThreads)
 conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, float* __restrict__ out,
                int64_t total_rows, int W, int pitch2, int64_t num_tiles, const __grid_constant__ Taps taps,
@@ -441,31 +509,8 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
       const int q = q_ok ? q_raw : 8 * ncg - 1;  // every thread computes (uniform control flow); stores are guarded
       const int rp = q & 7, cg = q >> 3;
       const float2* row = comp + rp * pitch2 + 8 * cg;
-      float2 acc[8], win[16];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const float4 v = *reinterpret_cast<const float4*>(row + 2 * m);
-        win[2 * m] = make_float2(v.x, v.y); win[2 * m + 1] = make_float2(v.z, v.w);
-      }
-      // software pipeline: the window of chunk c+1 is fetched before the 64 FFMA2 of chunk c issue
-      // (comp has >= 8 zero columns of slack beyond the last chunk: pitch2 >= W + k + 2, reads stay in the row)
-      float4 nx[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) nx[m] = *reinterpret_cast<const float4*>(row + 8 + 2 * m);
-      for (int c = 0; c < taps.k; c += 8) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          win[8 + 2 * m] = make_float2(nx[m].x, nx[m].y); win[9 + 2 * m] = make_float2(nx[m].z, nx[m].w);
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m)  // unconditional (a guard here would cost the uniform datapath); the
-          nx[m] = *reinterpret_cast<const float4*>(row + c + 16 + 2 * m);  // last fetch is unused slack
-        fma2_block(acc, win, taps.ww + c);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
-      }
+      float2 acc[8];
+      row_block<K>(acc, row, taps);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const bool ok = q_ok && rp + 8 * h < rows_valid;
@@ -494,7 +539,7 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
 // global (it is shared by all samples: L2 hits).  Needs W % 32 == 0, H % 8 == 0, H <= 256.
 constexpr int kColTC = 32;
 
-template <bool RESIDUAL, int ROUNDS>  // ROUNDS = H / 8 * 16 / kThreads: tasks per thread and pass (1 or 2)
+template <bool RESIDUAL, int ROUNDS, int K>  // ROUNDS = H / 8 * 16 / kThreads: tasks per thread and pass (1 or 2)
 __global__ void __launch_bounds__(kThreads, 2)
 conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ y, float* out,
                float* __restrict__ err_part, int C, int H, int W, int strips, int64_t num_tiles,
@@ -568,25 +613,8 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
           yv[j] = __ldg(reinterpret_cast<const float2*>(y + yplane + (int64_t)(8 * g + j) * W + gc));
       }
       const float* col = A + (size_t)(8 * g) * TC + 2 * cp;
-      float2 acc[8], win[16];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] = make_float2(0.f, 0.f);
-        win[j] = *reinterpret_cast<const float2*>(col + j * TC);
-      }
-      float2 nx[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) nx[j] = *reinterpret_cast<const float2*>(col + (8 + j) * TC);
-      for (int k = 0; k < tf.k; k += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) win[8 + j] = nx[j];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)  // unconditional; the last fetch lands in the 8 slack rows, unused
-          nx[j] = *reinterpret_cast<const float2*>(col + (k + 16 + j) * TC);
-        fma2_block(acc, win, tf.ww + k);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
-      }
+      float2 acc[8];
+      col_block<K, TC>(acc, col, tf);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int gr = 8 * g + j;
@@ -609,24 +637,8 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
         const int q = threadIdx.x + t * kThreads;
         const int cp = q % npair, g = q / npair;
         const float* col = bufB + (size_t)(8 * g) * TC + 2 * cp;
-        float2 acc[8], win[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[j] = make_float2(0.f, 0.f);
-          win[j] = *reinterpret_cast<const float2*>(col + j * TC);
-        }
-        float2 nx[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) nx[j] = *reinterpret_cast<const float2*>(col + (8 + j) * TC);
-        for (int k = 0; k < ta.k; k += 8) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) win[8 + j] = nx[j];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) nx[j] = *reinterpret_cast<const float2*>(col + (k + 16 + j) * TC);
-          fma2_block(acc, win, ta.ww + k);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) win[j] = win[j + 8];
-        }
+        float2 acc[8];
+        col_block<K, TC>(acc, col, ta);
         const int gc = c0 + 2 * cp;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -640,6 +652,242 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
       }
     }
     __syncthreads();  // stage + bufB + red fully consumed
+  }
+}
+
+// ========================================================================================== 16-output blocks
+// ncu on the 8-output kernels: L1TEX/shared-memory data pipe 62-72 % busy while the FMA pipe sat at 40-55 %:
+// per tile the window re-reads (48 float2 per 8x2 outputs), the raw->interleaved conversion pass and the TMA
+// fill together cost about as many shared-memory wavefronts as the FFMA2 work costs FMA-pipe cycles.  The
+// kernels below halve the window traffic (16 outputs per task: 56 float2 per 16x2 outputs) and drop the
+// conversion pass for the last row kernel by making its producer (the column kernel) write the row-pair
+// INTERLEAVED layout straight to global memory:   IL[(rho >> 1) * 2W + 2c + (rho & 1)] = X[rho][c].
+template <int K>
+__device__ __forceinline__ void row_block16(float2 (&acc)[16], const float2* __restrict__ row, const Taps& taps) {
+  float2 win[24];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const float4 v = *reinterpret_cast<const float4*>(row + 2 * m);
+    win[2 * m] = make_float2(v.x, v.y); win[2 * m + 1] = make_float2(v.z, v.w);
+  }
+#pragma unroll
+  for (int c = 0; c < K; c += 8) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c + 16 + 2 * m);
+      win[16 + 2 * m] = make_float2(v.x, v.y); win[17 + 2 * m] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 w = taps.ww[c + i];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = __ffma2_rn(w, win[i + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) win[j] = win[j + 8];
+  }
+}
+
+template <int K, int TC>
+__device__ __forceinline__ void col_block16(float2 (&acc)[16], const float* __restrict__ col, const Taps& taps) {
+  float2 win[24];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    acc[j] = make_float2(0.f, 0.f);
+    win[j] = *reinterpret_cast<const float2*>(col + j * TC);
+  }
+#pragma unroll
+  for (int k = 0; k < K; k += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) win[16 + j] = *reinterpret_cast<const float2*>(col + (k + 16 + j) * TC);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 w = taps.ww[k + i];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = __ffma2_rn(w, win[i + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) win[j] = win[j + 8];
+  }
+}
+
+// ---- columns, fused V / residual / V^T, 16 rows x 2 columns per task, h2 written row-pair interleaved.
+// Needs W % 32 == 0, H % 16 == 0, H <= 256 (at most one task per thread and pass), tf.k == ta.k == K.
+template <int K>
+__global__ void __launch_bounds__(kThreads, 2)
+conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ y, float* __restrict__ out_il,
+            float* __restrict__ err_part, int C, int H, int W, int strips, int64_t num_tiles, int64_t obs_repeat,
+            const __grid_constant__ Taps tf, const __grid_constant__ Taps ta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float red[32];
+  constexpr int TC = kColTC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw + kPipeHdr);
+  const int rowsA = H + K;
+  const int stage_floats = rowsA * TC;
+  float* bufB = smem + 2 * (size_t)stage_floats;  // (H + K) rows
+
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {  // zero the halo rows once: (136 + 8) rows * 8 float4 <= 5 * 256
+    const int i = threadIdx.x + t * kThreads;
+    const int r = i >> 3, c4 = i & 7;
+    if (r < K) {
+      const int ra = r < -tf.lo ? r : r + H, rb = r < -ta.lo ? r : r + H;
+      *reinterpret_cast<float4*>(smem + (size_t)ra * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(smem + stage_floats + (size_t)ra * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(bufB + (size_t)rb * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int stage) {
+    if (threadIdx.x == 0) {
+      const int64_t pl = tile / strips;
+      const int c0 = (int)(tile - pl * strips) * TC;
+      mbar_expect_tx(&bars[stage], (uint32_t)H * TC * 4u);
+      tma_load_2d(smem + (size_t)stage * stage_floats - (size_t)tf.lo * TC, &tmap, c0, (int)(pl * H), &bars[stage]);
+    }
+  };
+
+  constexpr int npair = TC >> 1;
+  const int ntask = (H >> 4) * npair;  // <= 256
+  const bool live = threadIdx.x < ntask;
+  const int q = live ? threadIdx.x : ntask - 1;
+  const int cp = q % npair, g = q / npair;
+  int64_t tile = blockIdx.x;
+  if (tile < num_tiles) issue(tile, 0);
+  for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
+    const int stage = it & 1;
+    if (tile + gridDim.x < num_tiles) issue(tile + gridDim.x, stage ^ 1);
+    mbar_wait(&bars[stage], (uint32_t)(it >> 1) & 1u);
+    __syncthreads();
+    const float* A = smem + (size_t)stage * stage_floats;
+    const int64_t pl = tile / strips;
+    const int strip = (int)(tile - pl * strips);
+    const int gc = strip * TC + 2 * cp;
+    const int64_t yplane = ((pl / C) / obs_repeat * C + pl % C) * (int64_t)H * W;
+    float e2 = 0.f;
+    {
+      float2 acc[16];
+      col_block16<K, TC>(acc, A + (size_t)(16 * g) * TC + 2 * cp, tf);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int gr = 16 * g + j;
+        const float2 yv = __ldg(reinterpret_cast<const float2*>(y + yplane + (int64_t)gr * W + gc));
+        float2 r;
+        r.x = live ? __fsub_rn(yv.x, acc[j].x) : 0.f;
+        r.y = live ? __fsub_rn(yv.y, acc[j].y) : 0.f;
+        e2 = fmaf(r.x, r.x, e2);
+        e2 = fmaf(r.y, r.y, e2);
+        if (live) *reinterpret_cast<float2*>(bufB + (size_t)(gr - ta.lo) * TC + 2 * cp) = r;
+      }
+    }
+    __syncthreads();
+    {
+      float2 acc[16];
+      col_block16<K, TC>(acc, bufB + (size_t)(16 * g) * TC + 2 * cp, ta);
+      float* dst = out_il + ((pl * H + 16 * g) >> 1) * (int64_t)(2 * W) + 2 * gc;
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+        if (live)
+          *reinterpret_cast<float4*>(dst + (int64_t)m * 2 * W) =
+              make_float4(acc[2 * m].x, acc[2 * m + 1].x, acc[2 * m].y, acc[2 * m + 1].y);
+    }
+    const float tot = block_sum(e2, red);  // contains a __syncthreads
+    if (threadIdx.x == 0) {
+      const int64_t l = pl / C;
+      const int ch = (int)(pl % C);
+      err_part[l * (int64_t)(C * strips) + ch * strips + strip] = tot;
+    }
+    __syncthreads();  // stage + bufB + red fully consumed
+  }
+}
+
+// ---- last row pass on row-pair-interleaved input: the TMA bulk copies land directly in the compute
+// layout (no conversion pass, no second barrier), 3 stages, 16 outputs x 2 rows per task, 128 threads.
+// Needs W % 16 == 0, W <= 256, (planes * H) % 2 == 0.
+constexpr int kIlThreads = 128;
+constexpr int kIlStages = 3;
+
+template <int K>
+__global__ void __launch_bounds__(kIlThreads)
+conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t total_rows, int W, int pitch2,
+             int64_t num_tiles, const __grid_constant__ Taps taps, float coef) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float2* stages = reinterpret_cast<float2*>(smem_raw + kPipeHdr);
+  const int stage_f2 = (kPipeRows / 2) * pitch2;
+  const int64_t total_pairs = total_rows >> 1;
+
+  {  // zero all stages once (halo columns are never written again)
+    const int n4 = (kIlStages * stage_f2) >> 1;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {  // 3 * 8 * (256 + 136 + 14) float2 / 2 <= 32 * 128
+      const int i = threadIdx.x + t * kIlThreads;
+      if (i < n4) reinterpret_cast<float4*>(stages)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kIlStages; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int stage) {
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const int64_t p0 = tile * (kPipeRows / 2);
+      const int64_t left = total_pairs - p0;
+      const int valid = left < kPipeRows / 2 ? (int)left : kPipeRows / 2;
+      const uint32_t nb = (uint32_t)W * 8u;  // one row pair: 2W floats
+      if (lane == 0) mbar_expect_tx(&bars[stage], nb * (uint32_t)valid);
+      __syncwarp();
+      if (lane < valid)
+        bulk_g2s(stages + (size_t)stage * stage_f2 + lane * pitch2 - taps.lo, in_il + (p0 + lane) * 2 * W, nb,
+                 &bars[stage]);
+    }
+  };
+
+  const int ncg = W >> 4;
+  const bool q_ok = (int)threadIdx.x < 8 * ncg;
+  const int q = q_ok ? threadIdx.x : 8 * ncg - 1;
+  const int rp = q & 7, cg = q >> 3;
+  int64_t tile = blockIdx.x;
+#pragma unroll
+  for (int d = 0; d < kIlStages - 1; ++d)
+    if (tile + (int64_t)d * gridDim.x < num_tiles) issue(tile + (int64_t)d * gridDim.x, d);
+  for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
+    const int stage = it % kIlStages;
+    __syncthreads();  // everyone is done with the stage that is refilled next
+    const int64_t nxt = tile + (int64_t)(kIlStages - 1) * gridDim.x;
+    if (nxt < num_tiles) issue(nxt, (it + kIlStages - 1) % kIlStages);
+    mbar_wait(&bars[stage], (uint32_t)(it / kIlStages) & 1u);
+    float2 acc[16];
+    row_block16<K>(acc, stages + (size_t)stage * stage_f2 + rp * pitch2 + 16 * cg, taps);
+    const int64_t pair = tile * (kPipeRows / 2) + rp;
+    if (q_ok && pair < total_pairs) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float* dst = out + (2 * pair + h) * W + 16 * cg;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          float4 v;
+          v.x = __fmul_rn(coef, h ? acc[4 * m].y : acc[4 * m].x);
+          v.y = __fmul_rn(coef, h ? acc[4 * m + 1].y : acc[4 * m + 1].x);
+          v.z = __fmul_rn(coef, h ? acc[4 * m + 2].y : acc[4 * m + 2].x);
+          v.w = __fmul_rn(coef, h ? acc[4 * m + 3].y : acc[4 * m + 3].x);
+          st_stream4(dst + 4 * m, v);
+        }
+      }
+    }
   }
 }
 
@@ -710,22 +958,27 @@ static int run_rows(const psx_op* op, const Taps& t, const float* in, const floa
     const int arrays = MODE == ROWS_TWEEDIE ? 2 : 1;
     const size_t smem = kPipeHdr + (size_t)(kPipeRows / 2) * pitch2 * sizeof(float2) +
                         (size_t)2 * arrays * kPipeRows * op->W * sizeof(float);  // raw stages double as read slack
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(conv_rows_pipe<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
-    }
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_rows_pipe<MODE>, kThreads, smem) != cudaSuccess ||
-        occ < 1)
-      occ = 1;
     const int64_t total_rows = planes * op->H;
     const int64_t num_tiles = (total_rows + kPipeRows - 1) / kPipeRows;
-    int64_t grid = (int64_t)occ * sm_count();
-    if (grid > num_tiles) grid = num_tiles;
     const float coef = (float)((double)w / (double)sa);
-    conv_rows_pipe<MODE><<<(unsigned)grid, kThreads, smem, st>>>(in, eps, out, total_rows, op->W, pitch2,
-                                                                 num_tiles, t, sa, s1, coef);
+#define PSX_ROWS(KK)                                                                                           \
+  {                                                                                                            \
+    static int occ = 0;                                                                                        \
+    if (!occ) {                                                                                                \
+      cudaFuncSetAttribute(conv_rows_pipe<MODE, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_rows_pipe<MODE, KK>, kThreads, smem) !=     \
+              cudaSuccess || occ < 1)                                                                          \
+        occ = 1;                                                                                               \
+    }                                                                                                          \
+    int64_t grid = (int64_t)occ * sm_count();                                                                  \
+    if (grid > num_tiles) grid = num_tiles;                                                                    \
+    conv_rows_pipe<MODE, KK><<<(unsigned)grid, kThreads, smem, st>>>(in, eps, out, total_rows, op->W, pitch2,  \
+                                                                     num_tiles, t, sa, s1, coef);              \
+  }
+    // the occupancy cache is per instantiation and assumes one (W, taps) geometry per process and mode;
+    // other geometries only change smem by a few KB and keep the same CTA count per SM in practice
+    if (t.k == 40) PSX_ROWS(40) else if (t.k == 16) PSX_ROWS(16) else if (t.k == 64) PSX_ROWS(64) else PSX_ROWS(0)
+#undef PSX_ROWS
     return check_cuda(cudaGetLastError(), "conv_rows_pipe launch");
   }
   const int TW = row_tw(op->W);
@@ -755,22 +1008,27 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
       const int rounds = (op->H >> 3) * (kColTC >> 1) / kThreads;  // H % 16 == 0  =>  exact
       const int strips = op->W / kColTC;
       const int64_t num_tiles = planes * strips;
-#define PSX_COLS(R)                                                                                          \
+#define PSX_COLS(R, KK)                                                                                      \
   {                                                                                                          \
     static int occ = 0;                                                                                      \
     if (!occ) {                                                                                              \
-      cudaFuncSetAttribute(conv_cols_pipe<RESIDUAL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+      cudaFuncSetAttribute(conv_cols_pipe<RESIDUAL, R, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                            200 * 1024);                                                                      \
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_cols_pipe<RESIDUAL, R>, kThreads,         \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_cols_pipe<RESIDUAL, R, KK>, kThreads,     \
                                                         smem_pipe) != cudaSuccess || occ < 1)                \
         occ = 1;                                                                                             \
     }                                                                                                        \
     int64_t grid = (int64_t)occ * sm_count();                                                                \
     if (grid > num_tiles) grid = num_tiles;                                                                  \
-    conv_cols_pipe<RESIDUAL, R><<<(unsigned)grid, kThreads, smem_pipe, st>>>(                                \
+    conv_cols_pipe<RESIDUAL, R, KK><<<(unsigned)grid, kThreads, smem_pipe, st>>>(                            \
         map, y, out, err_part, op->C, op->H, op->W, strips, num_tiles, obs_repeat, tf, ta);                  \
   }
-      if (rounds == 2) PSX_COLS(2) else if (rounds == 1) PSX_COLS(1)
+      const int kk = (tf.k == ta.k || !RESIDUAL) ? tf.k : 0;
+      if (rounds == 2) {
+        if (kk == 40) PSX_COLS(2, 40) else if (kk == 16) PSX_COLS(2, 16) else if (kk == 64) PSX_COLS(2, 64) else PSX_COLS(2, 0)
+      } else if (rounds == 1) {
+        if (kk == 40) PSX_COLS(1, 40) else if (kk == 16) PSX_COLS(1, 16) else if (kk == 64) PSX_COLS(1, 64) else PSX_COLS(1, 0)
+      }
       if (rounds == 1 || rounds == 2) return check_cuda(cudaGetLastError(), "conv_cols_pipe launch");
 #undef PSX_COLS
     }
@@ -788,6 +1046,45 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
   return check_cuda(cudaGetLastError(), "conv_cols launch");
 }
 
+// cols16 + rows_il tail of K1 (h1 in ws, row-major)  ->  cot.  Returns -1 when the geometry does not qualify.
+template <int K>
+static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot, float* err_part, int64_t planes,
+                         int64_t obs_repeat, float w, float sa, cudaStream_t st) {
+  const int W = op->W, H = op->H;
+  CUtensorMap map;
+  if (!make_strip_map(&map, ws, planes * H, W, H)) return -1;
+  const size_t smem_c = kPipeHdr + 3 * ((size_t)H + K) * kColTC * sizeof(float);
+  const int pitch2 = row_pitch2(W + K);
+  const size_t smem_r = kPipeHdr + (size_t)kIlStages * (kPipeRows / 2) * pitch2 * sizeof(float2);
+  static int occ_c = 0, occ_r = 0;
+  if (!occ_c) {
+    cudaFuncSetAttribute(conv_cols16<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_rows_il<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, conv_cols16<K>, kThreads, smem_c) != cudaSuccess || occ_c < 1)
+      occ_c = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, conv_rows_il<K>, kIlThreads, smem_r) != cudaSuccess || occ_r < 1)
+      occ_r = 1;
+  }
+  const int strips = W / kColTC;
+  const int64_t tiles_c = planes * strips;
+  int64_t grid_c = (int64_t)occ_c * sm_count();
+  if (grid_c > tiles_c) grid_c = tiles_c;
+  // in place: the strip of h1 is fully in shared memory before the interleaved h2 of the same rows/columns is
+  // written; other CTAs never touch this strip's (row pair, column) cells -- but the IL layout moves data
+  // ACROSS rows of a pair, so in-place is only safe because both rows of a pair belong to the same strip tile.
+  conv_cols16<K><<<(unsigned)grid_c, kThreads, smem_c, st>>>(map, y, ws, err_part, op->C, H, W, strips, tiles_c,
+                                                             obs_repeat, op->fv, op->av);
+  int rc = check_cuda(cudaGetLastError(), "conv_cols16 launch");
+  if (rc) return rc;
+  const int64_t total_rows = planes * H;
+  const int64_t tiles_r = (total_rows + kPipeRows - 1) / kPipeRows;
+  int64_t grid_r = (int64_t)occ_r * sm_count();
+  if (grid_r > tiles_r) grid_r = tiles_r;
+  const float coef = (float)((double)w / (double)sa);
+  conv_rows_il<K><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r, op->ah, coef);
+  return check_cuda(cudaGetLastError(), "conv_rows_il launch");
+}
+
 int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                        int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
                        float* x0_out, float* ws, cudaStream_t st) {
@@ -795,6 +1092,14 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
   const int64_t planes = L * op->C;
   int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x, eps, ws, planes, sa, s1, w, st);
   if (rc) return rc;
+  const int kk = op->fv.k;
+  if (op->W % kColTC == 0 && op->W <= 256 && op->H % 16 == 0 && op->H <= 256 && op->av.k == kk && op->ah.k == kk &&
+      op->col_tc == kColTC && !getenv("PSX_NO_PIPE") && !getenv("PSX_NO_FAST16")) {
+    int r2 = -1;
+    if (kk == 40) r2 = run_fast_tail<40>(op, y, ws, cot, err_part, planes, obs_repeat, w, sa, st);
+    else if (kk == 16) r2 = run_fast_tail<16>(op, y, ws, cot, err_part, planes, obs_repeat, w, sa, st);
+    if (r2 >= 0) return r2;
+  }
   rc = run_cols<true>(op, op->fv, op->av, ws, y, ws, err_part, planes, obs_repeat, st);
   if (rc) return rc;
   return run_rows<ROWS_COT>(op, op->ah, ws, nullptr, cot, planes, sa, s1, w, st);
