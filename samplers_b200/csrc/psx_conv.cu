@@ -6,6 +6,7 @@
 //     cols<RESIDUAL> : r = y - V h1, |r|^2 partials, h2 = V^T r  (strip-local) -> workspace (in place)
 //     rows<COT>      : cot = w * H^T h2 / sa                                   -> d_cot
 // All passes are zero-padded "same" cross-correlations; halos are zero-filled in shared memory.
+#include <cooperative_groups.h>
 #include <cuda.h>
 
 #include <cstdlib>
@@ -438,14 +439,6 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
   const int tile_floats = kPipeRows * W;
   const int w4 = W >> 2;
 
-  {  // zero the compute tile once: its halo columns are never written again
-    const int n4 = ((kPipeRows / 2) * pitch2) >> 1;
-#pragma unroll
-    for (int t = 0; t < 11; ++t) {  // 8 x (512 + 136 + 14) float2 / 2 <= 11 * 256
-      const int i = threadIdx.x + t * kThreads;
-      if (i < n4) reinterpret_cast<float4*>(comp)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -467,11 +460,20 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
 
   int64_t tile = blockIdx.x;
   if (tile < num_tiles) issue(tile, 0);
+  {  // zero the compute tile once while the first loads are in flight (its halo columns are never written
+     // again; the raw stages are written by the bulk copies only)
+    const int n4 = ((kPipeRows / 2) * pitch2) >> 1;
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {  // 8 x (512 + 136 + 14) float2 / 2 <= 11 * 256
+      const int i = threadIdx.x + t * kThreads;
+      if (i < n4) reinterpret_cast<float4*>(comp)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
     const int stage = it & 1;
     if (tile + gridDim.x < num_tiles) issue(tile + gridDim.x, stage ^ 1);
     mbar_wait(&bars[stage], (uint32_t)(it >> 1) & 1u);
-    __syncthreads();  // B1: previous tile's compute is done with `comp`
+    __syncthreads();  // B1: previous tile's compute is done with `comp` (first pass: the zero fill is done)
     const float* xs = raw + (size_t)stage * kArrays * tile_floats;
     const int64_t r0 = tile * kPipeRows;
     const int64_t left = total_rows - r0;
@@ -729,17 +731,6 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
   const int stage_floats = rowsA * TC;
   float* bufB = smem + 2 * (size_t)stage_floats;  // (H + K) rows
 
-#pragma unroll
-  for (int t = 0; t < 5; ++t) {  // zero the halo rows once: (136 + 8) rows * 8 float4 <= 5 * 256
-    const int i = threadIdx.x + t * kThreads;
-    const int r = i >> 3, c4 = i & 7;
-    if (r < K) {
-      const int ra = r < -tf.lo ? r : r + H, rb = r < -ta.lo ? r : r + H;
-      *reinterpret_cast<float4*>(smem + (size_t)ra * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(smem + stage_floats + (size_t)ra * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(bufB + (size_t)rb * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -763,6 +754,17 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
   const int cp = q % npair, g = q / npair;
   int64_t tile = blockIdx.x;
   if (tile < num_tiles) issue(tile, 0);
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {  // zero the halo rows once, while the first box load is in flight (the TMA
+    const int i = threadIdx.x + t * kThreads;  // writes interior rows only): (136 + 8) rows * 8 float4 <= 5 * 256
+    const int r = i >> 3, c4 = i & 7;
+    if (r < K) {
+      const int ra = r < -tf.lo ? r : r + H, rb = r < -ta.lo ? r : r + H;
+      *reinterpret_cast<float4*>(smem + (size_t)ra * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(smem + stage_floats + (size_t)ra * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(bufB + (size_t)rb * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
     const int stage = it & 1;
     if (tile + gridDim.x < num_tiles) issue(tile + gridDim.x, stage ^ 1);
@@ -826,14 +828,6 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
   const int stage_f2 = (kPipeRows / 2) * pitch2;
   const int64_t total_pairs = total_rows >> 1;
 
-  {  // zero all stages once (halo columns are never written again)
-    const int n4 = (kIlStages * stage_f2) >> 1;
-#pragma unroll
-    for (int t = 0; t < 32; ++t) {  // 3 * 8 * (256 + 136 + 14) float2 / 2 <= 32 * 128
-      const int i = threadIdx.x + t * kIlThreads;
-      if (i < n4) reinterpret_cast<float4*>(stages)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kIlStages; ++s) mbar_init(&bars[s], 1);
@@ -864,9 +858,22 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
 #pragma unroll
   for (int d = 0; d < kIlStages - 1; ++d)
     if (tile + (int64_t)d * gridDim.x < num_tiles) issue(tile + (int64_t)d * gridDim.x, d);
+  {  // zero the halo columns of every stage once, while the first loads are in flight (the bulk copies write the
+     // interior columns [-lo, -lo + W) only): per row pair the float2 columns [0, -lo) and [-lo + W, pitch2)
+    const int left = -taps.lo, right = pitch2 - left - W, per_row = left + right;  // all even
+#pragma unroll
+    for (int t = 0; t < 20; ++t) {  // 3 stages * 8 rows * (136 + 16 + 14) / 2 float4 <= 20 * 128
+      const int i = threadIdx.x + t * kIlThreads;
+      const int row = i / (per_row >> 1), c2 = 2 * (i - row * (per_row >> 1));
+      if (row < kIlStages * (kPipeRows / 2)) {
+        const int col = c2 < left ? c2 : c2 - left + left + W;
+        *reinterpret_cast<float4*>(stages + (size_t)row * pitch2 + col) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
   for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
     const int stage = it % kIlStages;
-    __syncthreads();  // everyone is done with the stage that is refilled next
+    __syncthreads();  // everyone is done with the stage that is refilled next (first pass: halo zero fill done)
     const int64_t nxt = tile + (int64_t)(kIlStages - 1) * gridDim.x;
     if (nxt < num_tiles) issue(nxt, (it + kIlStages - 1) % kIlStages);
     mbar_wait(&bars[stage], (uint32_t)(it / kIlStages) & 1u);
@@ -889,6 +896,225 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
       }
     }
   }
+}
+
+// ========================================================================================== cluster-fused K1
+// One launch for the whole blur K1 on 256 x 256 planes.  A thread-block CLUSTER of 8 CTAs owns one plane
+// (CTA c: rows [32c, 32c + 32)); the plane never leaves shared memory between the four passes:
+//   TMA bulk: x_t, eps rows -> smem | Tweedie -> row-pair-interleaved tile | H pass | h1 -> row-major buffer |
+//   cluster.sync + halo rows pulled from the two neighbour CTAs over distributed shared memory | V pass,
+//   r = y - V h1, |r|^2 | r -> buffer, halo exchange | V^T pass -> interleaved tile | H^T pass -> cot.
+// HBM traffic is exactly the algorithmic 16 B/element (x_t, eps, y in; cot out); no workspace.
+// Needs H == W == 256, all four tap sets with k == K and equal offsets per direction.
+#ifdef PSX_TRACE
+__device__ long long psx_trace[4096 * 16];
+#define PSX_TICK(slot)                                                                 \
+  if (threadIdx.x == 0 && blockIdx.x < 4096) {                                         \
+    long long t_;                                                                      \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+    psx_trace[blockIdx.x * 16 + (slot)] = t_;                                          \
+  }
+#else
+#define PSX_TICK(slot)
+#endif
+
+constexpr int kFusedCL = 8;      // CTAs per cluster (= per plane)
+constexpr int kFusedRB = 32;     // rows per CTA
+constexpr int kFusedW = 256;
+constexpr int kFusedHP = 260;    // pitch (floats) of the row-major h1 / r buffer: % 32 == 4
+
+template <int K>
+__global__ void __cluster_dims__(kFusedCL, 1, 1) __launch_bounds__(kThreads, 2)
+blur_k1_fused(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
+              float* __restrict__ cot, float* __restrict__ err_part, int C, int64_t obs_repeat, int pitch2,
+              const __grid_constant__ Taps fh, const __grid_constant__ Taps fv, const __grid_constant__ Taps av,
+              const __grid_constant__ Taps ah, float sa, float s1, float coef) {
+  namespace cg = cooperative_groups;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float red[32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int64_t pl = blockIdx.x / kFusedCL;  // plane index over L * C
+  constexpr int W = kFusedW, RB = kFusedRB, HP = kFusedHP, H = kFusedCL * kFusedRB;
+  const TweedieC tc = make_tc(s1, sa);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  float2* comp = reinterpret_cast<float2*>(smem_raw + kPipeHdr);              // 16 row pairs x pitch2
+  float* hb = reinterpret_cast<float*>(comp + (RB / 2) * pitch2);               // (RB + K) rows x HP; raw x|eps alias
+  const int64_t gbase = pl * (int64_t)H * W + (int64_t)rank * RB * W;           // first own element
+
+  PSX_TICK(0)
+  // ---- P0: zero the interleaved tile (its halo columns stay zero) and the outer halo rows of the edge CTAs
+  // (inner halo rows are always fully overwritten by the neighbours' pushes), arm the barrier, start the load
+  {
+    const int n4 = ((RB / 2) * pitch2) >> 1;
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {
+      const int i = threadIdx.x + t * kThreads;
+      if (i < n4) reinterpret_cast<float4*>(comp)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {  // K (40) halo rows x 65 quads (pitch 260) = 2600 <= 11 * 256
+      const int i = threadIdx.x + t * kThreads;
+      const int hr = i / (HP / 4), c4 = i - hr * (HP / 4);
+      if (hr < K) {
+        const bool top = hr < -fv.lo;
+        const int b = top ? hr : hr + RB;
+        if ((top && rank == 0) || (!top && rank == kFusedCL - 1))
+          *reinterpret_cast<float4*>(hb + (size_t)b * HP + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  float* own = hb + (size_t)(-fv.lo) * HP;  // own rows of the h1 / r buffer; also the landing zone of raw x_t
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    constexpr uint32_t nb = RB * W * 4;
+    mbar_expect_tx(bar, nb);
+    bulk_g2s(own, x + gbase, nb, bar);  // 32 KB contiguous (pitch W) inside the 33 KB own-row region
+  }
+  PSX_TICK(1)
+  cluster.sync();  // #0: every CTA of the cluster is running => remote shared memory may be written from now on
+  float* up = rank > 0 ? cluster.map_shared_rank(hb, rank - 1) : nullptr;
+  float* dn = rank < kFusedCL - 1 ? cluster.map_shared_rank(hb, rank + 1) : nullptr;
+
+  PSX_TICK(2)
+  // ---- P2: Tweedie + interleave (row pairs (2rp, 2rp+1)) -> comp; eps straight from global
+  {
+    float4 ea[4], eb[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int idx = threadIdx.x + t * kThreads;
+      const int rp = idx >> 6, c4 = idx & 63;
+      ea[t] = ld_stream4(eps + gbase + (2 * rp) * W + 4 * c4);
+      eb[t] = ld_stream4(eps + gbase + (2 * rp + 1) * W + 4 * c4);
+    }
+    mbar_wait(bar, 0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {  // 16 row pairs x 64 column quads = 4 * 256
+      const int idx = threadIdx.x + t * kThreads;
+      const int rp = idx >> 6, c4 = idx & 63;
+      float4 a = *reinterpret_cast<const float4*>(own + (2 * rp) * W + 4 * c4);
+      float4 b = *reinterpret_cast<const float4*>(own + (2 * rp + 1) * W + 4 * c4);
+      a.x = tweedie(a.x, ea[t].x, tc); a.y = tweedie(a.y, ea[t].y, tc);
+      a.z = tweedie(a.z, ea[t].z, tc); a.w = tweedie(a.w, ea[t].w, tc);
+      b.x = tweedie(b.x, eb[t].x, tc); b.y = tweedie(b.y, eb[t].y, tc);
+      b.z = tweedie(b.z, eb[t].z, tc); b.w = tweedie(b.w, eb[t].w, tc);
+      float2* dst = comp + rp * pitch2 - fh.lo + 4 * c4;
+      *reinterpret_cast<float4*>(dst) = make_float4(a.x, b.x, a.y, b.y);
+      *reinterpret_cast<float4*>(dst + 2) = make_float4(a.z, b.z, a.w, b.w);
+    }
+  }
+  PSX_TICK(3)
+  __syncthreads();  // comp ready; raw x_t dead => own rows reusable
+
+  // own row i (0..31) is also row i + RB - lo of the upper neighbour's buffer when i < K + lo ... see below:
+  //   upper neighbour (rank-1) bottom halo: buffer row i + RB - lo   for i in [0, K + lo)
+  //   lower neighbour (rank+1) top halo   : buffer row i - RB - lo   for i in [RB + lo, RB)
+  // ---- P3: H pass (16 row pairs x 16 column groups of 16) -> h1 into own rows, boundary rows pushed next door
+  const int hrp = threadIdx.x & 15, hcg = threadIdx.x >> 4;
+  {
+    float2 acc[16];
+    row_block16<K>(acc, comp + hrp * pitch2 + 16 * hcg, fh);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * hrp + h;
+      float4 v[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        v[m] = make_float4(h ? acc[4 * m].y : acc[4 * m].x, h ? acc[4 * m + 1].y : acc[4 * m + 1].x,
+                           h ? acc[4 * m + 2].y : acc[4 * m + 2].x, h ? acc[4 * m + 3].y : acc[4 * m + 3].x);
+      float* dst = hb + (size_t)(-fv.lo + i) * HP + 16 * hcg;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) *reinterpret_cast<float4*>(dst + 4 * m) = v[m];
+      if (up && i < K + fv.lo) {
+        float* rd = up + (size_t)(i + RB - fv.lo) * HP + 16 * hcg;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) *reinterpret_cast<float4*>(rd + 4 * m) = v[m];
+      }
+      if (dn && i >= RB + fv.lo) {
+        float* rd = dn + (size_t)(i - RB - fv.lo) * HP + 16 * hcg;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) *reinterpret_cast<float4*>(rd + 4 * m) = v[m];
+      }
+    }
+  }
+  PSX_TICK(4)
+  cluster.sync();  // #1: own h1 rows and both halos (pushed by the neighbours) are in place
+
+  PSX_TICK(5)
+  // ---- P5: V pass, r = y - V h1, |r|^2 (128 column pairs x 2 groups of 16 rows)
+  const int vcp = threadIdx.x & 127, vg = threadIdx.x >> 7;
+  float e2 = 0.f;
+  float2 r[16];
+  {
+    col_block16<K, HP>(r, hb + (size_t)(16 * vg) * HP + 2 * vcp, fv);
+    const float* yp = y + ((pl / C) / obs_repeat * C + pl % C) * (int64_t)H * W +
+                      (int64_t)(rank * RB + 16 * vg) * W + 2 * vcp;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 yv = __ldg(reinterpret_cast<const float2*>(yp + (int64_t)j * W));
+      r[j].x = __fsub_rn(yv.x, r[j].x);
+      r[j].y = __fsub_rn(yv.y, r[j].y);
+      e2 = fmaf(r[j].x, r[j].x, e2);
+      e2 = fmaf(r[j].y, r[j].y, e2);
+    }
+  }
+  PSX_TICK(6)
+  cluster.sync();  // #2: nobody (here or next door) still reads h1
+  PSX_TICK(7)
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int i = 16 * vg + j;
+    *reinterpret_cast<float2*>(hb + (size_t)(-av.lo + i) * HP + 2 * vcp) = r[j];
+    if (up && i < K + av.lo) *reinterpret_cast<float2*>(up + (size_t)(i + RB - av.lo) * HP + 2 * vcp) = r[j];
+    if (dn && i >= RB + av.lo) *reinterpret_cast<float2*>(dn + (size_t)(i - RB - av.lo) * HP + 2 * vcp) = r[j];
+  }
+  PSX_TICK(8)
+  cluster.sync();  // #3: every CTA's r rows and halos are in place
+
+  PSX_TICK(9)
+  // ---- P7: V^T pass -> h2 into comp (interleaved)
+  {
+    col_block16<K, HP>(r, hb + (size_t)(16 * vg) * HP + 2 * vcp, av);
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+      *reinterpret_cast<float4*>(comp + (8 * vg + m) * pitch2 - ah.lo + 2 * vcp) =
+          make_float4(r[2 * m].x, r[2 * m + 1].x, r[2 * m].y, r[2 * m + 1].y);
+  }
+  __syncthreads();
+
+  PSX_TICK(10)
+  // ---- P8: H^T pass -> cot
+  {
+    float2 acc[16];
+    row_block16<K>(acc, comp + hrp * pitch2 + 16 * hcg, ah);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float* dst = cot + gbase + (int64_t)(2 * hrp + h) * W + 16 * hcg;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        float4 v;
+        v.x = __fmul_rn(coef, h ? acc[4 * m].y : acc[4 * m].x);
+        v.y = __fmul_rn(coef, h ? acc[4 * m + 1].y : acc[4 * m + 1].x);
+        v.z = __fmul_rn(coef, h ? acc[4 * m + 2].y : acc[4 * m + 2].x);
+        v.w = __fmul_rn(coef, h ? acc[4 * m + 3].y : acc[4 * m + 3].x);
+        st_stream4(dst + 4 * m, v);
+      }
+    }
+  }
+  PSX_TICK(11)
+  const float tot = block_sum(e2, red);
+  if (threadIdx.x == 0) {
+    const int64_t l = pl / C;
+    const int ch = (int)(pl % C);
+    err_part[l * (int64_t)(C * kFusedCL) + ch * kFusedCL + rank] = tot;
+  }
+  PSX_TICK(12)
+  cluster.sync();  // no CTA may exit while a neighbour could still read its shared memory
+  PSX_TICK(13)
 }
 
 // host: 2-D tensor map over the tall (planes*H) x W fp32 matrix, box = 32 columns x H rows
@@ -1090,6 +1316,27 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
                        float* x0_out, float* ws, cudaStream_t st) {
   if (x0_out) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: d_x0_out is not produced for blur operators");
   const int64_t planes = L * op->C;
+  // cluster-fused single launch for 256 x 256 planes
+  if (op->H == kFusedCL * kFusedRB && op->W == kFusedW && op->fh.k == 40 && op->fv.k == 40 && op->ah.k == 40 &&
+      op->av.k == 40 && op->fh.lo == op->ah.lo && op->fv.lo == op->av.lo && -op->fv.lo <= kFusedRB &&
+      op->err_parts == op->C * kFusedCL && getenv("PSX_FUSED")) {
+    // opt-in: measured 48.0 us vs 46.1 us for the three-launch path at L = 16 (profiles/README.md) -- each CTA runs
+    // its nine phases back to back (21 us per CTA, 6 us of it in cluster barriers) and 48 planes need two waves
+    // of the 33 clusters that fit, so the single launch does not pay off yet despite its minimal HBM traffic.
+    constexpr int K = 40;
+    const int pitch2 = row_pitch2(kFusedW + K);
+    const size_t smem = kPipeHdr + (size_t)(kFusedRB / 2) * pitch2 * sizeof(float2) +
+                        (size_t)(kFusedRB + K) * kFusedHP * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(blur_k1_fused<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    const float coef = (float)((double)w / (double)sa);
+    blur_k1_fused<K><<<(unsigned)(planes * kFusedCL), kThreads, smem, st>>>(
+        x, eps, y, cot, err_part, op->C, obs_repeat, pitch2, op->fh, op->fv, op->av, op->ah, sa, s1, coef);
+    return check_cuda(cudaGetLastError(), "blur_k1_fused launch");
+  }
   int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x, eps, ws, planes, sa, s1, w, st);
   if (rc) return rc;
   const int kk = op->fv.k;

@@ -145,3 +145,27 @@ def test_full_size_k1_consistent_with_standalone_kernels():
         ref = nat.adjoint(r.contiguous()) * w / sa
         assert rel_err(cot.cpu(), ref.cpu()) < 2e-6, type(op).__name__
         assert rel_err(part.sum(1).cpu(), r.double().square().sum(1).float().cpu()) < 1e-5, type(op).__name__
+
+
+def test_cluster_fused_blur_k1_matches_three_launch_path(monkeypatch):
+    """The opt-in single-launch cluster/DSMEM kernel (PSX_FUSED=1) against the default three-launch K1."""
+    from samplers_b200 import _native, operators as pops
+    op = pops.GaussianBlurOperator(FULL).to(DEV)
+    nat = op._native_cached(torch.device(DEV))
+    L = 5
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.randn(L, nat.n, device=DEV, generator=gen)
+    eps = torch.randn(L, nat.n, device=DEV, generator=gen)
+    y = torch.randn(1, nat.n_y, device=DEV, generator=gen)
+    ws = torch.empty(nat.workspace_bytes(L) // 4, device=DEV)
+    outs = []
+    for fused in (False, True):
+        if fused:
+            monkeypatch.setenv("PSX_FUSED", "1")
+        else:
+            monkeypatch.delenv("PSX_FUSED", raising=False)
+        cot, part = torch.empty_like(x), torch.empty(L, nat.err_parts, device=DEV)
+        _native.dps_pre(nat, x, eps, y, L, 0.8, 0.6, 400.0, cot, part, ws)
+        outs.append((cot.clone(), part.sum(1).clone()))
+    assert rel_err(outs[1][0].cpu(), outs[0][0].cpu()) < 2e-6
+    assert rel_err(outs[1][1].cpu(), outs[0][1].cpu()) < 1e-6
