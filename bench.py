@@ -35,6 +35,9 @@ BATCH_PER_GPU = 16
 SAMPLING_STEPS = 1000
 GUIDED_STEPS = SAMPLING_STEPS - 2        # range(len(ts)-1, 1, -1)
 SIGMA_Y = 0.05
+# dram__bytes_read.sum + dram__bytes_write.sum per step from the committed ncu --set full capture of the four
+# launches at this exact shape (L = 16): 25.19 + 13.41 + 12.61 (K1) + 62.93 + 1.25 (K2) MB
+NCU_DRAM_BYTES_PER_STEP = int((25.19 + 13.41 + 12.61 + 62.93 + 1.25) * 1e6)
 METRIC = "dps_posterior_samples_per_s_256"
 WORKLOAD = "cfg2: DPS gaussian-blur 61x61 sigma3, ddpm-celebahq-256 UNet, 1000 steps, batch 16/GPU, 3x256x256"
 
@@ -246,7 +249,10 @@ def run_own(args):
         "gpu_launches": int(sum(_native.KERNELS_PER_CALL[c] for c in ("pre_sepblur", "post")) * K),
         "abi_calls": int(abi_calls),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "fused DPS step = K1 (3 launches) + K2",
+                     "traffic": NCU_DRAM_BYTES_PER_STEP if (L, n) == (16, 3 * 256 * 256) else None,
+                     "traffic_source": "profiles/r01_ncu_full_summary.csv (ncu --set full, cold cache: "
+                                       "dram read+write of the 3 K1 launches + K2)",
+                     "peak_source": peak_src, "kernel": "fused DPS step = K1 (3 launches) + K2",
                      "algorithmic_bytes": alg_bytes, "k1_ms": k1_ms, "k2_ms": k2_ms,
                      "k2_alone_gbs": 24 * L * n / (k2_ms / 1e3) / 1e9,
                      "share_of_step": (k1_ms + k2_ms) / (ms / K)},
