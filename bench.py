@@ -137,11 +137,11 @@ def run_own(args):
                                   channels_last=bool(args.channels_last))
     problem = build_problem(device, L)
     sampler = DPSSampler(net)
-    gen = torch.Generator(device=device).manual_seed(2 + rank)
-    sampler.draw = lambda shape, dev, dt: torch.randn(shape, device=dev, dtype=dt, generator=gen)
+    torch.manual_seed(2 + rank)                 # the N(0,1) draws come from torch's CUDA generator on every path
     run = sampler.prepare(problem, num_sampling_steps=SAMPLING_STEPS, num_reconstructions=L, gamma=1.0, eta=1.0)
     n = run.n
     K, W = args.steps, args.warmup
+    use_graph, graph_error = bool(args.cuda_graph), None
 
     def barrier():
         if world > 1:
@@ -166,7 +166,33 @@ def run_own(args):
     dps_mod._native.dps_pre = timed("k1", real_pre)
     dps_mod._native.dps_post = timed("k2", real_post)
 
+    # CUDA-graph replay of the timestep: K1 / K2 are bracketed by EXTERNAL events recorded inside the graph
+    gev = {}
+    real_pre_dev, real_post_dev = _native.dps_pre_dev, _native.dps_post_dev
+
+    def timed_dev(name, fn):
+        def wrap(*a, **k):
+            if not torch.cuda.is_current_stream_capturing():
+                return fn(*a, **k)
+            s, e = (torch.cuda.Event(enable_timing=True, external=True) for _ in range(2))
+            s.record(); fn(*a, **k); e.record()
+            gev[name] = (s, e)
+        return wrap
+
+    dps_mod._native.dps_pre_dev = timed_dev("k1", real_pre_dev)
+    dps_mod._native.dps_post_dev = timed_dev("k2", real_post_dev)
+
     try:
+        if use_graph:
+            try:
+                run.capture(draw_in_graph=False)   # noise buffer filled per step: on device (value) / from host (e2e)
+            except Exception as exc:               # reported in the JSON line, never silent
+                graph_error = f"{type(exc).__name__}: {exc}"[:200]
+                use_graph = False
+                torch.cuda.synchronize()
+                sampler.release()
+                run = sampler.prepare(problem, num_sampling_steps=SAMPLING_STEPS, num_reconstructions=L,
+                                      gamma=1.0, eta=1.0)
         for k in range(W):
             run.step(k)
         # ---------------- device-resident timing (value)
@@ -183,14 +209,28 @@ def run_own(args):
         timing["on"] = False
         ms = t0.elapsed_time(t1)
         abi_calls = _native.launch_count - launches0
-        k1_ms = statistics.mean(s.elapsed_time(e) for s, e in ev["k1"])
-        k2_ms = statistics.mean(s.elapsed_time(e) for s, e in ev["k2"])
+        if use_graph:
+            # the in-graph events now hold the LAST timed step; K more replays, read after each, give the mean
+            k_last = {name: s.elapsed_time(e) for name, (s, e) in gev.items()}
+            samples = {"k1": [], "k2": []}
+            for k in range(K):
+                run.step((W + K + k) % run.num_steps)
+                torch.cuda.synchronize()
+                for name, (s, e) in gev.items():
+                    samples[name].append(s.elapsed_time(e))
+            k1_ms, k2_ms = statistics.mean(samples["k1"]), statistics.mean(samples["k2"])
+            abi_calls = 2 * K                      # the two ABI calls are nodes of the replayed graph
+        else:
+            k_last = None
+            k1_ms = statistics.mean(s.elapsed_time(e) for s, e in ev["k1"])
+            k2_ms = statistics.mean(s.elapsed_time(e) for s, e in ev["k2"])
 
         # ---------------- end-to-end through the public step API with HOST buffers
         z_host = [torch.randn(run.view.flat_shape, generator=torch.Generator().manual_seed(100 + i)).pin_memory()
                   for i in range(2)]
         err_host = torch.empty(L, dtype=torch.float32).pin_memory()
-        z_dev = torch.empty(run.view.flat_shape, device=device)
+        # graph replay reads its noise from run.z: copy straight into it
+        z_dev = run.z.view(run.view.flat_shape) if use_graph else torch.empty(run.view.flat_shape, device=device)
         for k in range(2):  # warm the copy path
             z_dev.copy_(z_host[k % 2], non_blocking=True); run.step((W + K + k) % run.num_steps, z=z_dev)
         barrier()
@@ -221,6 +261,7 @@ def run_own(args):
     finally:
         sampler.release()
         dps_mod._native.dps_pre, dps_mod._native.dps_post = real_pre, real_post
+        dps_mod._native.dps_pre_dev, dps_mod._native.dps_post_dev = real_pre_dev, real_post_dev
 
     t = torch.tensor([ms, ms_e2e, k1_ms, k2_ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -243,7 +284,10 @@ def run_own(args):
                    "l2": "inputs larger than L2: the UNet pass between consecutive K1/K2 touches GBs of activations",
                    "network": "ddpm-celebahq-256 UNet2D, random init, torch (cuDNN TF32 conv defaults"
                               + (", channels_last" if args.channels_last else "") + ")",
-                   "parallelism": f"independent samples x{world}", "terminal_gather_ms": final_ms},
+                   "parallelism": f"independent samples x{world}", "terminal_gather_ms": final_ms,
+                   "launch": ("one CUDA-graph replay per timestep (scalars + timestep from device tables)"
+                              if use_graph else "eager launches"),
+                   **({"cuda_graph_error": graph_error} if graph_error else {})},
         "e2e": {"value": world * L / (GUIDED_STEPS * e2e_s), "unit": "samples/s",
                 "h2d_bytes_per_step": L * n * 4, "d2h_bytes_per_step": L * 4, "ms_per_step": ms_e2e / K},
         "gpu_launches": int(sum(_native.KERNELS_PER_CALL[c] for c in ("pre_sepblur", "post")) * K),
@@ -254,6 +298,10 @@ def run_own(args):
                                        "dram read+write of the 3 K1 launches + K2)",
                      "peak_source": peak_src, "kernel": "fused DPS step = K1 (3 launches) + K2",
                      "algorithmic_bytes": alg_bytes, "k1_ms": k1_ms, "k2_ms": k2_ms,
+                     "kernel_timing": ("external CUDA events inside the replayed graph, mean of K replays read "
+                                       "one by one right after the timed region; last timed step: "
+                                       f"k1 {k_last['k1']:.4f} ms, k2 {k_last['k2']:.4f} ms") if use_graph
+                                      else "CUDA events around every ABI call inside the timed region",
                      "k2_alone_gbs": 24 * L * n / (k2_ms / 1e3) / 1e9,
                      "share_of_step": (k1_ms + k2_ms) / (ms / K)},
         "clocks": clocks.summary(),
@@ -346,6 +394,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--channels-last", type=int, default=int(os.environ.get("PSX_CHANNELS_LAST", "0")))  # NCHW measured 1.36x faster (tools/unet_bench.py)
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
+    ap.add_argument("--cuda-graph", type=int, default=int(os.environ.get("PSX_CUDA_GRAPH", "1")))  # 1.03x at config 2 (tools/graph_bench.py)
     ap.add_argument("--cpu-batch", type=int, default=1)
     ap.add_argument("--ref-max-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

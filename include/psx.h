@@ -151,6 +151,26 @@ PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_
                  float c_s, float std, float gamma, float* d_x_next, float* d_err_out,
                  void* stream);
 
+/* ------------------------------------------------------------------ graph-replayable K1 / K2
+ * Same kernels, but the per-timestep scalars are read from DEVICE memory, so that one captured CUDA graph of
+ * a whole timestep (network forward, K1, network VJP, K2) can be replayed for every timestep of the loop
+ * (dps.py:91-122) without re-recording launch parameters: the caller keeps the table of all steps on the device
+ * and moves row k into d_step_row with a device-side copy inside the graph.
+ *
+ *   d_step_row[PSX_STEP_ROW] = { sqrt_acp, sqrt_1m_acp, lik_weight / sqrt_acp (one fp32 division),
+ *                                c_ell, c_s, std, gamma, unused }
+ *
+ * psx_dps_pre_dev reads entries 0-2, psx_dps_post_dev entries 0, 1, 3-6; d_z is required (std may be 0 in the
+ * row; the product std * z is then an exact zero).  Results are bit-identical to the by-value entry points. */
+#define PSX_STEP_ROW 8
+PSX_API int psx_dps_pre_dev(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y,
+                            int64_t L, int64_t obs_repeat, const float* d_step_row, float* d_cot,
+                            float* d_err_part, float* d_x0_out, void* d_workspace, size_t workspace_bytes,
+                            void* stream);
+PSX_API int psx_dps_post_dev(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
+                             const float* d_z, const float* d_err_part, int err_parts, int64_t L, int64_t n,
+                             const float* d_step_row, float* d_x_next, float* d_err_out, void* stream);
+
 /* ------------------------------------------------------------- latent samplers (PSLD)
  * psx_bridge_update -- bridge (DDIM/DDPM) update with an additive correction, the tail of a PSLD step:
  *   x_next = c_ell*x + c_s*x0 + std*z + grad_scale*grad,   x0 = (x - s1*eps)/sa

@@ -44,6 +44,10 @@ PROTOTYPES = {
                               _vp, C.c_size_t, _vp]),
     "psx_dps_post": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64,
                                _f, _f, _f, _f, _f, _f, _f32p, _f32p, _vp]),
+    "psx_dps_pre_dev": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
+                                  C.c_size_t, C.c_void_p]),
+    "psx_dps_post_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _f32p,
+                                   _f32p, C.c_void_p]),
     "psx_tweedie": (C.c_int, [_f32p, _f32p, _i64, _i64, _f, _f, _f32p, _f32p, _f32p, _vp]),
     "psx_bridge_update": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, _f, _f32p, _vp]),
     "psx_lincomb3": (C.c_int, [_f32p, _f, _f32p, _f, _f32p, _f, _f32p, _i64, _vp]),
@@ -232,6 +236,32 @@ def dps_post(x_t, eps, cot, vjp, z, err_part, err_parts: int, n: int, sa: float,
                                   ptr(err_part), err_parts if err_part is not None else 0, L, n, sa, s1, c_ell,
                                   c_s, std, gamma,
                                   x_next.data_ptr(), ptr(err_out), stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+STEP_ROW = 8  # floats per device step row (PSX_STEP_ROW): sa, s1, w / sa, c_ell, c_s, std, gamma, unused
+
+
+def dps_pre_dev(op: NativeOp, x_t, eps, y, obs_repeat: int, step_row, cot, err_part, ws, x0_out=None) -> None:
+    """psx_dps_pre with the step scalars read from the device row ``step_row`` (graph-replayable)."""
+    global launch_count
+    L = x_t.shape[0]
+    with torch.cuda.device(x_t.device):
+        check(load().psx_dps_pre_dev(op.handle, x_t.data_ptr(), eps.data_ptr(), y.data_ptr(), L, obs_repeat,
+                                     step_row.data_ptr(), cot.data_ptr(), err_part.data_ptr(), ptr(x0_out),
+                                     ptr(ws), 0 if ws is None else ws.numel() * 4, stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def dps_post_dev(x_t, eps, cot, vjp, z, err_part, err_parts: int, n: int, step_row, x_next, err_out=None) -> None:
+    """psx_dps_post with the step scalars read from the device row ``step_row`` (graph-replayable)."""
+    global launch_count
+    L = x_t.shape[0]
+    with torch.cuda.device(x_t.device):
+        check(load().psx_dps_post_dev(x_t.data_ptr(), eps.data_ptr(), cot.data_ptr(), vjp.data_ptr(), z.data_ptr(),
+                                      ptr(err_part), err_parts if err_part is not None else 0, L, n,
+                                      step_row.data_ptr(), x_next.data_ptr(), ptr(err_out),
+                                      stream_ptr(x_t.device)))
     launch_count += 1
 
 

@@ -26,7 +26,8 @@ int check_cuda(cudaError_t e, const char* what) {
 int pointwise_parts(int64_t n);
 int box_parts(int64_t ny);
 int launch_post(const float*, const float*, const float*, const float*, const float*, const float*, int,
-                int64_t, int64_t, float, float, float, float, float, float, float*, float*, cudaStream_t);
+                int64_t, int64_t, float, float, float, float, float, float, const float*, float*, float*,
+                cudaStream_t);
 int launch_tweedie(const float*, const float*, int64_t, int64_t, float, float, float*, float*, float*,
                    cudaStream_t);
 int launch_gather(bool, const float*, const int64_t*, float*, int64_t, int64_t, int64_t, cudaStream_t);
@@ -214,32 +215,49 @@ PSX_API int psx_scatter(const float* d_in, const int64_t* d_idx, float* d_out, i
   return launch_gather(true, d_in, d_idx, d_out, L, n, m, (cudaStream_t)stream);
 }
 
-PSX_API int psx_dps_pre(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y, int64_t L,
-                int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight, float* d_cot,
-                float* d_err_part, float* d_x0_out, void* ws, size_t ws_bytes, void* stream) {
-  PSX_REQUIRE(op && d_x_t && d_eps && d_y && d_cot && d_err_part, "psx_dps_pre: null pointer");
-  PSX_REQUIRE(L > 0 && L <= 65535, "psx_dps_pre: L must be in [1, 65535]");
-  PSX_REQUIRE(obs_repeat > 0, "psx_dps_pre: obs_repeat must be positive");
-  PSX_REQUIRE(sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(sqrt_1m_acp) && std::isfinite(lik_weight),
-              "psx_dps_pre: non-finite or non-positive schedule scalar");
+// Shared body of psx_dps_pre / psx_dps_pre_dev: with d_row the kernels read their step scalars from device memory.
+static int dps_pre_impl(const char* who, const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y,
+                        int64_t L, int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight,
+                        const float* d_row, float* d_cot, float* d_err_part, float* d_x0_out, void* ws,
+                        size_t ws_bytes, void* stream) {
+  if (!(op && d_x_t && d_eps && d_y && d_cot && d_err_part)) return fail(PSX_ERR_INVALID, std::string(who) + ": null pointer");
+  if (!(L > 0 && L <= 65535)) return fail(PSX_ERR_INVALID, std::string(who) + ": L must be in [1, 65535]");
+  if (!(obs_repeat > 0)) return fail(PSX_ERR_INVALID, std::string(who) + ": obs_repeat must be positive");
   if (int rc = check_ws(op, L, ws, ws_bytes)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   switch (op->kind) {
     case PSX_OP_IDENTITY:
     case PSX_OP_MASK:
-      return launch_pre_pointwise(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight,
+      return launch_pre_pointwise(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight, d_row,
                                   d_cot, d_err_part, d_x0_out, st);
     case PSX_OP_BOX:
-      return launch_pre_box(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight, d_cot,
+      return launch_pre_box(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight, d_row, d_cot,
                             d_err_part, d_x0_out, st);
     case PSX_OP_SEPBLUR:
-      return launch_pre_sepblur(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight,
+      return launch_pre_sepblur(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight, d_row,
                                 d_cot, d_err_part, d_x0_out, (float*)ws, st);
     case PSX_OP_CONV2D:
-      return launch_pre_conv2d(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight,
+      return launch_pre_conv2d(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight, d_row,
                                d_cot, d_err_part, d_x0_out, (float*)ws, st);
   }
-  return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: unknown operator kind");
+  return fail(PSX_ERR_UNSUPPORTED, std::string(who) + ": unknown operator kind");
+}
+
+PSX_API int psx_dps_pre(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y, int64_t L,
+                int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight, float* d_cot,
+                float* d_err_part, float* d_x0_out, void* ws, size_t ws_bytes, void* stream) {
+  PSX_REQUIRE(sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(sqrt_1m_acp) && std::isfinite(lik_weight),
+              "psx_dps_pre: non-finite or non-positive schedule scalar");
+  return dps_pre_impl("psx_dps_pre", op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight,
+                      nullptr, d_cot, d_err_part, d_x0_out, ws, ws_bytes, stream);
+}
+
+PSX_API int psx_dps_pre_dev(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y, int64_t L,
+                            int64_t obs_repeat, const float* d_step_row, float* d_cot, float* d_err_part,
+                            float* d_x0_out, void* ws, size_t ws_bytes, void* stream) {
+  PSX_REQUIRE(d_step_row != nullptr, "psx_dps_pre_dev: null step row");
+  return dps_pre_impl("psx_dps_pre_dev", op, d_x_t, d_eps, d_y, L, obs_repeat, 1.f, 0.f, 1.f, d_step_row, d_cot,
+                      d_err_part, d_x0_out, ws, ws_bytes, stream);
 }
 
 PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
@@ -254,8 +272,18 @@ PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_
                   std::isfinite(std_) && std::isfinite(gamma),
               "psx_dps_post: non-finite scalar");
   return launch_post(d_x_t, d_eps, d_cot, d_vjp, std_ == 0.f ? nullptr : d_z, d_err_part, err_parts, L, n,
-                     sqrt_acp, sqrt_1m_acp, c_ell, c_s, std_, gamma, d_x_next, d_err_out,
+                     sqrt_acp, sqrt_1m_acp, c_ell, c_s, std_, gamma, nullptr, d_x_next, d_err_out,
                      (cudaStream_t)stream);
+}
+
+PSX_API int psx_dps_post_dev(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
+                             const float* d_z, const float* d_err_part, int err_parts, int64_t L, int64_t n,
+                             const float* d_step_row, float* d_x_next, float* d_err_out, void* stream) {
+  PSX_REQUIRE(d_x_t && d_eps && d_cot && d_vjp && d_z && d_x_next && d_step_row, "psx_dps_post_dev: null pointer");
+  PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts >= 0, "psx_dps_post_dev: bad sizes");
+  PSX_REQUIRE((err_parts > 0) == (d_err_part != nullptr), "psx_dps_post_dev: d_err_part and err_parts must agree");
+  return launch_post(d_x_t, d_eps, d_cot, d_vjp, d_z, d_err_part, err_parts, L, n, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+                     d_step_row, d_x_next, d_err_out, (cudaStream_t)stream);
 }
 
 PSX_API int psx_bridge_update(const float* d_x, const float* d_eps, const float* d_z, const float* d_grad,

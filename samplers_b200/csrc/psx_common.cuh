@@ -93,6 +93,30 @@ __device__ __forceinline__ float tweedie(float x, float e, const TweedieC& c) {
   return __fmaf_rn(rem, c.rcp, q0);
 }
 
+// Step scalars: kernels take them by value; the *_dev entry points (graph-replayable launches) pass a device
+// row psx_step_row = [sqrt_acp, sqrt_1m_acp, lik_weight / sqrt_acp, c_ell, c_s, std, gamma, -] that overrides them.
+__device__ __forceinline__ void step_scalars_k1(const float* dsc, float& sa, float& s1, float& coef) {
+  if (dsc != nullptr) {
+    sa = __ldg(dsc);
+    s1 = __ldg(dsc + 1);
+    coef = __ldg(dsc + 2);
+  }
+}
+__device__ __forceinline__ void step_scalars_coef(const float* dsc, float& coef) {
+  if (dsc != nullptr) coef = __ldg(dsc + 2);
+}
+__device__ __forceinline__ void step_scalars_k2(const float* dsc, float& sa, float& s1, float& c_ell, float& c_s,
+                                                float& sd, float& gamma) {
+  if (dsc != nullptr) {
+    sa = __ldg(dsc);
+    s1 = __ldg(dsc + 1);
+    c_ell = __ldg(dsc + 3);
+    c_s = __ldg(dsc + 4);
+    sd = __ldg(dsc + 5);
+    gamma = __ldg(dsc + 6);
+  }
+}
+
 // ---------------------------------------------------------------- reductions (fixed order => deterministic)
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -132,16 +156,16 @@ inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // launchers implemented in the .cu files ------------------------------------------------
 int launch_pre_pointwise(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
-                         int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                         int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                          float* x0_out, cudaStream_t st);
 int launch_pre_box(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
-                   int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                   int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                    float* x0_out, cudaStream_t st);
 int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
-                       int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                       int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                        float* x0_out, float* ws, cudaStream_t st);
 int launch_pre_conv2d(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
-                      int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                      int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                       float* x0_out, float* ws, cudaStream_t st);
 int launch_op(const psx_op* op, bool adjoint, const float* in, float* out, int64_t L, float* ws,
               cudaStream_t st);

@@ -65,8 +65,9 @@ __device__ __forceinline__ float4 load_row4(const float* __restrict__ in, const 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 conv_rows(const float* __restrict__ in, const float* __restrict__ eps, float* __restrict__ out, int H, int W,
-          int TW, int pitch2, const __grid_constant__ Taps taps, float sa, float s1, float coef) {
+          int TW, int pitch2, const __grid_constant__ Taps taps, float sa, float s1, float coef, const float* __restrict__ dsc) {
   extern __shared__ __align__(16) float2 smem2[];
+  step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   const int c0 = blockIdx.x * TW;
   const int r0 = blockIdx.y * kRowTH;
@@ -429,8 +430,9 @@ template <int MODE, int K>
 __global__ void __launch_bounds__(kThreads)
 conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, float* __restrict__ out,
                int64_t total_rows, int W, int pitch2, int64_t num_tiles, const __grid_constant__ Taps taps,
-               float sa, float s1, float coef) {
+               float sa, float s1, float coef, const float* __restrict__ dsc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   constexpr int kArrays = MODE == ROWS_TWEEDIE ? 2 : 1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -821,7 +823,8 @@ constexpr int kIlStages = 3;
 template <int K>
 __global__ void __launch_bounds__(kIlThreads)
 conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t total_rows, int W, int pitch2,
-             int64_t num_tiles, const __grid_constant__ Taps taps, float coef) {
+             int64_t num_tiles, const __grid_constant__ Taps taps, float coef,
+             const float* __restrict__ dsc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float2* stages = reinterpret_cast<float2*>(smem_raw + kPipeHdr);
@@ -881,6 +884,7 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
     row_block16<K>(acc, stages + (size_t)stage * stage_f2 + rp * pitch2 + 16 * cg, taps);
     const int64_t pair = tile * (kPipeRows / 2) + rp;
     if (q_ok && pair < total_pairs) {
+      step_scalars_coef(dsc, coef);  // after the FFMA2 block: keeps the tap pairs on the uniform datapath
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float* dst = out + (2 * pair + h) * W + 16 * cg;
@@ -928,7 +932,7 @@ __global__ void __cluster_dims__(kFusedCL, 1, 1) __launch_bounds__(kThreads, 2)
 blur_k1_fused(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
               float* __restrict__ cot, float* __restrict__ err_part, int C, int64_t obs_repeat, int pitch2,
               const __grid_constant__ Taps fh, const __grid_constant__ Taps fv, const __grid_constant__ Taps av,
-              const __grid_constant__ Taps ah, float sa, float s1, float coef) {
+              const __grid_constant__ Taps ah, float sa, float s1, float coef, const float* __restrict__ dsc) {
   namespace cg = cooperative_groups;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float red[32];
@@ -936,6 +940,7 @@ blur_k1_fused(const float* __restrict__ x, const float* __restrict__ eps, const 
   const int rank = (int)cluster.block_rank();
   const int64_t pl = blockIdx.x / kFusedCL;  // plane index over L * C
   constexpr int W = kFusedW, RB = kFusedRB, HP = kFusedHP, H = kFusedCL * kFusedRB;
+  step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   float2* comp = reinterpret_cast<float2*>(smem_raw + kPipeHdr);              // 16 row pairs x pitch2
@@ -1178,7 +1183,7 @@ int sm_count();
 
 template <int MODE>
 static int run_rows(const psx_op* op, const Taps& t, const float* in, const float* eps, float* out,
-                    int64_t planes, float sa, float s1, float w, cudaStream_t st) {
+                    int64_t planes, float sa, float s1, float w, const float* dsc, cudaStream_t st) {
   if ((op->W & 7) == 0 && op->W <= 512 && !getenv("PSX_NO_PIPE")) {
     const int pitch2 = row_pitch2(op->W + t.k);
     const int arrays = MODE == ROWS_TWEEDIE ? 2 : 1;
@@ -1199,7 +1204,7 @@ static int run_rows(const psx_op* op, const Taps& t, const float* in, const floa
     int64_t grid = (int64_t)occ * sm_count();                                                                  \
     if (grid > num_tiles) grid = num_tiles;                                                                    \
     conv_rows_pipe<MODE, KK><<<(unsigned)grid, kThreads, smem, st>>>(in, eps, out, total_rows, op->W, pitch2,  \
-                                                                     num_tiles, t, sa, s1, coef);              \
+                                                                     num_tiles, t, sa, s1, coef, dsc);         \
   }
     // the occupancy cache is per instantiation and assumes one (W, taps) geometry per process and mode;
     // other geometries only change smem by a few KB and keep the same CTA count per SM in practice
@@ -1217,7 +1222,7 @@ static int run_rows(const psx_op* op, const Taps& t, const float* in, const floa
     attr_done = true;
   }
   dim3 grid(ceil_div(op->W, TW), ceil_div(op->H, kRowTH), (unsigned)planes);
-  conv_rows<MODE><<<grid, kThreads, smem, st>>>(in, eps, out, op->H, op->W, TW, pitch, t, sa, s1, coef);
+  conv_rows<MODE><<<grid, kThreads, smem, st>>>(in, eps, out, op->H, op->W, TW, pitch, t, sa, s1, coef, dsc);
   return check_cuda(cudaGetLastError(), "conv_rows launch");
 }
 
@@ -1275,7 +1280,7 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
 // cols16 + rows_il tail of K1 (h1 in ws, row-major)  ->  cot.  Returns -1 when the geometry does not qualify.
 template <int K>
 static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot, float* err_part, int64_t planes,
-                         int64_t obs_repeat, float w, float sa, cudaStream_t st) {
+                         int64_t obs_repeat, float w, float sa, const float* dsc, cudaStream_t st) {
   const int W = op->W, H = op->H;
   CUtensorMap map;
   if (!make_strip_map(&map, ws, planes * H, W, H)) return -1;
@@ -1307,12 +1312,12 @@ static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot
   int64_t grid_r = (int64_t)occ_r * sm_count();
   if (grid_r > tiles_r) grid_r = tiles_r;
   const float coef = (float)((double)w / (double)sa);
-  conv_rows_il<K><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r, op->ah, coef);
+  conv_rows_il<K><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r, op->ah, coef, dsc);
   return check_cuda(cudaGetLastError(), "conv_rows_il launch");
 }
 
 int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
-                       int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                       int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                        float* x0_out, float* ws, cudaStream_t st) {
   if (x0_out) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: d_x0_out is not produced for blur operators");
   const int64_t planes = L * op->C;
@@ -1334,22 +1339,22 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
     }
     const float coef = (float)((double)w / (double)sa);
     blur_k1_fused<K><<<(unsigned)(planes * kFusedCL), kThreads, smem, st>>>(
-        x, eps, y, cot, err_part, op->C, obs_repeat, pitch2, op->fh, op->fv, op->av, op->ah, sa, s1, coef);
+        x, eps, y, cot, err_part, op->C, obs_repeat, pitch2, op->fh, op->fv, op->av, op->ah, sa, s1, coef, dsc);
     return check_cuda(cudaGetLastError(), "blur_k1_fused launch");
   }
-  int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x, eps, ws, planes, sa, s1, w, st);
+  int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x, eps, ws, planes, sa, s1, w, dsc, st);
   if (rc) return rc;
   const int kk = op->fv.k;
   if (op->W % kColTC == 0 && op->W <= 256 && op->H % 16 == 0 && op->H <= 256 && op->av.k == kk && op->ah.k == kk &&
       op->col_tc == kColTC && !getenv("PSX_NO_PIPE") && !getenv("PSX_NO_FAST16")) {
     int r2 = -1;
-    if (kk == 40) r2 = run_fast_tail<40>(op, y, ws, cot, err_part, planes, obs_repeat, w, sa, st);
-    else if (kk == 16) r2 = run_fast_tail<16>(op, y, ws, cot, err_part, planes, obs_repeat, w, sa, st);
+    if (kk == 40) r2 = run_fast_tail<40>(op, y, ws, cot, err_part, planes, obs_repeat, w, sa, dsc, st);
+    else if (kk == 16) r2 = run_fast_tail<16>(op, y, ws, cot, err_part, planes, obs_repeat, w, sa, dsc, st);
     if (r2 >= 0) return r2;
   }
   rc = run_cols<true>(op, op->fv, op->av, ws, y, ws, err_part, planes, obs_repeat, st);
   if (rc) return rc;
-  return run_rows<ROWS_COT>(op, op->ah, ws, nullptr, cot, planes, sa, s1, w, st);
+  return run_rows<ROWS_COT>(op, op->ah, ws, nullptr, cot, planes, sa, s1, w, dsc, st);
 }
 
 // ------------------------------------------------------------------------------------------ sparse 2-D
@@ -1364,7 +1369,8 @@ __global__ void __launch_bounds__(kThreads)
 conv2d_sparse(const float* __restrict__ in, const float* __restrict__ eps, const float* __restrict__ y,
               float* __restrict__ out, float* __restrict__ err_part, const Tap2D* __restrict__ taps,
               int ntaps, int C, int H, int W, int kh, int kw, int64_t obs_repeat, float sa, float s1,
-              float wgt) {
+              float wgt, const float* __restrict__ dsc) {
+  step_scalars_k1(dsc, sa, s1, wgt);
   const TweedieC tc = make_tc(s1, sa);
   extern __shared__ __align__(16) float smem[];
   __shared__ Tap2D stap[kC2Chunk];
@@ -1437,7 +1443,7 @@ int conv2d_err_parts(const psx_op* op) {
 
 template <int MODE, bool ADJ>
 static int run_conv2d(const psx_op* op, const float* in, const float* eps, const float* y, float* out,
-                      float* err_part, int64_t planes, int64_t obs_repeat, float sa, float s1, float w,
+                      float* err_part, int64_t planes, int64_t obs_repeat, float sa, float s1, float w, const float* dsc,
                       cudaStream_t st) {
   const size_t smem = (size_t)(kC2Tile + op->kh - 1) * (kC2Tile + op->kw - 1) * sizeof(float);
   static bool attr_done = false;
@@ -1449,18 +1455,18 @@ static int run_conv2d(const psx_op* op, const float* in, const float* eps, const
   const float wgt = MODE == C2_COT ? (float)((double)w / (double)sa) : w;
   conv2d_sparse<MODE, ADJ><<<grid, kThreads, smem, st>>>(in, eps, y, out, err_part, op->d_taps_f,
                                                          op->n_taps2d, op->C, op->H, op->W, op->kh, op->kw,
-                                                         obs_repeat, sa, s1, wgt);
+                                                         obs_repeat, sa, s1, wgt, dsc);
   return check_cuda(cudaGetLastError(), "conv2d_sparse launch");
 }
 
 int launch_pre_conv2d(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
-                      int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                      int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                       float* x0_out, float* ws, cudaStream_t st) {
   if (x0_out) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: d_x0_out is not produced for blur operators");
   const int64_t planes = L * op->C;
-  int rc = run_conv2d<C2_RESIDUAL, false>(op, x, eps, y, ws, err_part, planes, obs_repeat, sa, s1, w, st);
+  int rc = run_conv2d<C2_RESIDUAL, false>(op, x, eps, y, ws, err_part, planes, obs_repeat, sa, s1, w, dsc, st);
   if (rc) return rc;
-  return run_conv2d<C2_COT, true>(op, ws, nullptr, nullptr, cot, nullptr, planes, 1, sa, s1, w, st);
+  return run_conv2d<C2_COT, true>(op, ws, nullptr, nullptr, cot, nullptr, planes, 1, sa, s1, w, dsc, st);
 }
 
 // ------------------------------------------------------------------------------------------ stand-alone A / A^T
@@ -1472,18 +1478,18 @@ int launch_op(const psx_op* op, bool adjoint, const float* in, float* out, int64
   switch (op->kind) {
     case PSX_OP_SEPBLUR: {
       if (!adjoint) {  // y = V(H(x))
-        int rc = run_rows<ROWS_PLAIN>(op, op->fh, in, nullptr, ws, planes, 1.f, 0.f, 1.f, st);
+        int rc = run_rows<ROWS_PLAIN>(op, op->fh, in, nullptr, ws, planes, 1.f, 0.f, 1.f, nullptr, st);
         if (rc) return rc;
         return run_cols<false>(op, op->fv, op->fv, ws, nullptr, out, nullptr, planes, 1, st);
       }
       int rc = run_cols<false>(op, op->av, op->av, in, nullptr, ws, nullptr, planes, 1, st);
       if (rc) return rc;
-      return run_rows<ROWS_PLAIN>(op, op->ah, ws, nullptr, out, planes, 1.f, 0.f, 1.f, st);
+      return run_rows<ROWS_PLAIN>(op, op->ah, ws, nullptr, out, planes, 1.f, 0.f, 1.f, nullptr, st);
     }
     case PSX_OP_CONV2D:
       if (!adjoint)
-        return run_conv2d<C2_PLAIN, false>(op, in, nullptr, nullptr, out, nullptr, planes, 1, 1.f, 0.f, 1.f, st);
-      return run_conv2d<C2_PLAIN, true>(op, in, nullptr, nullptr, out, nullptr, planes, 1, 1.f, 0.f, 1.f, st);
+        return run_conv2d<C2_PLAIN, false>(op, in, nullptr, nullptr, out, nullptr, planes, 1, 1.f, 0.f, 1.f, nullptr, st);
+      return run_conv2d<C2_PLAIN, true>(op, in, nullptr, nullptr, out, nullptr, planes, 1, 1.f, 0.f, 1.f, nullptr, st);
     default:
       return launch_op_pointwise(op, adjoint, in, out, L, st);
   }

@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(kThreads)
 k1_pointwise_v4(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
                 const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part,
                 int slots, float* __restrict__ x0_out, int64_t n, int64_t chunk4, int64_t obs_repeat, float sa,
-                float s1, float coef) {
+                float s1, float coef, const float* __restrict__ dsc) {
+  step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(kThreads)
 k1_pointwise_s(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
                const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part,
                int slots, float* __restrict__ x0_out, int64_t n, int64_t chunk, int64_t obs_repeat, float sa,
-               float s1, float coef) {
+               float s1, float coef, const float* __restrict__ dsc) {
+  step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
@@ -142,7 +144,7 @@ int one_wave_parts(int slots, int64_t L, int64_t units_per_sample, int cap) {
 int pointwise_parts(int64_t) { return kMaxParts; }  // size of the per-sample partial-sum row
 
 int launch_pre_pointwise(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
-                         int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                         int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                          float* x0_out, cudaStream_t st) {
   const int64_t n = op->n;
   const int slots = op->err_parts;
@@ -156,7 +158,7 @@ int launch_pre_pointwise(const psx_op* op, const float* x, const float* eps, con
     const int parts = one_wave_parts(rs, L, n / 4, slots);                                             \
     const int64_t chunk4 = (n / 4 + parts - 1) / parts;                                                \
     k1_pointwise_v4<M, X><<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(                              \
-        x, eps, y, op->d_keep, cot, err_part, slots, x0_out, n, chunk4, obs_repeat, sa, s1, coef);     \
+        x, eps, y, op->d_keep, cot, err_part, slots, x0_out, n, chunk4, obs_repeat, sa, s1, coef, dsc);\
   }
     if (mask) {
       if (x0_out) PSX_LAUNCH(true, true) else PSX_LAUNCH(true, false)
@@ -170,10 +172,10 @@ int launch_pre_pointwise(const psx_op* op, const float* x, const float* eps, con
     dim3 grid(parts, (unsigned)L);
     if (mask)
       k1_pointwise_s<true><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, slots, x0_out, n,
-                                                      chunk, obs_repeat, sa, s1, coef);
+                                                      chunk, obs_repeat, sa, s1, coef, dsc);
     else
       k1_pointwise_s<false><<<grid, kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, slots, x0_out, n,
-                                                       chunk, obs_repeat, sa, s1, coef);
+                                                       chunk, obs_repeat, sa, s1, coef, dsc);
   }
   return check_cuda(cudaGetLastError(), "k1_pointwise launch");
 }
@@ -190,7 +192,8 @@ template <int F>
 __global__ void __launch_bounds__(kThreads)
 k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
        float* __restrict__ cot, float* __restrict__ err_part, int slots, float* __restrict__ x0_out,
-       int planes, int H, int W, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef) {
+       int planes, int H, int W, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef, const float* __restrict__ dsc) {
+  step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int Hc = H / F, Wc = W / F;
@@ -260,7 +263,8 @@ k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* 
 __global__ void __launch_bounds__(kThreads)
 k1_box_any(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
            float* __restrict__ cot, float* __restrict__ err_part, int slots, float* __restrict__ x0_out,
-           int planes, int H, int W, int F, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef) {
+           int planes, int H, int W, int F, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef, const float* __restrict__ dsc) {
+  step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int Hc = H / F, Wc = W / F;
@@ -297,7 +301,7 @@ k1_box_any(const float* __restrict__ x, const float* __restrict__ eps, const flo
 int box_parts(int64_t) { return kMaxParts; }
 
 int launch_pre_box(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
-                   int64_t obs_repeat, float sa, float s1, float w, float* cot, float* err_part,
+                   int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                    float* x0_out, cudaStream_t st) {
   const int slots = op->err_parts;
   const int F = op->factor;
@@ -310,7 +314,7 @@ int launch_pre_box(const psx_op* op, const float* x, const float* eps, const flo
     const int64_t chunk = (op->n_y + parts - 1) / parts;                                              \
     KERNEL<<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(x, eps, y, cot, err_part, slots, x0_out,    \
                                                           op->C, op->H, op->W, __VA_ARGS__ chunk,     \
-                                                          obs_repeat, sa, s1, coef);                  \
+                                                          obs_repeat, sa, s1, coef, dsc);             \
   }
   if (F == 4 && op->W % 4 == 0) PSX_BOX(k1_box<4>, )
   else if (F == 2) PSX_BOX(k1_box<2>, )
@@ -328,7 +332,9 @@ __global__ void __launch_bounds__(kThreads)
 k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ cot,
            const float* __restrict__ vjp, const float* __restrict__ z, const float* __restrict__ err_part,
            int err_parts, int64_t n, int64_t chunk4, float sa, float s1, float c_ell, float c_s,
-           float sd, float gamma, float* __restrict__ x_next, float* __restrict__ err_out) {
+           float sd,
+           float gamma, float* __restrict__ x_next, float* __restrict__ err_out, const float* __restrict__ dsc) {
+  step_scalars_k2(dsc, sa, s1, c_ell, c_s, sd, gamma);
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
@@ -383,7 +389,8 @@ __global__ void __launch_bounds__(kThreads)
 k2_post_s(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ cot,
           const float* __restrict__ vjp, const float* __restrict__ z, const float* __restrict__ err_part,
           int err_parts, int64_t n, int64_t chunk, float sa, float s1, float c_ell, float c_s, float sd,
-          float gamma, float* __restrict__ x_next, float* __restrict__ err_out) {
+           float gamma, float* __restrict__ x_next, float* __restrict__ err_out, const float* __restrict__ dsc) {
+  step_scalars_k2(dsc, sa, s1, c_ell, c_s, sd, gamma);
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
@@ -407,8 +414,8 @@ k2_post_s(const float* __restrict__ x, const float* __restrict__ eps, const floa
 
 int launch_post(const float* x, const float* eps, const float* cot, const float* vjp, const float* z,
                 const float* err_part, int err_parts, int64_t L, int64_t n, float sa, float s1,
-                float c_ell, float c_s, float sd, float gamma, float* x_next, float* err_out,
-                cudaStream_t st) {
+                float c_ell, float c_s, float sd, float gamma, const float* dsc, float* x_next,
+                float* err_out, cudaStream_t st) {
   const bool has_z = z != nullptr;
 #define PSX_POST(KERNEL, UNITS)                                                                        \
   {                                                                                                    \
@@ -418,7 +425,7 @@ int launch_post(const float* x, const float* eps, const float* cot, const float*
     const int64_t chunk = ((UNITS) + parts - 1) / parts;                                               \
     KERNEL<<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, \
                                                           chunk, sa, s1, c_ell, c_s, sd, gamma, x_next, \
-                                                          err_out);                                    \
+                                                          err_out, dsc);                               \
   }
   if (n % 4 == 0) {
     if (has_z) PSX_POST(k2_post_v4<true>, n / 4) else PSX_POST(k2_post_v4<false>, n / 4)

@@ -6,8 +6,12 @@ from ..networks import EpsilonNetwork
 
 
 class PosteriorSampler(ABC):
-    def __init__(self, network: EpsilonNetwork):
+    def __init__(self, network: EpsilonNetwork, cuda_graph: bool = False):
+        """``network`` as in the reference.  ``cuda_graph=True`` (DPS / PGDM) records one guided timestep as a CUDA
+        graph and replays it for the whole loop; it needs a network whose ``forward`` takes the timestep as a
+        device tensor without synchronising, and fails loudly otherwise (there is no silent eager fallback)."""
         self._epsilon_network = network
+        self.cuda_graph = bool(cuda_graph)
 
     @staticmethod
     def _flatten_leading(x: Tensor, *, x_shape: Shape) -> tuple[Tensor, Shape]:

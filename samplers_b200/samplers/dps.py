@@ -33,7 +33,7 @@ from ..networks.base import tweedie_scalars
 from ..noise import NoiseModel
 from .base import PosteriorSampler
 from .utils.batch_view import BatchView
-from .utils.bridge_kernels import StepScalars, plan_steps
+from .utils.bridge_kernels import StepScalars, plan_steps, step_rows
 
 Condition_co = TypeVar("Condition_co", covariant=True)
 
@@ -86,9 +86,100 @@ class DPSRun:
         self.err = torch.empty((self.L,), device=self.device, dtype=torch.float32)
         wsb = self.op.workspace_bytes(self.L)
         self.ws = torch.empty(wsb // 4, device=self.device, dtype=torch.float32) if wsb else None
+        self._graph: torch.cuda.CUDAGraph | None = None
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the timestep
+    def step_table(self) -> Tensor:
+        """(num_steps, PSX_STEP_ROW) fp32 host table for the *_dev entry points (utils/bridge_kernels.step_rows)."""
+        return step_rows(self.plan, self.weight, self.gamma if self._fixed_scale is None else self._fixed_scale)
+
+    def _timestep_body(self) -> None:
+        """One guided timestep with every per-step quantity read from device memory (row k_dev of the table)."""
+        torch.index_select(self.table, 0, self.k_dev, out=self.row)
+        torch.index_select(self.t_table, 0, self.k_dev, out=self.t_dev)
+        x_in = self.x.view(self.view.flat_shape).detach().requires_grad_()
+        eps = self.net.forward(x_in, self.t_dev)
+        eps_flat = eps.detach().reshape(self.L, self.n)
+        if not eps_flat.is_contiguous():
+            eps_flat = eps_flat.contiguous()
+        _native.dps_pre_dev(self.op, self.x, eps_flat, self.y, self.obs_repeat, self.row, self.cot, self.err_part,
+                            self.ws)
+        (v,) = torch.autograd.grad(eps, x_in, grad_outputs=self.cot.view_as(eps))
+        v = v.reshape(self.L, self.n)
+        if not v.is_contiguous():
+            v = v.contiguous()
+        if self._draw_in_graph:
+            self.z.normal_()
+        fixed = self._fixed_scale is not None
+        # in place: every element of x is read and written by the same thread of K2
+        _native.dps_post_dev(self.x, eps_flat, self.cot, v, self.z, None if fixed else self.err_part,
+                             0 if fixed else self.op.err_parts, self.n, self.row, self.x,
+                             None if fixed else self.err)
+        self.k_dev.add_(1)
+
+    def capture(self, warmup: int = 2, draw_in_graph: bool | None = None) -> None:
+        """Record one guided timestep -- network forward, K1, network VJP, noise draw, K2, step counter -- as a
+        CUDA graph; ``step`` then replays it.  The step scalars and the timestep fed to the network come from
+        device tables indexed by a device counter, so that one graph serves every timestep and the host issues
+        ONE launch per timestep instead of ~2000.  The network must accept the timestep
+        as a 1-element device tensor without synchronising (no ``int(t)`` / ``.item()`` in ``forward``).
+        ``draw_in_graph`` (default: True iff the sampler uses the stock ``torch.randn`` draw) puts the N(0, 1) draw
+        inside the graph; with False the noise buffer ``self.z`` is filled before each replay, from ``step``'s
+        ``z`` argument or the ``draw`` hook."""
+        if self._graph is not None:
+            return
+        dev = self.device
+        self.table = self.step_table().to(dev)
+        self.t_table = torch.tensor([sc.t for sc in self.plan], dtype=torch.int64, device=dev)
+        self.row = torch.zeros((1, _native.STEP_ROW), dtype=torch.float32, device=dev)
+        self.t_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.k_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.z = torch.zeros((self.L, self.n), dtype=torch.float32, device=dev)
+        self._draw_in_graph = (self.draw is _default_draw) if draw_in_graph is None else bool(draw_in_graph)
+        self._k_host = 0
+        keep = self.x.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        # Eager warm-up off the capture stream (autograd, cuDNN autotuning), with torch's sync detector armed: a
+        # network that synchronises on the timestep raises HERE, before a capture could be left half-open.
+        sync_mode = torch.cuda.get_sync_debug_mode()
+        torch.cuda.set_sync_debug_mode("error")
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    self._timestep_body()
+        finally:
+            torch.cuda.set_sync_debug_mode(sync_mode)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.x.copy_(keep)
+        self.k_dev.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._timestep_body()
+        self.x.copy_(keep)                               # capture does not execute, but keep this explicit
+        self.k_dev.zero_()
+        self._graph = graph
+
+    def _replay(self, k: int, z: Tensor | None) -> None:
+        if k != self._k_host:
+            self.k_dev.fill_(k)
+        if z is not None:
+            if self._draw_in_graph:
+                raise ValueError("this graph draws its noise itself; capture(draw_in_graph=False) to inject z")
+            if z.data_ptr() != self.z.data_ptr():        # step(k, z=run.z): the caller filled the buffer in place
+                self.z.copy_(z.reshape(self.L, self.n))
+        elif not self._draw_in_graph:
+            if self.draw is _default_draw:
+                self.z.normal_()
+            else:
+                self.z.copy_(self.draw(self.view.flat_shape, self.device, self.dtype).reshape(self.L, self.n))
+        self._graph.replay()
+        self._k_host = k + 1
 
     def step(self, k: int, z: Tensor | None = None) -> None:
         """Guided timestep k (0 = noisiest).  ``z`` overrides the injected noise draw."""
+        if self._graph is not None:
+            return self._replay(k, z)
         sc = self.plan[k]
         x_in = self.x.view(self.view.flat_shape).detach().requires_grad_()
         eps = self.net.forward(x_in, sc.t)                                   # graph kept for the VJP
@@ -160,6 +251,8 @@ class DPSSampler(PosteriorSampler, Generic[Condition_co]):
             print(f"Warning: Unused args={args}, kwargs={kwargs} in DPSSampler")
         run = self.prepare(inverse_problem, num_sampling_steps, num_reconstructions, gamma, eta, condition)
         try:
+            if self.cuda_graph:
+                run.capture()
             for k in range(run.num_steps):
                 run.step(k)
             x0 = run.view.unflatten(run.finalize().view(run.view.flat_shape))

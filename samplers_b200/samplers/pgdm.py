@@ -50,6 +50,8 @@ class PGDMSampler(PosteriorSampler, Generic[Condition_co]):
                 return float(gw * torch.tensor(sc.sqrt_1m_acp, dtype=torch.float32))
 
             run = DPSRun(net, inverse_problem, view, 0.0, eta, self.draw, weight=2.0 * gain, fixed_scale=scale)
+            if self.cuda_graph:
+                run.capture()
             for k in range(run.num_steps):
                 run.step(k)
             x0 = view.unflatten(run.finalize().view(view.flat_shape))

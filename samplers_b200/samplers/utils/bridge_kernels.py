@@ -70,6 +70,24 @@ def plan_steps(acp: Tensor, timesteps: Sequence[int], eta: float) -> list[StepSc
     return plan
 
 
+STEP_ROW = 8  # PSX_STEP_ROW (include/psx.h)
+
+
+def step_rows(plan: Sequence[StepScalars], weight: float, gamma) -> Tensor:
+    """Device-table form of ``plan`` for psx_dps_pre_dev / psx_dps_post_dev: one fp32 row
+    [sqrt_acp, sqrt_1m_acp, weight / sqrt_acp, c_ell, c_s, std, gamma, 0] per guided step, holding exactly the
+    fp32 values the by-value entry points receive (weight / sqrt_acp is one fp32 division, as inside libpsx).
+    ``gamma`` is a float or a callable ``StepScalars -> float`` (PGDM's per-step scale)."""
+    rows = torch.zeros((len(plan), STEP_ROW), dtype=torch.float32)
+    w = torch.tensor(float(weight), dtype=torch.float32)
+    for k, sc in enumerate(plan):
+        g = gamma(sc) if callable(gamma) else gamma
+        coef = float(w / torch.tensor(sc.sqrt_acp, dtype=torch.float32))
+        rows[k, :7] = torch.tensor([sc.sqrt_acp, sc.sqrt_1m_acp, coef, sc.c_ell, sc.c_s, sc.std, float(g)],
+                                   dtype=torch.float64).to(torch.float32)
+    return rows
+
+
 # ---------------------------------------------------------------------------- utilities with the reference's names
 def compute_bridge_kernel_statistics(x_ell: Tensor, x_s: Tensor, epsilon_net, ell: int, t: int, s: int,
                                      eta: float = 1.0) -> BridgeStatistics:

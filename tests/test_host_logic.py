@@ -194,3 +194,20 @@ def test_bench_reference_arm_runs_nothing_on_nonzero_rank():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"],
                          capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_step_rows_hold_the_by_value_scalars():
+    """Device step table (psx_dps_*_dev): fp32 copies of the plan, w / sa as ONE fp32 division (as libpsx does)."""
+    import numpy as np
+    from oracle.schedule import ddpm_linear_alphas_cumprod, leading_timesteps_ascending, padded_clipped_acp
+    from samplers_b200.samplers.utils.bridge_kernels import STEP_ROW, plan_steps, step_rows
+    acp = padded_clipped_acp(ddpm_linear_alphas_cumprod())
+    plan = plan_steps(acp, leading_timesteps_ascending(20).tolist(), eta=1.0)
+    rows = step_rows(plan, 400.0, 1.5)
+    assert rows.shape == (len(plan), STEP_ROW) and rows.dtype == torch.float32
+    for k, sc in enumerate(plan):
+        want = [sc.sqrt_acp, sc.sqrt_1m_acp, float(np.float32(400.0) / np.float32(sc.sqrt_acp)), sc.c_ell, sc.c_s,
+                sc.std, 1.5, 0.0]
+        assert rows[k].tolist() == [float(np.float32(v)) for v in want]
+    per_step = step_rows(plan, 2.0, lambda sc: 0.5 * sc.sqrt_1m_acp)
+    assert per_step[3, 6].item() == float(np.float32(0.5 * plan[3].sqrt_1m_acp))
