@@ -95,6 +95,27 @@ PSX_API int psx_op_apply(const psx_op* op, const float* d_x, float* d_y, int64_t
 PSX_API int psx_op_adjoint(const psx_op* op, const float* d_y, float* d_x, int64_t L,
                    void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ data formats either side of the loop
+ * psx_observe -- simulate an observation: d_y = A d_x + eps,  eps = noise_scale * d_noise + noise_shift
+ * (each op rounded as torch does).  Replaces InverseProblem.from_clean_data (samplers/inverse_problem.py:35-67):
+ *   GaussianNoise.sample (noise.py:81-92):  d_noise ~ N(0,1),            noise_scale = sigma, noise_shift = 0
+ *   PoissonNoise.sample  (noise.py:125-138): d_noise = k ~ Poisson(rate), noise_scale = 1,     noise_shift = -rate
+ * The random draw itself stays with the caller's generator.  d_noise (L, n_y) may be NULL (noise-free). */
+PSX_API int psx_observe(const psx_op* op, const float* d_x, const float* d_noise, float noise_scale,
+                        float noise_shift, float* d_y, int64_t L, void* d_workspace, size_t workspace_bytes,
+                        void* stream);
+/* the noise half alone, in place: d_y += noise_scale * d_noise + noise_shift (observations whose layout is not the
+ * operator descriptor's, e.g. the gathered (L, m) form of inpainting) */
+PSX_API int psx_add_noise(float* d_y, const float* d_noise, int64_t numel, float noise_scale, float noise_shift,
+                          void* stream);
+/* Image tensors <-> bytes on the device, so that only uint8 crosses PCIe.  Replaces samplers/utils/image.py:
+ *   psx_image_to_u8  : tensor_to_pil (:9-32)  clamp to [-1,1], (x+1)*0.5, then torchvision's mul(255).byte();
+ *                      (images, C, H, W) float -> (images, H, W, C) uint8
+ *   psx_image_from_u8: pil_to_tensor (:35-64) u8/255 (to_tensor), *2 - 1;  (images, H, W, C) -> (images, C, H, W) */
+PSX_API int psx_image_to_u8(const float* d_chw, uint8_t* d_hwc, int64_t images, int C, int H, int W, void* stream);
+PSX_API int psx_image_from_u8(const uint8_t* d_hwc, float* d_chw, int64_t images, int C, int H, int W,
+                              void* stream);
+
 /* Gather / scatter form of the inpainting operator (flatten=True in the reference:
  * inpainting.py:141-145 gather of the kept pixels, :178-187 scatter into zeros).
  *   psx_gather : d_out[l, j] = d_in[l, d_idx[j]]           (L, n) -> (L, m)

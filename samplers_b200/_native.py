@@ -38,16 +38,20 @@ PROTOTYPES = {
     "psx_op_workspace_bytes": (C.c_size_t, [_opp, _i64]),
     "psx_op_apply": (C.c_int, [_opp, _f32p, _f32p, _i64, _vp, C.c_size_t, _vp]),
     "psx_op_adjoint": (C.c_int, [_opp, _f32p, _f32p, _i64, _vp, C.c_size_t, _vp]),
+    "psx_observe": (C.c_int, [_opp, _f32p, _f32p, _f, _f, _f32p, _i64, _vp, C.c_size_t, _vp]),
+    "psx_add_noise": (C.c_int, [_f32p, _f32p, _i64, _f, _f, _vp]),
+    "psx_image_to_u8": (C.c_int, [_f32p, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp]),
+    "psx_image_from_u8": (C.c_int, [_vp, _f32p, _i64, C.c_int, C.c_int, C.c_int, _vp]),
     "psx_gather": (C.c_int, [_f32p, _vp, _f32p, _i64, _i64, _i64, _vp]),
     "psx_scatter": (C.c_int, [_f32p, _vp, _f32p, _i64, _i64, _i64, _vp]),
     "psx_dps_pre": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f, _f, _f, _f32p, _f32p, _f32p,
                               _vp, C.c_size_t, _vp]),
     "psx_dps_post": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64,
                                _f, _f, _f, _f, _f, _f, _f32p, _f32p, _vp]),
-    "psx_dps_pre_dev": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
-                                  C.c_size_t, C.c_void_p]),
+    "psx_dps_pre_dev": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _vp,
+                                  C.c_size_t, _vp]),
     "psx_dps_post_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _f32p,
-                                   _f32p, C.c_void_p]),
+                                   _f32p, _vp]),
     "psx_tweedie": (C.c_int, [_f32p, _f32p, _i64, _i64, _f, _f, _f32p, _f32p, _f32p, _vp]),
     "psx_bridge_update": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, _f, _f32p, _vp]),
     "psx_lincomb3": (C.c_int, [_f32p, _f, _f32p, _f, _f32p, _f, _f32p, _i64, _vp]),
@@ -317,4 +321,36 @@ def adamw_step(param, grad, m, v, lr: float, step: int, *, beta1=0.9, beta2=0.99
                                     beta1, beta2, eps, weight_decay, step, ptr(flags), flag_in, ptr(loss_parts),
                                     0 if loss_parts is None else loss_parts.numel(), loss_scale, loss_threshold,
                                     stream_ptr(param.device)))
+    launch_count += 1
+
+
+def observe(op: NativeOp, x, noise, scale: float, shift: float, y, ws=None) -> None:
+    """y = A x + (scale * noise + shift); ``noise`` may be None."""
+    global launch_count
+    L = x.shape[0]
+    with torch.cuda.device(x.device):
+        check(load().psx_observe(op.handle, x.data_ptr(), ptr(noise), scale, shift, y.data_ptr(), L, ptr(ws),
+                                 0 if ws is None else ws.numel() * 4, stream_ptr(x.device)))
+    launch_count += 1
+
+
+def add_noise(y, noise, scale: float, shift: float) -> None:
+    """In place: y += scale * noise + shift (torch's two roundings)."""
+    global launch_count
+    with torch.cuda.device(y.device):
+        check(load().psx_add_noise(y.data_ptr(), noise.data_ptr(), y.numel(), scale, shift, stream_ptr(y.device)))
+    launch_count += 1
+
+
+def image_to_u8(chw, hwc, images: int, c: int, h: int, w: int) -> None:
+    global launch_count
+    with torch.cuda.device(chw.device):
+        check(load().psx_image_to_u8(chw.data_ptr(), hwc.data_ptr(), images, c, h, w, stream_ptr(chw.device)))
+    launch_count += 1
+
+
+def image_from_u8(hwc, chw, images: int, c: int, h: int, w: int) -> None:
+    global launch_count
+    with torch.cuda.device(hwc.device):
+        check(load().psx_image_from_u8(hwc.data_ptr(), chw.data_ptr(), images, c, h, w, stream_ptr(hwc.device)))
     launch_count += 1

@@ -30,6 +30,9 @@ int launch_post(const float*, const float*, const float*, const float*, const fl
                 cudaStream_t);
 int launch_tweedie(const float*, const float*, int64_t, int64_t, float, float, float*, float*, float*,
                    cudaStream_t);
+int launch_add_noise(float*, const float*, int64_t, float, float, cudaStream_t);
+int launch_image_to_u8(const float*, uint8_t*, int64_t, int, int64_t, cudaStream_t);
+int launch_image_from_u8(const uint8_t*, float*, int64_t, int, int64_t, cudaStream_t);
 int launch_gather(bool, const float*, const int64_t*, float*, int64_t, int64_t, int64_t, cudaStream_t);
 int launch_bridge_update(const float*, const float*, const float*, const float*, int64_t, float, float, float,
                          float, float, float, float*, cudaStream_t);
@@ -199,6 +202,36 @@ PSX_API int psx_op_adjoint(const psx_op* op, const float* d_y, float* d_x, int64
   PSX_REQUIRE(op && d_x && d_y && L > 0, "psx_op_adjoint: null argument or L <= 0");
   if (int rc = check_ws(op, L, ws, ws_bytes)) return rc;
   return launch_op(op, true, d_y, d_x, L, (float*)ws, (cudaStream_t)stream);
+}
+
+PSX_API int psx_observe(const psx_op* op, const float* d_x, const float* d_noise, float noise_scale, float noise_shift,
+                        float* d_y, int64_t L, void* ws, size_t ws_bytes, void* stream) {
+  PSX_REQUIRE(op && d_x && d_y && L > 0, "psx_observe: null argument or L <= 0");
+  PSX_REQUIRE(d_x != d_y, "psx_observe: d_y must not alias d_x");
+  PSX_REQUIRE(std::isfinite(noise_scale) && std::isfinite(noise_shift), "psx_observe: non-finite noise parameter");
+  if (int rc = check_ws(op, L, ws, ws_bytes)) return rc;
+  if (int rc = launch_op(op, false, d_x, d_y, L, (float*)ws, (cudaStream_t)stream)) return rc;
+  if (!d_noise) return PSX_OK;
+  return launch_add_noise(d_y, d_noise, L * op->n_y, noise_scale, noise_shift, (cudaStream_t)stream);
+}
+
+PSX_API int psx_add_noise(float* d_y, const float* d_noise, int64_t numel, float noise_scale, float noise_shift,
+                          void* stream) {
+  PSX_REQUIRE(d_y && d_noise && numel > 0, "psx_add_noise: null pointer or empty tensor");
+  PSX_REQUIRE(std::isfinite(noise_scale) && std::isfinite(noise_shift), "psx_add_noise: non-finite noise parameter");
+  return launch_add_noise(d_y, d_noise, numel, noise_scale, noise_shift, (cudaStream_t)stream);
+}
+
+PSX_API int psx_image_to_u8(const float* d_chw, uint8_t* d_hwc, int64_t images, int C, int H, int W, void* stream) {
+  PSX_REQUIRE(d_chw && d_hwc, "psx_image_to_u8: null pointer");
+  PSX_REQUIRE(images > 0 && C > 0 && C <= 16 && H > 0 && W > 0, "psx_image_to_u8: bad sizes");
+  return launch_image_to_u8(d_chw, d_hwc, images, C, (int64_t)H * W, (cudaStream_t)stream);
+}
+
+PSX_API int psx_image_from_u8(const uint8_t* d_hwc, float* d_chw, int64_t images, int C, int H, int W, void* stream) {
+  PSX_REQUIRE(d_chw && d_hwc, "psx_image_from_u8: null pointer");
+  PSX_REQUIRE(images > 0 && C > 0 && C <= 16 && H > 0 && W > 0, "psx_image_from_u8: bad sizes");
+  return launch_image_from_u8(d_hwc, d_chw, images, C, (int64_t)H * W, (cudaStream_t)stream);
 }
 
 PSX_API int psx_gather(const float* d_in, const int64_t* d_idx, float* d_out, int64_t L, int64_t n, int64_t m,

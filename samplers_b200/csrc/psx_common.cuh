@@ -16,6 +16,7 @@ constexpr int kMaxParts = 64;  // upper bound on per-sample partial sums (pointw
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 int check_cuda(cudaError_t e, const char* what);
+int sm_count();
 
 #define PSX_REQUIRE(cond, msg) \
   do {                         \

@@ -38,8 +38,22 @@ class InverseProblem:
     @classmethod
     def from_clean_data(cls, x_true: Tensor, *, operator: Operator, noise: NoiseModel,
                         rng: RNG = None) -> "InverseProblem":
-        """Simulate y = A(x_true) + eps, eps ~ noise.sample (rng makes the draw reproducible)."""
+        """Simulate y = A(x_true) + eps, eps ~ noise.sample (rng makes the draw reproducible).  The operator pass
+        runs in its sm_100a kernel and the noise is folded in by psx_add_noise (same roundings as the reference's
+        ``y_clean + eps``, inverse_problem.py:55-62); the random draw itself stays with torch's generator."""
+        from . import _native
         with torch.no_grad():
-            clean = operator(x_true)
-            y = clean + noise.sample(shape=clean.shape, device=clean.device, dtype=clean.dtype, generator=rng)
+            y = operator(x_true)
+            if y.is_cuda and y.dtype == torch.float32:
+                try:
+                    raw, scale, shift = noise._draw_affine(y.shape, y.device, rng)
+                except NotImplementedError:
+                    raw = None
+                if raw is not None:
+                    y = y.contiguous()
+                    if y.data_ptr() == x_true.data_ptr():      # identity operators may hand back a view of x_true
+                        y = y.clone()
+                    _native.add_noise(y, raw.contiguous(), scale, shift)
+                    return cls(operator=operator, observation=y, noise=noise)
+            y = y + noise.sample(shape=y.shape, device=y.device, dtype=y.dtype, generator=rng)
         return cls(operator=operator, observation=y, noise=noise)

@@ -37,6 +37,11 @@ class NoiseModel(nn.Module, ABC):
     @abstractmethod
     def _likelihood_weight(self) -> float: ...
 
+    def _draw_affine(self, shape: Shape, device, generator: RNG = None) -> tuple[Tensor, float, float]:
+        """(raw draw, scale, shift) with ``sample() == scale * raw + shift``: lets psx_observe / psx_add_noise
+        fuse the affine map into the observation pass.  Noise models without this decomposition raise."""
+        raise NotImplementedError(f"{type(self).__name__} has no (draw, scale, shift) form")
+
     @property
     def device(self) -> torch.device:
         return next(self.buffers()).device
@@ -72,6 +77,10 @@ class GaussianNoise(NoiseModel):
         var = self.sigma.detach().to(device="cpu", dtype=torch.float32).pow(2)
         return 1.0 / float(var)
 
+    def _draw_affine(self, shape, device, generator=None):
+        raw = torch.randn(tuple(shape), dtype=torch.float32, device=device, generator=generator)
+        return raw, float(self.sigma.detach().to(device="cpu", dtype=torch.float32)), 0.0
+
     def sample(self, shape: Shape, *, device: Device = None, dtype: DType = None, generator: RNG = None) -> Tensor:
         device = self.sigma.device if device is None else device
         dtype = self.sigma.dtype if dtype is None else dtype
@@ -96,6 +105,11 @@ class PoissonNoise(NoiseModel):
     def _likelihood_weight(self) -> float:
         lam = self.rate.detach().to(device="cpu", dtype=torch.float32)
         return 2.0 / float(lam + 1e-3)
+
+    def _draw_affine(self, shape, device, generator=None):
+        lam = float(self.rate.detach().to(device="cpu", dtype=torch.float32))
+        k = torch.poisson(torch.full(tuple(shape), lam, device=device, dtype=torch.float32), generator=generator)
+        return k, 1.0, -lam
 
     def sample(self, shape: Shape, *, device: Device = None, dtype: DType = None, generator: RNG = None) -> Tensor:
         device = self.rate.device if device is None else device
