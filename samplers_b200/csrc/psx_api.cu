@@ -136,6 +136,16 @@ PSX_API int psx_op_create_sepblur(int C, int H, int W, const float* h_taps_h, in
   if (!rc) rc = make_taps(h_taps_v, kv, true, &op->av);
   if (!rc) rc = sepblur_plan(op);
   if (rc) { delete op; return rc; }
+  // Side streams / events for the split K1 (launch_pre_sepblur).  Without a device (host-only use of the
+  // descriptor) or on any failure the descriptor simply has none and K1 runs on the caller's stream alone.
+  op->aux_mu = new (std::nothrow) std::mutex();
+  bool ok = op->aux_mu && cudaEventCreateWithFlags(&op->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 3; ++i) {
+    ok = cudaStreamCreateWithFlags(&op->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&op->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) op->aux_n = i + 1;
+  }
+  if (!ok) cudaGetLastError();
   *out = op;
   return PSX_OK;
 }
@@ -169,6 +179,12 @@ PSX_API int psx_op_create_conv2d(int C, int H, int W, const float* h_kernel, int
 PSX_API int psx_op_destroy(psx_op* op) {
   if (!op) return PSX_OK;
   if (op->d_taps_f) cudaFree(op->d_taps_f);
+  for (int i = 0; i < op->aux_n; ++i) {
+    cudaStreamDestroy(op->aux_stream[i]);
+    cudaEventDestroy(op->ev_join[i]);
+  }
+  if (op->ev_fork) cudaEventDestroy(op->ev_fork);
+  delete op->aux_mu;
   delete op;
   return PSX_OK;
 }

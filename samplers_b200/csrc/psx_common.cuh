@@ -1,6 +1,7 @@
 // psx_common.cuh -- shared device helpers for libpsx (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 
 #include <string>
@@ -51,6 +52,12 @@ struct psx_op {
   int n_taps2d, kh, kw;
   int err_parts;
   int col_tc;                 // sepblur: column-strip width
+  // sepblur: side streams + events for running K1 as independent sample groups that overlap each other's
+  // kernel tails (launch_pre_sepblur); created with the descriptor when a device is present, owned
+  int aux_n;                  // number of usable side streams (0: no split)
+  cudaStream_t aux_stream[3];
+  cudaEvent_t ev_fork, ev_join[3];
+  std::mutex* aux_mu;         // serialises the fork/join sequence of concurrent callers
 };
 
 namespace psx {

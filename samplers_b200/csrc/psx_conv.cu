@@ -57,6 +57,19 @@ __device__ __forceinline__ float4 load_row4(const float* __restrict__ in, const 
   return v;
 }
 
+#ifdef PSX_TRACE
+// %globaltimer phase trace of the three default-path kernels (tools/micro/k1_trace_main.cu): [kernel][cta][slot]
+__device__ long long psx_trace3[3 * 1024 * 8];
+#define PSX_TRK(kid, slot)                                                             \
+  if (threadIdx.x == 0 && blockIdx.x < 1024) {                                         \
+    long long t_;                                                                      \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+    psx_trace3[((kid) * 1024 + blockIdx.x) * 8 + (slot)] = t_;                         \
+  }
+#else
+#define PSX_TRK(kid, slot)
+#endif
+
 // ------------------------------------------------------------------------------------------ rows
 // grid = (ceil(W/TW), ceil(H/32), planes_total); dynamic smem = 16 * pitch2 float2.
 // The tile is stored ROW-PAIR INTERLEAVED: smem2[rp][s] = (row 2rp, row 2rp+1) at image column
@@ -432,6 +445,7 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
                int64_t total_rows, int W, int pitch2, int64_t num_tiles, const __grid_constant__ Taps taps,
                float sa, float s1, float coef, const float* __restrict__ dsc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (MODE == ROWS_TWEEDIE) { PSX_TRK(0, 0) }
   step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   constexpr int kArrays = MODE == ROWS_TWEEDIE ? 2 : 1;
@@ -471,10 +485,12 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
       if (i < n4) reinterpret_cast<float4*>(comp)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  if (MODE == ROWS_TWEEDIE) { PSX_TRK(0, 1) }
   for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
     const int stage = it & 1;
     if (tile + gridDim.x < num_tiles) issue(tile + gridDim.x, stage ^ 1);
     mbar_wait(&bars[stage], (uint32_t)(it >> 1) & 1u);
+    if (MODE == ROWS_TWEEDIE && it == 0) { PSX_TRK(0, 2) }
     __syncthreads();  // B1: previous tile's compute is done with `comp` (first pass: the zero fill is done)
     const float* xs = raw + (size_t)stage * kArrays * tile_floats;
     const int64_t r0 = tile * kPipeRows;
@@ -504,6 +520,7 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
       }
     }
     __syncthreads();  // B2: `comp` complete; raw[stage] fully consumed (may be refilled from now on)
+    if (MODE == ROWS_TWEEDIE && it == 0) { PSX_TRK(0, 3) }
 
     const int ncg = W >> 3;
 #pragma unroll
@@ -534,7 +551,9 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
     }
     // no trailing barrier: B1 of the next iteration orders this compute before the next conversion pass,
     // and the stage refilled next (this one) was fully read before B2.
+    if (MODE == ROWS_TWEEDIE && it == 0) { PSX_TRK(0, 4) }
   }
+  if (MODE == ROWS_TWEEDIE) { PSX_TRK(0, 5) }
 }
 
 // ---- columns.  Tile = one 32-column strip (all H rows) of one plane, fetched by ONE 2-D TMA box load
@@ -723,9 +742,10 @@ template <int K>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ y, float* __restrict__ out_il,
             float* __restrict__ err_part, int C, int H, int W, int strips, int64_t num_tiles, int64_t obs_repeat,
-            const __grid_constant__ Taps tf, const __grid_constant__ Taps ta) {
+            int64_t sample0, const __grid_constant__ Taps tf, const __grid_constant__ Taps ta) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float red[32];
+  PSX_TRK(1, 0)
   constexpr int TC = kColTC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw + kPipeHdr);
@@ -767,16 +787,18 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
       *reinterpret_cast<float4*>(bufB + (size_t)rb * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  PSX_TRK(1, 1)
   for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
     const int stage = it & 1;
     if (tile + gridDim.x < num_tiles) issue(tile + gridDim.x, stage ^ 1);
     mbar_wait(&bars[stage], (uint32_t)(it >> 1) & 1u);
+    if (it == 0) { PSX_TRK(1, 2) }
     __syncthreads();
     const float* A = smem + (size_t)stage * stage_floats;
     const int64_t pl = tile / strips;
     const int strip = (int)(tile - pl * strips);
     const int gc = strip * TC + 2 * cp;
-    const int64_t yplane = ((pl / C) / obs_repeat * C + pl % C) * (int64_t)H * W;
+    const int64_t yplane = ((sample0 + pl / C) / obs_repeat * C + pl % C) * (int64_t)H * W;  // pl: plane within this launch
     float e2 = 0.f;
     {
       float2 acc[16];
@@ -794,6 +816,7 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
       }
     }
     __syncthreads();
+    if (it == 0) { PSX_TRK(1, 3) }
     {
       float2 acc[16];
       col_block16<K, TC>(acc, bufB + (size_t)(16 * g) * TC + 2 * cp, ta);
@@ -811,7 +834,9 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
       err_part[l * (int64_t)(C * strips) + ch * strips + strip] = tot;
     }
     __syncthreads();  // stage + bufB + red fully consumed
+    if (it == 0) { PSX_TRK(1, 4) }
   }
+  PSX_TRK(1, 5)
 }
 
 // ---- last row pass on row-pair-interleaved input: the TMA bulk copies land directly in the compute
@@ -826,6 +851,7 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
              int64_t num_tiles, const __grid_constant__ Taps taps, float coef,
              const float* __restrict__ dsc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  PSX_TRK(2, 0)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float2* stages = reinterpret_cast<float2*>(smem_raw + kPipeHdr);
   const int stage_f2 = (kPipeRows / 2) * pitch2;
@@ -862,26 +888,30 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
   for (int d = 0; d < kIlStages - 1; ++d)
     if (tile + (int64_t)d * gridDim.x < num_tiles) issue(tile + (int64_t)d * gridDim.x, d);
   {  // zero the halo columns of every stage once, while the first loads are in flight (the bulk copies write the
-     // interior columns [-lo, -lo + W) only): per row pair the float2 columns [0, -lo) and [-lo + W, pitch2)
-    const int left = -taps.lo, right = pitch2 - left - W, per_row = left + right;  // all even
+     // interior columns [-lo, -lo + W) only): per row pair the float2 columns [0, -lo) and [-lo + W, pitch2).
+     // pitch2 - W <= K + 16 <= 64 float2 = 32 float4 per row pair: shifts only, no integer division.
+    const int left = -taps.lo, per_row4 = (pitch2 - W) >> 1;  // left, pitch2 - W even
 #pragma unroll
-    for (int t = 0; t < 20; ++t) {  // 3 stages * 8 rows * (136 + 16 + 14) / 2 float4 <= 20 * 128
+    for (int t = 0; t < (kIlStages * (kPipeRows / 2) * 32) / kIlThreads; ++t) {
       const int i = threadIdx.x + t * kIlThreads;
-      const int row = i / (per_row >> 1), c2 = 2 * (i - row * (per_row >> 1));
-      if (row < kIlStages * (kPipeRows / 2)) {
-        const int col = c2 < left ? c2 : c2 - left + left + W;
+      const int row = i >> 5, c2 = 2 * (i & 31);
+      if ((i & 31) < per_row4) {
+        const int col = c2 < left ? c2 : c2 + W;
         *reinterpret_cast<float4*>(stages + (size_t)row * pitch2 + col) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
+  PSX_TRK(2, 1)
   for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
     const int stage = it % kIlStages;
     __syncthreads();  // everyone is done with the stage that is refilled next (first pass: halo zero fill done)
     const int64_t nxt = tile + (int64_t)(kIlStages - 1) * gridDim.x;
     if (nxt < num_tiles) issue(nxt, (it + kIlStages - 1) % kIlStages);
     mbar_wait(&bars[stage], (uint32_t)(it / kIlStages) & 1u);
+    if (it == 0) { PSX_TRK(2, 2) }
     float2 acc[16];
     row_block16<K>(acc, stages + (size_t)stage * stage_f2 + rp * pitch2 + 16 * cg, taps);
+    if (it == 0) { PSX_TRK(2, 3) }
     const int64_t pair = tile * (kPipeRows / 2) + rp;
     if (q_ok && pair < total_pairs) {
       step_scalars_coef(dsc, coef);  // after the FFMA2 block: keeps the tap pairs on the uniform datapath
@@ -899,7 +929,9 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
         }
       }
     }
+    if (it == 0) { PSX_TRK(2, 4) }
   }
+  PSX_TRK(2, 5)
 }
 
 // ========================================================================================== cluster-fused K1
@@ -1280,7 +1312,7 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
 // cols16 + rows_il tail of K1 (h1 in ws, row-major)  ->  cot.  Returns -1 when the geometry does not qualify.
 template <int K>
 static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot, float* err_part, int64_t planes,
-                         int64_t obs_repeat, float w, float sa, const float* dsc, cudaStream_t st) {
+                         int64_t sample0, int64_t obs_repeat, float w, float sa, const float* dsc, cudaStream_t st) {
   const int W = op->W, H = op->H;
   CUtensorMap map;
   if (!make_strip_map(&map, ws, planes * H, W, H)) return -1;
@@ -1304,7 +1336,7 @@ static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot
   // written; other CTAs never touch this strip's (row pair, column) cells -- but the IL layout moves data
   // ACROSS rows of a pair, so in-place is only safe because both rows of a pair belong to the same strip tile.
   conv_cols16<K><<<(unsigned)grid_c, kThreads, smem_c, st>>>(map, y, ws, err_part, op->C, H, W, strips, tiles_c,
-                                                             obs_repeat, op->fv, op->av);
+                                                             obs_repeat, sample0, op->fv, op->av);
   int rc = check_cuda(cudaGetLastError(), "conv_cols16 launch");
   if (rc) return rc;
   const int64_t total_rows = planes * H;
@@ -1342,16 +1374,49 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
         x, eps, y, cot, err_part, op->C, obs_repeat, pitch2, op->fh, op->fv, op->av, op->ah, sa, s1, coef, dsc);
     return check_cuda(cudaGetLastError(), "blur_k1_fused launch");
   }
+  const int kk = op->fv.k;
+  const bool fast = op->W % kColTC == 0 && op->W <= 256 && op->H % 16 == 0 && op->H <= 256 && op->av.k == kk &&
+                    op->ah.k == kk && op->col_tc == kColTC && (kk == 40 || kk == 16) && !getenv("PSX_NO_PIPE") &&
+                    !getenv("PSX_NO_FAST16") && encode_fn() != nullptr;
+  if (fast) {
+    // The three launches of one group leave SMs idle in every kernel's ramp-up and tail (about a third of K1 at
+    // L = 16, tools/micro/k1_trace_main.cu).  Samples are independent, so K1 runs as `parts` groups on the caller's
+    // stream plus side streams: one group's tails and launch gaps are filled by the other groups' kernels.
+    // Measured (profiles/README.md): inside a replayed CUDA graph the fork/join is free and two groups cut K1 by 8 %
+    // at L = 16; launched eagerly the extra event calls cost more than the overlap returns until L >= 32.
+    static const int forced = [] { const char* e = getenv("PSX_SPLIT"); return e ? atoi(e) : 0; }();
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    const int want = forced ? forced : ((cap == cudaStreamCaptureStatusActive || L >= 32) ? 2 : 1);
+    int parts = want < 1 ? 1 : (want > op->aux_n + 1 ? op->aux_n + 1 : want);
+    while (parts > 1 && (L % parts != 0 || L / parts < 2)) --parts;
+    const int64_t Lp = L / parts, planes_p = Lp * op->C;
+    std::unique_lock<std::mutex> lock;
+    if (parts > 1) {
+      lock = std::unique_lock<std::mutex>(*op->aux_mu);
+      if (int rc = check_cuda(cudaEventRecord(op->ev_fork, st), "K1 fork event")) return rc;
+    }
+    for (int p = 0; p < parts; ++p) {
+      cudaStream_t s = p == 0 ? st : op->aux_stream[p - 1];
+      if (p > 0)
+        if (int rc = check_cuda(cudaStreamWaitEvent(s, op->ev_fork, 0), "K1 fork wait")) return rc;
+      const int64_t l0 = p * Lp, off = l0 * op->n;
+      int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x + off, eps + off, ws + off, planes_p, sa, s1, w, dsc, s);
+      if (rc) return rc;
+      float* part = err_part + l0 * op->err_parts;
+      rc = kk == 40 ? run_fast_tail<40>(op, y, ws + off, cot + off, part, planes_p, l0, obs_repeat, w, sa, dsc, s)
+                    : run_fast_tail<16>(op, y, ws + off, cot + off, part, planes_p, l0, obs_repeat, w, sa, dsc, s);
+      if (rc < 0) return fail(PSX_ERR_CUDA, "blur K1: could not encode the strip tensor map");
+      if (rc) return rc;
+      if (p > 0) {
+        if (int e = check_cuda(cudaEventRecord(op->ev_join[p - 1], s), "K1 join event")) return e;
+        if (int e = check_cuda(cudaStreamWaitEvent(st, op->ev_join[p - 1], 0), "K1 join wait")) return e;
+      }
+    }
+    return PSX_OK;
+  }
   int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x, eps, ws, planes, sa, s1, w, dsc, st);
   if (rc) return rc;
-  const int kk = op->fv.k;
-  if (op->W % kColTC == 0 && op->W <= 256 && op->H % 16 == 0 && op->H <= 256 && op->av.k == kk && op->ah.k == kk &&
-      op->col_tc == kColTC && !getenv("PSX_NO_PIPE") && !getenv("PSX_NO_FAST16")) {
-    int r2 = -1;
-    if (kk == 40) r2 = run_fast_tail<40>(op, y, ws, cot, err_part, planes, obs_repeat, w, sa, dsc, st);
-    else if (kk == 16) r2 = run_fast_tail<16>(op, y, ws, cot, err_part, planes, obs_repeat, w, sa, dsc, st);
-    if (r2 >= 0) return r2;
-  }
   rc = run_cols<true>(op, op->fv, op->av, ws, y, ws, err_part, planes, obs_repeat, st);
   if (rc) return rc;
   return run_rows<ROWS_COT>(op, op->ah, ws, nullptr, cot, planes, sa, s1, w, dsc, st);
