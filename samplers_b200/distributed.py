@@ -1,13 +1,19 @@
 """Multi-GPU posterior sampling: independent samples sharded across ranks, one
 process per GPU, no collective inside the sampling loop (DPS samples are
 independent: per-sample norm dps.py:118-120, per-sample log-prob noise.py:79).
-NCCL is used only at the end:
+NCCL is used only at the end for DPS:
 
   * all_gather of every rank's final x0 samples,
   * all_reduce(SUM) of the per-pixel [sum, sum of squares] -> posterior mean / variance.
 
 The final Tweedie kernel (psx_tweedie) writes each rank's samples straight into
 its slot of the gather buffer and produces the two moment buffers in the same pass.
+
+PSLD and ReSample couple the samples of a batch through batch-global norms / means.  Sharded over
+ranks they run either as replicas with rank-local norms (``process_group=None``, the default: each shard behaves
+like a separate reference call) or with exact global-batch semantics (``process_group=<group>``): the sums of
+squares behind every norm / MSE are all-reduced (``reduce_sum_`` / ``AllReduceSum`` / ``global_norm``), one
+scalar per reduction, so the union of the shards reproduces one reference call on the concatenated batch.
 """
 from __future__ import annotations
 
@@ -16,6 +22,42 @@ import dataclasses
 import torch
 import torch.distributed as dist
 from torch import Tensor
+
+
+def group_size(group) -> int:
+    """Ranks sharing batch-global reductions: 1 when ``group`` is None or torch.distributed is not initialised."""
+    if group is None or not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(group)
+
+
+def reduce_sum_(value: Tensor, group) -> Tensor:
+    """In-place SUM all-reduce of a (scalar) tensor over ``group``; a no-op for a single rank.  Not recorded by
+    autograd -- for use inside autograd.Function.forward."""
+    if group_size(group) > 1:
+        dist.all_reduce(value, op=dist.ReduceOp.SUM, group=group)
+    return value
+
+
+class AllReduceSum(torch.autograd.Function):
+    """S = sum over ranks of s_r, differentiable: every rank holds the SAME scalar loss f(S) and wants its gradient
+    with respect to its own shard, d f(S) / d s_r = f'(S), so the backward is the identity (no second reduction)."""
+
+    @staticmethod
+    def forward(ctx, value: Tensor, group):
+        return reduce_sum_(value.detach().clone(), group)
+
+    @staticmethod
+    def backward(ctx, grad: Tensor):
+        return grad, None
+
+
+def global_norm(x: Tensor, group=None) -> Tensor:
+    """Frobenius norm over the batch of ALL ranks of ``group`` (the reference's batch-global ``torch.norm`` when the
+    batch is sharded: psld.py:130,138, resample_kernels.py:27).  With one rank it is ``torch.norm(x)`` itself."""
+    if group_size(group) == 1:
+        return torch.norm(x)
+    return AllReduceSum.apply(x.square().sum(), group).sqrt()
 
 
 def shard_count(total: int, rank: int, world: int) -> tuple[int, int]:
@@ -69,6 +111,8 @@ def sample_posterior(sampler, inverse_problem, *, num_reconstructions: int, num_
         raise ValueError("need at least one reconstruction per rank")
     run = sampler.prepare(inverse_problem, num_sampling_steps, counts[rank], gamma, eta, condition)
     try:
+        if getattr(sampler, "cuda_graph", False):
+            run.capture()
         for k in range(run.num_steps):
             run.step(k)
         max_count = max(counts)

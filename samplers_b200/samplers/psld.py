@@ -13,8 +13,10 @@ and semantics of the reference sampler (samplers/samplers/psld.py:19-166).  One 
                                                  one autograd node whose backward is again psx_dps_pre
     z_{t-1} = c_ell z_t + c_s z0 + std*noise - grad        psx_bridge_update (psld.py:144-153)
 
-The norms are batch-global exactly as in the reference: on several GPUs each rank's
-shard behaves like a separate reference run (replicas with local norms).
+The norms are batch-global exactly as in the reference.  On several GPUs each rank's shard
+behaves like a separate reference run (rank-local norms) unless the sampler is built with ``process_group``:
+then the two sums of squares are all-reduced (one scalar each per step) and the union of the shards reproduces
+one reference call on the concatenated batch (samplers_b200/distributed.py).
 """
 from __future__ import annotations
 
@@ -24,6 +26,7 @@ import torch
 from torch import Tensor
 
 from .. import _native
+from ..distributed import global_norm, reduce_sum_
 from ..inverse_problem import InverseProblem
 from ..networks.base import LatentEpsilonNetwork, _TweedieFn, tweedie_scalars
 from .base import PosteriorSampler
@@ -38,13 +41,13 @@ class _PsldDataTerm(torch.autograd.Function):
     Backward: c_x0 = c_xeff - A^T A c_xeff - (c_lik / lik) * A^T r."""
 
     @staticmethod
-    def forward(ctx, x0: Tensor, op, y: Tensor, obs_repeat: int, ws, zeros_y: Tensor):
+    def forward(ctx, x0: Tensor, op, y: Tensor, obs_repeat: int, ws, zeros_y: Tensor, group=None):
         L, n = x0.shape
         atr = torch.empty_like(x0)
         part = torch.empty((L, op.err_parts), device=x0.device, dtype=torch.float32)
         # K1 with sa = 1, s1 = 0, w = 1:  "Tweedie" is the identity, cot = A^T r
         _native.dps_pre(op, x0, x0, y, obs_repeat, 1.0, 0.0, 1.0, atr, part, ws)
-        lik = part.sum().sqrt()
+        lik = reduce_sum_(part.sum(), group).sqrt()   # batch-global over all ranks of `group`
         x_eff = torch.empty_like(x0)
         _native.lincomb3(x0, 1.0, atr, 1.0, None, 0.0, x_eff)
         ctx.op, ctx.ws, ctx.obs_repeat = op, ws, obs_repeat
@@ -62,14 +65,14 @@ class _PsldDataTerm(torch.autograd.Function):
         kappa = -(c_lik / lik)
         out = torch.empty_like(c)
         _native.lincomb3(c, 1.0, neg_ata_c, 1.0, atr, float(kappa), out)
-        return out, None, None, None, None, None
+        return out, None, None, None, None, None, None
 
 
 class PSLDSampler(PosteriorSampler, Generic[Condition_co]):
     draw: Callable = staticmethod(lambda shape, device, dtype: torch.randn(size=shape, device=device, dtype=dtype))
 
-    def __init__(self, network):
-        super().__init__(network)
+    def __init__(self, network, cuda_graph: bool = False, process_group=None):
+        super().__init__(network, cuda_graph=False, process_group=process_group)
         if not isinstance(self._epsilon_network, LatentEpsilonNetwork):
             raise TypeError(
                 f"{self.__class__.__name__} requires a latent diffusion model, but build_network returned a "
@@ -113,9 +116,10 @@ class PSLDSampler(PosteriorSampler, Generic[Condition_co]):
                 eps = net.forward(z_in, sc.t)
                 z0 = _TweedieFn.apply(z_in, eps, sc.sqrt_acp, sc.sqrt_1m_acp)
                 x0 = net.decode(z0, differentiable=True)
-                lik, x_eff = _PsldDataTerm.apply(x0.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, zeros_y)
+                lik, x_eff = _PsldDataTerm.apply(x0.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, zeros_y,
+                                                 self.process_group)
                 z_eff = net.encode(x_eff.view(L, *x_shape), differentiable=True)
-                glue = torch.norm(z0 - z_eff)
+                glue = global_norm(z0 - z_eff, self.process_group)
                 (grad,) = torch.autograd.grad(omega * lik + gamma * glue, z_in)
                 noise = self.draw(tuple(z.shape), device, dtype) if sc.std != 0.0 else None
                 _native.bridge_update(z, eps.detach().contiguous(), noise, grad.contiguous(), sc.sqrt_acp,

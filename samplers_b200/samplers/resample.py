@@ -14,7 +14,8 @@
   stochastic resample      psx_stochastic_resample      resample_kernels.py:96-107, :123-129
 
 As in the reference the residual norm / MSE are batch-global, and ``scale`` is accepted
-but unused (App. B-9).
+but unused (App. B-9).  With ``process_group`` the sums behind them are all-reduced over the ranks (one scalar per
+reduction), so equal shards of a batch reproduce one reference call on the whole batch, early stops included.
 """
 from __future__ import annotations
 
@@ -24,6 +25,7 @@ import torch
 from torch import Tensor
 
 from .. import _native
+from ..distributed import group_size, reduce_sum_
 from ..inverse_problem import InverseProblem
 from ..networks.base import LatentEpsilonNetwork
 from ..noise import GaussianNoise
@@ -59,13 +61,13 @@ class _ResidualTerm(torch.autograd.Function):
     forward (partials + A^T r), one scaling backward."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, op, y: Tensor, obs_repeat: int, ws, mode: str):
+    def forward(ctx, x: Tensor, op, y: Tensor, obs_repeat: int, ws, mode: str, group=None):
         L = x.shape[0]
         atr = torch.empty_like(x)
         part = torch.empty((L, op.err_parts), device=x.device, dtype=torch.float32)
         _native.dps_pre(op, x, x, y, obs_repeat, 1.0, 0.0, 1.0, atr, part, ws)
-        e2 = part.sum()
-        count = float(L * op.n_y)
+        e2 = reduce_sum_(part.sum(), group)             # batch-global over all ranks of `group`
+        count = float(L * op.n_y) * group_size(group)   # equal shards
         val = e2.sqrt() if mode == "norm" else e2 / count
         ctx.mode, ctx.count = mode, count
         ctx.save_for_backward(atr, val)
@@ -77,14 +79,14 @@ class _ResidualTerm(torch.autograd.Function):
         kappa = -(c / val) if ctx.mode == "norm" else -(2.0 / ctx.count) * c
         out = torch.empty_like(atr)
         _native.lincomb3(atr, float(kappa), atr, 0.0, None, 0.0, out)
-        return out, None, None, None, None, None
+        return out, None, None, None, None, None, None
 
 
 class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
     draw: Callable = staticmethod(lambda shape, device, dtype: torch.randn(size=shape, device=device, dtype=dtype))
 
-    def __init__(self, network):
-        super().__init__(network)
+    def __init__(self, network, cuda_graph: bool = False, process_group=None):
+        super().__init__(network, cuda_graph=False, process_group=process_group)
         if not isinstance(self._epsilon_network, LatentEpsilonNetwork):
             raise TypeError(
                 f"{self.__class__.__name__} requires a latent diffusion model, but received a non-latent network "
@@ -97,11 +99,15 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
         m, v, grad = torch.zeros_like(x), torch.zeros_like(x), torch.empty_like(x)
         part = torch.empty((L, nat.err_parts), device=x.device, dtype=torch.float32)
         flags = torch.zeros(2, device=x.device, dtype=torch.int32)
-        count = float(L * nat.n_y)
+        group = getattr(self, "process_group", None)
+        count = float(L * nat.n_y) * group_size(group)
         for i in range(max_iters):
             # grad of mean((y - A x)^2) = -(2/N) A^T (y - A x); partials of |r|^2 in the same launch
             _native.dps_pre(nat, x, x, y, obs_repeat, 1.0, 0.0, -2.0 / count, grad, part, ws)
-            _native.adamw_step(x, grad, m, v, 1e-2, i + 1, flags=flags, flag_in=i & 1, loss_parts=part,
+            # several ranks: the stop rule looks at the GLOBAL mean -> one scalar all-reduce per iteration, still
+            # without a host sync (the kernel reads the reduced sum from device memory)
+            loss_parts = part if group_size(group) == 1 else reduce_sum_(part.sum().reshape(1), group)
+            _native.adamw_step(x, grad, m, v, 1e-2, i + 1, flags=flags, flag_in=i & 1, loss_parts=loss_parts,
                                loss_scale=1.0 / count, loss_threshold=eps ** 2)
             if (i + 1) % CHECK_EVERY == 0 and int(flags[(i + 1) & 1]) != 0:
                 break
@@ -116,7 +122,8 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
         for itr in range(max_iters):
             leaf = z.detach().requires_grad_()
             x = net.decode(leaf, differentiable=True)
-            loss = _ResidualTerm.apply(x.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, "mse")
+            loss = _ResidualTerm.apply(x.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, "mse",
+                                       self.process_group)
             (g,) = torch.autograd.grad(loss, leaf)
             _native.adamw_step(z, g.contiguous(), m, v, 5e-3, itr + 1)
             cur = float(loss.detach())
@@ -182,7 +189,8 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
                 # DPS conditioning: d||y - A D(pseudo)|| / d z_t, with d pseudo / d z_t = 1/sqrt(acp_t)
                 leaf = pseudo.requires_grad_()
                 x = net.decode(leaf, differentiable=True)
-                norm = _ResidualTerm.apply(x.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, "norm")
+                norm = _ResidualTerm.apply(x.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, "norm",
+                                           self.process_group)
                 (g_pseudo,) = torch.autograd.grad(norm, leaf)
                 a_t = acp_host[t]
                 z = torch.empty_like(z_next)

@@ -70,3 +70,67 @@ def test_combine_posterior_single_process():
     out = combine_posterior(gathered, gathered, local.sum(0), local.square().sum(0), [5])
     assert torch.equal(out.samples, local)
     assert torch.allclose(out.variance, local.var(0), atol=1e-6)
+
+
+# ---------------------------------------------------------------- PSLD / ReSample: global-batch norms over ranks
+def _psld_like_loss(z, y, dec_w, enc_w, norm):
+    """A PSLD-shaped scalar: omega * ||y - A D(z)|| + gamma * ||z - E(x_eff)|| with linear stand-ins for D, E, A."""
+    x0 = torch.tanh(z @ dec_w)
+    r = y - 0.5 * x0
+    lik = norm(r)
+    x_eff = x0 + 0.5 * r
+    glue = norm(z - torch.tanh(x_eff @ enc_w))
+    return 0.1 * lik + 1.0 * glue
+
+
+def _norm_worker(rank, world, port, q):
+    from samplers_b200.distributed import AllReduceSum, global_norm, group_size, reduce_sum_
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(7)
+        z_all, y_all = torch.randn(6, 8, generator=g), torch.randn(6, 12, generator=g)
+        dec_w, enc_w = torch.randn(8, 12, generator=g) * 0.3, torch.randn(12, 8, generator=g) * 0.3
+        lo, hi = rank * 3, rank * 3 + 3
+        z = z_all[lo:hi].clone().requires_grad_()
+        loss = _psld_like_loss(z, y_all[lo:hi], dec_w, enc_w, lambda t: global_norm(t, dist.group.WORLD))
+        (grad,) = torch.autograd.grad(loss, z)
+        s = reduce_sum_(torch.tensor(float(rank + 1)), dist.group.WORLD)
+        a = AllReduceSum.apply(torch.tensor(2.0, requires_grad=True) * (rank + 1), dist.group.WORLD)
+        q.put((rank, float(loss), grad, float(s), float(a), group_size(dist.group.WORLD), group_size(None)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_global_norms_over_two_ranks_equal_the_full_batch():
+    """Sharding a batch over 2 ranks with all-reduced sums of squares reproduces the reference's batch-global
+    norms (psld.py:130,138; resample_kernels.py:27): same loss on both ranks, gradient = slice of the full one."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_norm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(7)
+    z_all, y_all = torch.randn(6, 8, generator=g), torch.randn(6, 12, generator=g)
+    dec_w, enc_w = torch.randn(8, 12, generator=g) * 0.3, torch.randn(12, 8, generator=g) * 0.3
+    z = z_all.clone().requires_grad_()
+    full = _psld_like_loss(z, y_all, dec_w, enc_w, torch.norm)
+    (full_grad,) = torch.autograd.grad(full, z)
+    for rank, loss, grad, s, a, gs, gs_none in results:
+        assert abs(loss - float(full)) < 1e-5 * abs(float(full))
+        assert torch.allclose(grad, full_grad[rank * 3: rank * 3 + 3], rtol=1e-5, atol=1e-7)
+        assert s == 3.0 and a == 6.0 and gs == 2 and gs_none == 1
+
+
+def test_global_norm_single_process_is_torch_norm():
+    from samplers_b200.distributed import global_norm, group_size, reduce_sum_
+    x = torch.randn(4, 5, generator=torch.Generator().manual_seed(1))
+    assert torch.equal(global_norm(x), torch.norm(x)) and group_size(None) == 1
+    t = torch.tensor(3.0)
+    assert reduce_sum_(t, None) is t and float(t) == 3.0
