@@ -192,6 +192,26 @@ PSX_API int psx_dps_post_dev(const float* d_x_t, const float* d_eps, const float
                              const float* d_z, const float* d_err_part, int err_parts, int64_t L, int64_t n,
                              const float* d_step_row, float* d_x_next, float* d_err_out, void* stream);
 
+/* ------------------------------------------------------------------ K2 with in-kernel noise (production mode)
+ * Same update as psx_dps_post, but the N(0,1) field is drawn inside the kernel instead of being read: no noise
+ * tensor is written by a generator kernel and read back (36 -> 32 algorithmic B/element with the generator's
+ * write).  Philox4x32-10, key = seed, counter = (flat element index / 4, step); four outputs ->
+ * four normals by Box-Muller; restated in oracle/philox.py.  The field is a pure function of (seed, step, element
+ * index): eager launches and graph replays agree bit for bit.  It replaces `torch.randn_like` of
+ * bridge_kernels.py:59 and is NOT bit-comparable with torch's stream -- parity runs inject z through psx_dps_post.
+ *   psx_dps_post_philox      scalars, seed and step by value
+ *   psx_dps_post_philox_dev  scalars from d_step_row, {seed, step} from the device pair d_seed_step (graph replay)
+ *   psx_philox_normal        writes the field itself: d_out[i], i < numel                                   */
+PSX_API int psx_dps_post_philox(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
+                                const float* d_err_part, int err_parts, int64_t L, int64_t n, float sqrt_acp,
+                                float sqrt_1m_acp, float c_ell, float c_s, float std, float gamma, uint64_t seed,
+                                uint64_t step, float* d_x_next, float* d_err_out, void* stream);
+PSX_API int psx_dps_post_philox_dev(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
+                                    const float* d_err_part, int err_parts, int64_t L, int64_t n,
+                                    const float* d_step_row, const uint64_t* d_seed_step, float* d_x_next,
+                                    float* d_err_out, void* stream);
+PSX_API int psx_philox_normal(float* d_out, int64_t numel, uint64_t seed, uint64_t step, void* stream);
+
 /* ------------------------------------------------------------- latent samplers (PSLD)
  * psx_bridge_update -- bridge (DDIM/DDPM) update with an additive correction, the tail of a PSLD step:
  *   x_next = c_ell*x + c_s*x0 + std*z + grad_scale*grad,   x0 = (x - s1*eps)/sa

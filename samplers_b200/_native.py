@@ -52,6 +52,11 @@ PROTOTYPES = {
                                   C.c_size_t, _vp]),
     "psx_dps_post_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _f32p,
                                    _f32p, _vp]),
+    "psx_dps_post_philox": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f, _f, _f, _f, _f, _f,
+                                      C.c_uint64, C.c_uint64, _f32p, _f32p, _vp]),
+    "psx_dps_post_philox_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _vp, _f32p,
+                                          _f32p, _vp]),
+    "psx_philox_normal": (C.c_int, [_f32p, _i64, C.c_uint64, C.c_uint64, _vp]),
     "psx_tweedie": (C.c_int, [_f32p, _f32p, _i64, _i64, _f, _f, _f32p, _f32p, _f32p, _vp]),
     "psx_bridge_update": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, _f, _f32p, _vp]),
     "psx_lincomb3": (C.c_int, [_f32p, _f, _f32p, _f, _f32p, _f, _f32p, _i64, _vp]),
@@ -266,6 +271,41 @@ def dps_post_dev(x_t, eps, cot, vjp, z, err_part, err_parts: int, n: int, step_r
                                       ptr(err_part), err_parts if err_part is not None else 0, L, n,
                                       step_row.data_ptr(), x_next.data_ptr(), ptr(err_out),
                                       stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def dps_post_philox(x_t, eps, cot, vjp, err_part, err_parts: int, n: int, sa: float, s1: float, c_ell: float,
+                    c_s: float, std: float, gamma: float, seed: int, step: int, x_next, err_out=None) -> None:
+    """psx_dps_post with the N(0,1) field drawn inside the kernel (Philox4x32-10 keyed by seed, counter = step)."""
+    global launch_count
+    L = x_t.shape[0]
+    with torch.cuda.device(x_t.device):
+        check(load().psx_dps_post_philox(x_t.data_ptr(), eps.data_ptr(), cot.data_ptr(), vjp.data_ptr(),
+                                         ptr(err_part), err_parts if err_part is not None else 0, L, n, sa, s1,
+                                         c_ell, c_s, std, gamma, seed & (2 ** 64 - 1), step, x_next.data_ptr(),
+                                         ptr(err_out), stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def dps_post_philox_dev(x_t, eps, cot, vjp, err_part, err_parts: int, n: int, step_row, seed_step, x_next,
+                        err_out=None) -> None:
+    """Graph-replayable form: scalars from ``step_row``, {seed, step} from the int64 device pair ``seed_step``."""
+    global launch_count
+    L = x_t.shape[0]
+    with torch.cuda.device(x_t.device):
+        check(load().psx_dps_post_philox_dev(x_t.data_ptr(), eps.data_ptr(), cot.data_ptr(), vjp.data_ptr(),
+                                             ptr(err_part), err_parts if err_part is not None else 0, L, n,
+                                             step_row.data_ptr(), seed_step.data_ptr(), x_next.data_ptr(),
+                                             ptr(err_out), stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def philox_normal(out, seed: int, step: int) -> None:
+    """out[i] = the N(0,1) field psx_dps_post_philox adds at (seed, step), i in flat element order."""
+    global launch_count
+    with torch.cuda.device(out.device):
+        check(load().psx_philox_normal(out.data_ptr(), out.numel(), seed & (2 ** 64 - 1), step,
+                                       stream_ptr(out.device)))
     launch_count += 1
 
 

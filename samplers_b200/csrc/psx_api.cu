@@ -26,8 +26,9 @@ int check_cuda(cudaError_t e, const char* what) {
 int pointwise_parts(int64_t n);
 int box_parts(int64_t ny);
 int launch_post(const float*, const float*, const float*, const float*, const float*, const float*, int,
-                int64_t, int64_t, float, float, float, float, float, float, const float*, float*, float*,
-                cudaStream_t);
+                int64_t, int64_t, float, float, float, float, float, float, const float*, float*, float*, int,
+                uint64_t, uint64_t, const uint64_t*, cudaStream_t);
+int launch_philox_normal(float*, int64_t, uint64_t, uint64_t, cudaStream_t);
 int launch_tweedie(const float*, const float*, int64_t, int64_t, float, float, float*, float*, float*,
                    cudaStream_t);
 int launch_add_noise(float*, const float*, int64_t, float, float, cudaStream_t);
@@ -322,7 +323,7 @@ PSX_API int psx_dps_post(const float* d_x_t, const float* d_eps, const float* d_
               "psx_dps_post: non-finite scalar");
   return launch_post(d_x_t, d_eps, d_cot, d_vjp, std_ == 0.f ? nullptr : d_z, d_err_part, err_parts, L, n,
                      sqrt_acp, sqrt_1m_acp, c_ell, c_s, std_, gamma, nullptr, d_x_next, d_err_out,
-                     (cudaStream_t)stream);
+                     std_ == 0.f ? 0 : 1, 0, 0, nullptr, (cudaStream_t)stream);
 }
 
 PSX_API int psx_dps_post_dev(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
@@ -332,7 +333,40 @@ PSX_API int psx_dps_post_dev(const float* d_x_t, const float* d_eps, const float
   PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts >= 0, "psx_dps_post_dev: bad sizes");
   PSX_REQUIRE((err_parts > 0) == (d_err_part != nullptr), "psx_dps_post_dev: d_err_part and err_parts must agree");
   return launch_post(d_x_t, d_eps, d_cot, d_vjp, d_z, d_err_part, err_parts, L, n, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f,
-                     d_step_row, d_x_next, d_err_out, (cudaStream_t)stream);
+                     d_step_row, d_x_next, d_err_out, 1, 0, 0, nullptr, (cudaStream_t)stream);
+}
+
+PSX_API int psx_dps_post_philox(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
+                                const float* d_err_part, int err_parts, int64_t L, int64_t n, float sqrt_acp,
+                                float sqrt_1m_acp, float c_ell, float c_s, float std_, float gamma, uint64_t seed,
+                                uint64_t step, float* d_x_next, float* d_err_out, void* stream) {
+  PSX_REQUIRE(d_x_t && d_eps && d_cot && d_vjp && d_x_next, "psx_dps_post_philox: null pointer");
+  PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts >= 0, "psx_dps_post_philox: bad sizes");
+  PSX_REQUIRE((err_parts > 0) == (d_err_part != nullptr), "psx_dps_post_philox: d_err_part and err_parts must agree");
+  PSX_REQUIRE(sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(c_ell) && std::isfinite(c_s) &&
+                  std::isfinite(std_) && std::isfinite(gamma),
+              "psx_dps_post_philox: non-finite scalar");
+  return launch_post(d_x_t, d_eps, d_cot, d_vjp, nullptr, d_err_part, err_parts, L, n, sqrt_acp, sqrt_1m_acp, c_ell,
+                     c_s, std_, gamma, nullptr, d_x_next, d_err_out, std_ == 0.f ? 0 : 2, seed, step, nullptr,
+                     (cudaStream_t)stream);
+}
+
+PSX_API int psx_dps_post_philox_dev(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
+                                    const float* d_err_part, int err_parts, int64_t L, int64_t n,
+                                    const float* d_step_row, const uint64_t* d_seed_step, float* d_x_next,
+                                    float* d_err_out, void* stream) {
+  PSX_REQUIRE(d_x_t && d_eps && d_cot && d_vjp && d_x_next && d_step_row && d_seed_step,
+              "psx_dps_post_philox_dev: null pointer");
+  PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts >= 0, "psx_dps_post_philox_dev: bad sizes");
+  PSX_REQUIRE((err_parts > 0) == (d_err_part != nullptr),
+              "psx_dps_post_philox_dev: d_err_part and err_parts must agree");
+  return launch_post(d_x_t, d_eps, d_cot, d_vjp, nullptr, d_err_part, err_parts, L, n, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+                     d_step_row, d_x_next, d_err_out, 2, 0, 0, d_seed_step, (cudaStream_t)stream);
+}
+
+PSX_API int psx_philox_normal(float* d_out, int64_t numel, uint64_t seed, uint64_t step, void* stream) {
+  PSX_REQUIRE(d_out && numel > 0, "psx_philox_normal: null pointer or empty tensor");
+  return launch_philox_normal(d_out, numel, seed, step, (cudaStream_t)stream);
 }
 
 PSX_API int psx_bridge_update(const float* d_x, const float* d_eps, const float* d_z, const float* d_grad,

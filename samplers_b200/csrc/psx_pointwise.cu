@@ -327,14 +327,72 @@ int launch_pre_box(const psx_op* op, const float* x, const float* eps, const flo
 // =========================================================================== K2
 // x_next = c_ell*x_t + c_s*x0 + std*z + gamma/(|r|+1e-9) * (cot - s1*vjp)
 // Rounding order follows bridge_kernels.py:41 (mean), :59 (+ std*z), dps.py:121-122 (+ scale*grad).
-template <bool HAS_Z>
+// ---- in-kernel noise (production mode): Philox4x32-10 keyed by (seed), counter = (element group,
+// step); four outputs -> four N(0,1) values by Box-Muller.  Layout and arithmetic are restated in oracle/philox.py
+// (pinned to the Random123 known-answer vectors); the field depends on (seed, step, element index) only, so eager
+// launches and graph replays draw identical noise.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r) {
+      k.x += 0x9E3779B9u;
+      k.y += 0xBB67AE85u;
+    }
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+  }
+  return c;
+}
+__device__ __forceinline__ float philox_u01(uint32_t x) {  // (x + 0.5) * 2^-32 in (0, 1]
+  return __fadd_rn(__fmul_rn(__uint2float_rn(x), 2.3283064365386963e-10f), 1.1641532182693481e-10f);
+}
+__device__ __forceinline__ float2 box_muller(float ua, float ub) {
+  const float r = sqrtf(-2.f * logf(ua));
+  float sn, cs;
+  sincospif(2.f * ub, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+__device__ __forceinline__ float4 philox_normal4(uint64_t group, uint64_t seed, uint64_t step) {
+  const uint4 b = philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), (uint32_t)step, (uint32_t)(step >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float2 p = box_muller(philox_u01(b.x), philox_u01(b.y)), q = box_muller(philox_u01(b.z), philox_u01(b.w));
+  return make_float4(p.x, p.y, q.x, q.y);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_philox_normal(float* __restrict__ out, int64_t total, uint64_t seed, uint64_t step) {
+  const int64_t groups = (total + 3) >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const float4 z = philox_normal4((uint64_t)g, seed, step);
+    const float v[4] = {z.x, z.y, z.z, z.w};
+    for (int c = 0; c < 4; ++c)
+      if (4 * g + c < total) out[4 * g + c] = v[c];
+  }
+}
+
+int launch_philox_normal(float* out, int64_t total, uint64_t seed, uint64_t step, cudaStream_t st) {
+  int64_t b = ((total + 3) / 4 + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  k_philox_normal<<<(unsigned)(b > cap ? cap : (b < 1 ? 1 : b)), kThreads, 0, st>>>(out, total, seed, step);
+  return check_cuda(cudaGetLastError(), "k_philox_normal launch");
+}
+
+// ZMODE: 0 = no noise term, 1 = noise read from `z`, 2 = noise drawn in the kernel (Philox; `rng` = device
+// {seed, step} when not null, else the by-value pair).
+template <int ZMODE>
 __global__ void __launch_bounds__(kThreads)
 k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ cot,
            const float* __restrict__ vjp, const float* __restrict__ z, const float* __restrict__ err_part,
            int err_parts, int64_t n, int64_t chunk4, float sa, float s1, float c_ell, float c_s,
            float sd,
-           float gamma, float* __restrict__ x_next, float* __restrict__ err_out, const float* __restrict__ dsc) {
+           float gamma, float* __restrict__ x_next, float* __restrict__ err_out, const float* __restrict__ dsc,
+           uint64_t seed, uint64_t step, const uint64_t* __restrict__ rng) {
   step_scalars_k2(dsc, sa, s1, c_ell, c_s, sd, gamma);
+  if (ZMODE == 2 && rng != nullptr) {
+    seed = rng[0];
+    step = rng[1];
+  }
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
@@ -360,7 +418,14 @@ k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const flo
         ev[u] = ld_stream4(eps + so + 4 * i);
         dv[u] = ld_stream4(cot + so + 4 * i);
         vv[u] = ld_stream4(vjp + so + 4 * i);
-        if (HAS_Z) zv[u] = ld_stream4(z + so + 4 * i);
+        if (ZMODE == 1) zv[u] = ld_stream4(z + so + 4 * i);
+      }
+    }
+    if (ZMODE == 2) {  // generated while the loads above are in flight
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = base + (int64_t)u * kThreads;
+        if (i < end) zv[u] = philox_normal4((uint64_t)(l * n4 + i), seed, step);
       }
     }
 #pragma unroll
@@ -372,7 +437,7 @@ k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const flo
   {                                                                                            \
     const float x0 = tweedie(xv[u].c, ev[u].c, tc);                                        \
     float m = __fadd_rn(__fmul_rn(c_ell, xv[u].c), __fmul_rn(c_s, x0));                        \
-    if (HAS_Z) m = __fadd_rn(m, __fmul_rn(sd, zv[u].c));                                       \
+    if (ZMODE != 0) m = __fadd_rn(m, __fmul_rn(sd, zv[u].c));                                  \
     const float g = __fadd_rn(dv[u].c, __fmul_rn(-s1, vv[u].c));                               \
     o.c = __fadd_rn(m, __fmul_rn(scale, g));                                                   \
   }
@@ -384,13 +449,18 @@ k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const flo
   }
 }
 
-template <bool HAS_Z>
+template <int ZMODE>
 __global__ void __launch_bounds__(kThreads)
 k2_post_s(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ cot,
           const float* __restrict__ vjp, const float* __restrict__ z, const float* __restrict__ err_part,
           int err_parts, int64_t n, int64_t chunk, float sa, float s1, float c_ell, float c_s, float sd,
-           float gamma, float* __restrict__ x_next, float* __restrict__ err_out, const float* __restrict__ dsc) {
+          float gamma, float* __restrict__ x_next, float* __restrict__ err_out, const float* __restrict__ dsc,
+          uint64_t seed, uint64_t step, const uint64_t* __restrict__ rng) {
   step_scalars_k2(dsc, sa, s1, c_ell, c_s, sd, gamma);
+  if (ZMODE == 2 && rng != nullptr) {
+    seed = rng[0];
+    step = rng[1];
+  }
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
@@ -406,17 +476,22 @@ k2_post_s(const float* __restrict__ x, const float* __restrict__ eps, const floa
     const int64_t j = l * n + i;
     const float x0 = tweedie(x[j], eps[j], tc);
     float m = __fadd_rn(__fmul_rn(c_ell, x[j]), __fmul_rn(c_s, x0));
-    if (HAS_Z) m = __fadd_rn(m, __fmul_rn(sd, z[j]));
+    if (ZMODE == 1) m = __fadd_rn(m, __fmul_rn(sd, z[j]));
+    if (ZMODE == 2) {  // ragged n: every element evaluates its group's Philox block and keeps one lane
+      const float4 zz = philox_normal4((uint64_t)(j >> 2), seed, step);
+      const int c = (int)(j & 3);
+      m = __fadd_rn(m, __fmul_rn(sd, c == 0 ? zz.x : c == 1 ? zz.y : c == 2 ? zz.z : zz.w));
+    }
     const float g = __fadd_rn(cot[j], __fmul_rn(-s1, vjp[j]));
     x_next[j] = __fadd_rn(m, __fmul_rn(scale, g));
   }
 }
 
+// zmode: 0 none, 1 tensor z, 2 Philox (seed, step by value, or from the device pair rng)
 int launch_post(const float* x, const float* eps, const float* cot, const float* vjp, const float* z,
                 const float* err_part, int err_parts, int64_t L, int64_t n, float sa, float s1,
                 float c_ell, float c_s, float sd, float gamma, const float* dsc, float* x_next,
-                float* err_out, cudaStream_t st) {
-  const bool has_z = z != nullptr;
+                float* err_out, int zmode, uint64_t seed, uint64_t step, const uint64_t* rng, cudaStream_t st) {
 #define PSX_POST(KERNEL, UNITS)                                                                        \
   {                                                                                                    \
     static int rs = 0;                                                                                 \
@@ -425,12 +500,14 @@ int launch_post(const float* x, const float* eps, const float* cot, const float*
     const int64_t chunk = ((UNITS) + parts - 1) / parts;                                               \
     KERNEL<<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(x, eps, cot, vjp, z, err_part, err_parts, n, \
                                                           chunk, sa, s1, c_ell, c_s, sd, gamma, x_next, \
-                                                          err_out, dsc);                               \
+                                                          err_out, dsc, seed, step, rng);              \
   }
   if (n % 4 == 0) {
-    if (has_z) PSX_POST(k2_post_v4<true>, n / 4) else PSX_POST(k2_post_v4<false>, n / 4)
+    if (zmode == 2) PSX_POST(k2_post_v4<2>, n / 4) else if (zmode == 1) PSX_POST(k2_post_v4<1>, n / 4)
+    else PSX_POST(k2_post_v4<0>, n / 4)
   } else {
-    if (has_z) PSX_POST(k2_post_s<true>, n) else PSX_POST(k2_post_s<false>, n)
+    if (zmode == 2) PSX_POST(k2_post_s<2>, n) else if (zmode == 1) PSX_POST(k2_post_s<1>, n)
+    else PSX_POST(k2_post_s<0>, n)
   }
 #undef PSX_POST
   return check_cuda(cudaGetLastError(), "k2_post launch");

@@ -6,15 +6,19 @@ from ..networks import EpsilonNetwork
 
 
 class PosteriorSampler(ABC):
-    def __init__(self, network: EpsilonNetwork, cuda_graph: bool = False, process_group=None):
+    def __init__(self, network: EpsilonNetwork, cuda_graph: bool = False, process_group=None,
+                 philox_seed: int | None = None):
         """``network`` as in the reference.  ``cuda_graph=True`` (DPS / PGDM) records one guided timestep as a CUDA
         graph and replays it for the whole loop; it needs a network whose ``forward`` takes the timestep as a
         device tensor without synchronising, and fails loudly otherwise (there is no silent eager fallback).
-        ``process_group`` (PSLD / ReSample): see samplers_b200/distributed.py."""
+        ``process_group`` (PSLD / ReSample): see samplers_b200/distributed.py.  ``philox_seed`` (DPS / PGDM): draw
+        the per-step noise inside the update kernel (Philox keyed by the seed) instead of with ``torch.randn``;
+        reproducible across eager / graph execution, not bit-comparable with torch's stream."""
         self._epsilon_network = network
         self.cuda_graph = bool(cuda_graph)
         #: PSLD / ReSample: ranks over which the batch-global norms are all-reduced (None: rank-local norms)
         self.process_group = process_group
+        self.philox_seed = philox_seed
 
     @staticmethod
     def _flatten_leading(x: Tensor, *, x_shape: Shape) -> tuple[Tensor, Shape]:

@@ -52,7 +52,7 @@ class DPSRun:
     """
 
     def __init__(self, network, inverse_problem: InverseProblem, view: BatchView, gamma: float, eta: float,
-                 draw: Draw, weight: float | None = None, fixed_scale=None):
+                 draw: Draw, weight: float | None = None, fixed_scale=None, philox_seed: int | None = None):
         op, noise = inverse_problem.operator, inverse_problem.noise
         if not isinstance(noise, NoiseModel):
             raise NotImplementedError(f"no fused likelihood for noise model {type(noise).__name__}")
@@ -67,6 +67,8 @@ class DPSRun:
         # `weight` / `fixed_scale` turn the same two kernels into the PGDM update (see samplers/pgdm.py)
         self.weight = float(noise._likelihood_weight()) if weight is None else float(weight)
         self._fixed_scale = fixed_scale
+        #: not None: the per-step N(0,1) field is drawn inside K2 (Philox keyed by this seed, counter = step index)
+        self.philox_seed = None if philox_seed is None else int(philox_seed) & (2 ** 63 - 1)
         y = inverse_problem.observation.to(device=self.device, dtype=torch.float32)
         self.y = op._dense_observation(y)                      # (num_obs, n_y)
         self.L, self.n = view.leading_size, self.op.n
@@ -108,13 +110,18 @@ class DPSRun:
         v = v.reshape(self.L, self.n)
         if not v.is_contiguous():
             v = v.contiguous()
-        if self._draw_in_graph:
-            self.z.normal_()
         fixed = self._fixed_scale is not None
         # in place: every element of x is read and written by the same thread of K2
-        _native.dps_post_dev(self.x, eps_flat, self.cot, v, self.z, None if fixed else self.err_part,
-                             0 if fixed else self.op.err_parts, self.n, self.row, self.x,
-                             None if fixed else self.err)
+        if self.philox_seed is not None:
+            _native.dps_post_philox_dev(self.x, eps_flat, self.cot, v, None if fixed else self.err_part,
+                                        0 if fixed else self.op.err_parts, self.n, self.row, self.seed_step, self.x,
+                                        None if fixed else self.err)
+        else:
+            if self._draw_in_graph:
+                self.z.normal_()
+            _native.dps_post_dev(self.x, eps_flat, self.cot, v, self.z, None if fixed else self.err_part,
+                                 0 if fixed else self.op.err_parts, self.n, self.row, self.x,
+                                 None if fixed else self.err)
         self.k_dev.add_(1)
 
     def capture(self, warmup: int = 2, draw_in_graph: bool | None = None) -> None:
@@ -133,9 +140,13 @@ class DPSRun:
         self.t_table = torch.tensor([sc.t for sc in self.plan], dtype=torch.int64, device=dev)
         self.row = torch.zeros((1, _native.STEP_ROW), dtype=torch.float32, device=dev)
         self.t_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
-        self.k_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
-        self.z = torch.zeros((self.L, self.n), dtype=torch.float32, device=dev)
-        self._draw_in_graph = (self.draw is _default_draw) if draw_in_graph is None else bool(draw_in_graph)
+        # {seed, step}: the step counter doubles as the Philox counter word, so graph replays and eager steps draw
+        # the same field for the same (seed, step)
+        self.seed_step = torch.tensor([self.philox_seed or 0, 0], dtype=torch.int64, device=dev)
+        self.k_dev = self.seed_step[1:]
+        philox = self.philox_seed is not None
+        self.z = None if philox else torch.zeros((self.L, self.n), dtype=torch.float32, device=dev)
+        self._draw_in_graph = philox or ((self.draw is _default_draw) if draw_in_graph is None else bool(draw_in_graph))
         self._k_host = 0
         keep = self.x.clone()
         side = torch.cuda.Stream(device=dev)
@@ -165,7 +176,8 @@ class DPSRun:
             self.k_dev.fill_(k)
         if z is not None:
             if self._draw_in_graph:
-                raise ValueError("this graph draws its noise itself; capture(draw_in_graph=False) to inject z")
+                raise ValueError("this graph draws its noise itself; capture(draw_in_graph=False) without a Philox "
+                                 "seed to inject z")
             if z.data_ptr() != self.z.data_ptr():        # step(k, z=run.z): the caller filled the buffer in place
                 self.z.copy_(z.reshape(self.L, self.n))
         elif not self._draw_in_graph:
@@ -192,6 +204,14 @@ class DPSRun:
         v = v.reshape(self.L, self.n)
         if not v.is_contiguous():
             v = v.contiguous()
+        if self.philox_seed is not None and z is None:
+            fixed = self._fixed_scale is not None
+            _native.dps_post_philox(self.x, eps_flat, self.cot, v, None if fixed else self.err_part,
+                                    0 if fixed else self.op.err_parts, self.n, sc.sqrt_acp, sc.sqrt_1m_acp, sc.c_ell,
+                                    sc.c_s, sc.std, self._fixed_scale(sc) if fixed else self.gamma, self.philox_seed,
+                                    k, self.x_next, None if fixed else self.err)
+            self.x, self.x_next = self.x_next, self.x
+            return
         if sc.std != 0.0 and z is None:
             z = self.draw(self.view.flat_shape, self.device, self.dtype)
         if z is not None:
@@ -233,7 +253,7 @@ class DPSSampler(PosteriorSampler, Generic[Condition_co]):
                                     num_reconstructions=num_reconstructions, batch_size=view.batch_size)
         net.set_condition(condition=condition)
         try:
-            return DPSRun(net, inverse_problem, view, gamma, eta, self.draw)
+            return DPSRun(net, inverse_problem, view, gamma, eta, self.draw, philox_seed=self.philox_seed)
         except Exception:
             self.release()
             raise

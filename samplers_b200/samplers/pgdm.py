@@ -49,7 +49,8 @@ class PGDMSampler(PosteriorSampler, Generic[Condition_co]):
             def scale(sc):  # guidance_weight * sqrt(1 - acp_t) in fp32, as pgdm.py:132-134
                 return float(gw * torch.tensor(sc.sqrt_1m_acp, dtype=torch.float32))
 
-            run = DPSRun(net, inverse_problem, view, 0.0, eta, self.draw, weight=2.0 * gain, fixed_scale=scale)
+            run = DPSRun(net, inverse_problem, view, 0.0, eta, self.draw, weight=2.0 * gain, fixed_scale=scale,
+                         philox_seed=self.philox_seed)
             if self.cuda_graph:
                 run.capture()
             for k in range(run.num_steps):

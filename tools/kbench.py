@@ -113,18 +113,29 @@ def main():
                 _native.dps_post(d["x"], d["eps"], d["cot"], d["v"], d["z"], d["part"], nat.err_parts, n, 0.8, 0.6,
                                  0.99, 0.01, 0.05, 1.0, d["out"], None)
 
+            def k2p(i):  # noise drawn inside the kernel (20 B/elem of traffic)
+                d = S[i]
+                _native.dps_post_philox(d["x"], d["eps"], d["cot"], d["v"], d["part"], nat.err_parts, n, 0.8, 0.6,
+                                        0.99, 0.01, 0.05, 1.0, 1234, i, d["out"], None)
+
+            def zgen(i):  # what the Philox K2 replaces: the generator kernel that writes z
+                S[i]["z"].normal_()
+
             for i in range(nsets):
-                k1(i); k2(i)
+                k1(i); k2(i); k2p(i)
             if args.mode == "rotate":
                 m1, m2 = time_rotate(k1, nsets, args.iters), time_rotate(k2, nsets, args.iters)
+                m2p, mz = time_rotate(k2p, nsets, args.iters), time_rotate(zgen, nsets, args.iters)
             else:
                 m1, m2 = time_flush(k1, args.iters, flush), time_flush(k2, args.iters, flush)
+                m2p, mz = time_flush(k2p, args.iters, flush), time_flush(zgen, args.iters, flush)
             b1, b2 = 16 * L * n, 24 * L * n
             print(json.dumps({
                 "op": kind, "L": L, "mode": args.mode, "nsets": nsets, "k1_us": m1 * 1e3, "k2_us": m2 * 1e3,
                 "k1_gbs": b1 / m1 / 1e6, "k2_gbs": b2 / m2 / 1e6,
                 "fused_gbs": (b1 + b2) / (m1 + m2) / 1e6, "fused_frac": (b1 + b2) / (m1 + m2) / 1e6 / pk,
-                "k1_frac": b1 / m1 / 1e6 / pk, "k2_frac": b2 / m2 / 1e6 / pk, "peak": pk}), flush=True)
+                "k1_frac": b1 / m1 / 1e6 / pk, "k2_frac": b2 / m2 / 1e6 / pk, "peak": pk,
+                "k2_philox_us": m2p * 1e3, "torch_normal_us": mz * 1e3}), flush=True)
             del S
 
 
