@@ -290,7 +290,9 @@ def run_own(args):
                    **({"cuda_graph_error": graph_error} if graph_error else {})},
         "e2e": {"value": world * L / (GUIDED_STEPS * e2e_s), "unit": "samples/s",
                 "h2d_bytes_per_step": L * n * 4, "d2h_bytes_per_step": L * 4, "ms_per_step": ms_e2e / K},
-        "gpu_launches": int(sum(_native.KERNELS_PER_CALL[c] for c in ("pre_sepblur", "post")) * K),
+        # K1 = 3 kernels per sample group; inside a captured graph the blur K1 runs as two groups (launch_pre_sepblur)
+        "gpu_launches": int((_native.KERNELS_PER_CALL["pre_sepblur"] * (2 if use_graph and L % 2 == 0 and L >= 4 else 1)
+                             + _native.KERNELS_PER_CALL["post"]) * K),
         "abi_calls": int(abi_calls),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_STEP if (L, n) == (16, 3 * 256 * 256) else None,
