@@ -349,7 +349,15 @@ def _cpu_port_step_time(batch: int, steps: int, warmup: int):
     return times
 
 
+def _use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host threads it can."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_baseline(args) -> dict:
+    _use_all_host_threads()
     batch = args.cpu_batch
     times = _cpu_port_step_time(batch, steps=1, warmup=1)
     sec = statistics.mean(times)
@@ -363,6 +371,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _use_all_host_threads()
     batch = args.cpu_batch
     K, W = args.steps, args.warmup
     K_eff, W_eff = min(K, args.ref_max_steps), min(W, 1)
