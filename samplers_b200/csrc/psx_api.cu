@@ -151,27 +151,68 @@ PSX_API int psx_op_create_sepblur(int C, int H, int W, const float* h_taps_h, in
   return PSX_OK;
 }
 
+// Row-segment form of a 2-D PSF for one direction: sign = +1 forward (out[p] = sum w in[p + off]),
+// -1 adjoint (the flipped PSF).
+static int make_psf2d(const float* k, int kh, int kw, int sign, Psf2D* out) {
+  std::vector<RowSeg> segs;
+  std::vector<float> w;
+  out->dy_lo = out->dx_lo = 1 << 20;
+  out->dy_hi = out->dx_hi = -(1 << 20);
+  for (int row = 0; row < kh; ++row) {
+    const int jy = sign > 0 ? row : kh - 1 - row;  // ascending dy in both directions
+    int lo = kw, hi = -1;
+    for (int jx = 0; jx < kw; ++jx)
+      if (k[jy * kw + jx] != 0.f) {
+        lo = jx < lo ? jx : lo;
+        hi = jx > hi ? jx : hi;
+      }
+    if (hi < 0) continue;
+    const int dy = sign * (jy - kh / 2);
+    const int dxa = sign * ((sign > 0 ? lo : hi) - kw / 2), dxb = sign * ((sign > 0 ? hi : lo) - kw / 2);  // dxa <= dxb
+    const int dx0 = dxa >= 0 ? (dxa / 4) * 4 : -(((-dxa) + 3) / 4) * 4;  // floor to a multiple of 4
+    const int nch = (dxb - dx0 + 4) / 4;
+    RowSeg sg;
+    sg.dy = (int16_t)dy; sg.dx0 = (int16_t)dx0; sg.nch = (int16_t)nch; sg.w4_off = (uint16_t)(w.size() / 4);
+    for (int i = 0; i < 4 * nch; ++i) {
+      const int dx = dx0 + i;                       // tap at column offset dx  <->  kernel column sign*dx + kw/2
+      const int jx = sign * dx + kw / 2;
+      w.push_back(jx >= 0 && jx < kw ? k[jy * kw + jx] : 0.f);
+    }
+    segs.push_back(sg);
+    out->dy_lo = dy < out->dy_lo ? dy : out->dy_lo;
+    out->dy_hi = dy > out->dy_hi ? dy : out->dy_hi;
+    out->dx_lo = dx0 < out->dx_lo ? dx0 : out->dx_lo;
+    out->dx_hi = dx0 + 4 * nch > out->dx_hi ? dx0 + 4 * nch : out->dx_hi;
+  }
+  if (segs.empty()) return fail(PSX_ERR_INVALID, "psx_op_create_conv2d: kernel is all zeros");
+  if (w.size() / 4 > 65535) return fail(PSX_ERR_UNSUPPORTED, "psx_op_create_conv2d: PSF too large");
+  out->nseg = (int)segs.size();
+  out->nw4 = (int)(w.size() / 4);
+  int rc = check_cuda(cudaMalloc(&out->d_segs, segs.size() * sizeof(RowSeg)), "cudaMalloc PSF segments");
+  if (!rc) rc = check_cuda(cudaMalloc(&out->d_w4, w.size() * sizeof(float)), "cudaMalloc PSF taps");
+  if (!rc) rc = check_cuda(cudaMemcpy(out->d_segs, segs.data(), segs.size() * sizeof(RowSeg), cudaMemcpyHostToDevice), "copy PSF segments");
+  if (!rc) rc = check_cuda(cudaMemcpy(out->d_w4, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice), "copy PSF taps");
+  return rc;
+}
+
+static void free_psf2d(Psf2D* p) {
+  if (p->d_segs) cudaFree(p->d_segs);
+  if (p->d_w4) cudaFree(p->d_w4);
+  p->d_segs = nullptr;
+  p->d_w4 = nullptr;
+}
+
 PSX_API int psx_op_create_conv2d(int C, int H, int W, const float* h_kernel, int kh, int kw, psx_op** out) {
   PSX_REQUIRE(out && C > 0 && H > 0 && W > 0 && h_kernel, "psx_op_create_conv2d: bad arguments");
   PSX_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && kh <= PSX_MAX_TAPS && kw <= PSX_MAX_TAPS,
               "psx_op_create_conv2d: kernel sizes must be odd and <= PSX_MAX_TAPS");
-  std::vector<Tap2D> taps;
-  for (int jy = 0; jy < kh; ++jy)
-    for (int jx = 0; jx < kw; ++jx) {
-      const float w = h_kernel[jy * kw + jx];
-      if (w != 0.f) taps.push_back(Tap2D{(int16_t)(jy - kh / 2), (int16_t)(jx - kw / 2), w});
-    }
-  PSX_REQUIRE(!taps.empty(), "psx_op_create_conv2d: kernel is all zeros");
   psx_op* op = new_op(PSX_OP_CONV2D);
   if (!op) return fail(PSX_ERR_INVALID, "out of host memory");
   op->C = C; op->H = H; op->W = W; op->kh = kh; op->kw = kw;
   op->n = op->n_y = (int64_t)C * H * W;
-  op->n_taps2d = (int)taps.size();
-  int rc = check_cuda(cudaMalloc(&op->d_taps_f, taps.size() * sizeof(Tap2D)), "cudaMalloc taps");
-  if (!rc)
-    rc = check_cuda(cudaMemcpy(op->d_taps_f, taps.data(), taps.size() * sizeof(Tap2D), cudaMemcpyHostToDevice),
-                    "copy taps");
-  if (rc) { if (op->d_taps_f) cudaFree(op->d_taps_f); delete op; return rc; }
+  int rc = make_psf2d(h_kernel, kh, kw, +1, &op->psf_f);
+  if (!rc) rc = make_psf2d(h_kernel, kh, kw, -1, &op->psf_a);
+  if (rc) { free_psf2d(&op->psf_f); free_psf2d(&op->psf_a); delete op; return rc; }
   op->err_parts = conv2d_err_parts(op);
   *out = op;
   return PSX_OK;
@@ -179,7 +220,10 @@ PSX_API int psx_op_create_conv2d(int C, int H, int W, const float* h_kernel, int
 
 PSX_API int psx_op_destroy(psx_op* op) {
   if (!op) return PSX_OK;
-  if (op->d_taps_f) cudaFree(op->d_taps_f);
+  if (op->kind == PSX_OP_CONV2D) {
+    free_psf2d(&op->psf_f);
+    free_psf2d(&op->psf_a);
+  }
   for (int i = 0; i < op->aux_n; ++i) {
     cudaStreamDestroy(op->aux_stream[i]);
     cudaEventDestroy(op->ev_join[i]);

@@ -33,9 +33,19 @@ struct Taps {
   float2 ww[PSX_MAX_TAPS + 9];
 };
 
-struct Tap2D {
-  int16_t dy, dx;
-  float w;
+// 2-D PSF as row segments: PSF row dy is a 1-D correlation whose taps start at column offset dx0 (a multiple of 4)
+// and span nch chunks of 4 taps (zero padded); w4_off indexes the float4 tap array.
+struct RowSeg {
+  int16_t dy, dx0;
+  int16_t nch;
+  uint16_t w4_off;
+};
+struct Psf2D {              // one direction (forward or adjoint = flipped PSF)
+  RowSeg* d_segs;           // device, owned
+  float4* d_w4;             // device, owned: zero-padded taps, 4 per chunk
+  int nseg, nw4;            // segments, float4 tap groups
+  int dy_lo, dy_hi;         // min / max dy over the segments
+  int dx_lo, dx_hi;         // min dx0 / max (dx0 + 4 * nch) over the segments (multiples of 4)
 };
 
 }  // namespace psx
@@ -47,9 +57,8 @@ struct psx_op {
   int factor;                 // box
   const uint8_t* d_keep;      // mask (caller-owned)
   psx::Taps fh, fv, ah, av;   // separable blur: forward / adjoint taps (rows, cols)
-  psx::Tap2D* d_taps_f;       // conv2d: device tap lists (owned)
-  psx::Tap2D* d_taps_a;
-  int n_taps2d, kh, kw;
+  psx::Psf2D psf_f, psf_a;    // conv2d: forward / adjoint PSF as row segments (device arrays owned)
+  int kh, kw;
   int err_parts;
   int col_tc;                 // sepblur: column-strip width
   // sepblur: side streams + events for running K1 as independent sample groups that overlap each other's
