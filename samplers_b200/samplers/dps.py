@@ -57,12 +57,14 @@ class DPSRun:
         if not isinstance(noise, NoiseModel):
             raise NotImplementedError(f"no fused likelihood for noise model {type(noise).__name__}")
         self.net, self.view, self.gamma, self.draw = network, view, float(gamma), draw
-        self.device, self.dtype = network.device, network.dtype
+        self.device, self.dtype, self.net_dtype = network.device, torch.float32, network.dtype
         if torch.device(self.device).type != "cuda":
             raise RuntimeError("DPSSampler needs the network on a CUDA device: the sampling step exists only as "
                                "sm_100a kernels (libpsx), there is no CPU path")
-        if self.dtype != torch.float32:
-            raise TypeError(f"DPSSampler state is float32; network dtype {self.dtype} is not supported yet")
+        # The sampler state and every kernel are fp32.  A half-precision network (the reference runs its latent
+        # pipelines in bf16, scripts/run_psld.py:14) is fed a cast of the state and its eps / VJP are cast back.
+        if self.net_dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise TypeError(f"DPSSampler supports float32 / bfloat16 / float16 networks, got {self.net_dtype}")
         self.op = op._native_cached(self.device)
         # `weight` / `fixed_scale` turn the same two kernels into the PGDM update (see samplers/pgdm.py)
         self.weight = float(noise._likelihood_weight()) if weight is None else float(weight)
@@ -90,6 +92,24 @@ class DPSRun:
         self.ws = torch.empty(wsb // 4, device=self.device, dtype=torch.float32) if wsb else None
         self._graph: torch.cuda.CUDAGraph | None = None
 
+    def _network_eps(self, t):
+        """(fp32 leaf over the state, eps in the network's dtype with its graph, eps as contiguous fp32 (L, n))."""
+        x_in = self.x.view(self.view.flat_shape).detach().requires_grad_()
+        eps = self.net.forward(x_in if self.net_dtype == torch.float32 else x_in.to(self.net_dtype), t)
+        eps_flat = eps.detach().reshape(self.L, self.n)
+        if eps_flat.dtype != torch.float32:
+            eps_flat = eps_flat.float()
+        if not eps_flat.is_contiguous():
+            eps_flat = eps_flat.contiguous()
+        return x_in, eps, eps_flat
+
+    def _network_vjp(self, eps, x_in) -> Tensor:
+        """VJP of the network at the cotangent K1 left in ``self.cot``, as contiguous fp32 (L, n)."""
+        cot = self.cot.view_as(eps)
+        (v,) = torch.autograd.grad(eps, x_in, grad_outputs=cot if eps.dtype == torch.float32 else cot.to(eps.dtype))
+        v = v.reshape(self.L, self.n)
+        return v if v.is_contiguous() else v.contiguous()
+
     # ------------------------------------------------------------------ CUDA-graph replay of the timestep
     def step_table(self) -> Tensor:
         """(num_steps, PSX_STEP_ROW) fp32 host table for the *_dev entry points (utils/bridge_kernels.step_rows)."""
@@ -99,17 +119,10 @@ class DPSRun:
         """One guided timestep with every per-step quantity read from device memory (row k_dev of the table)."""
         torch.index_select(self.table, 0, self.k_dev, out=self.row)
         torch.index_select(self.t_table, 0, self.k_dev, out=self.t_dev)
-        x_in = self.x.view(self.view.flat_shape).detach().requires_grad_()
-        eps = self.net.forward(x_in, self.t_dev)
-        eps_flat = eps.detach().reshape(self.L, self.n)
-        if not eps_flat.is_contiguous():
-            eps_flat = eps_flat.contiguous()
+        x_in, eps, eps_flat = self._network_eps(self.t_dev)
         _native.dps_pre_dev(self.op, self.x, eps_flat, self.y, self.obs_repeat, self.row, self.cot, self.err_part,
                             self.ws)
-        (v,) = torch.autograd.grad(eps, x_in, grad_outputs=self.cot.view_as(eps))
-        v = v.reshape(self.L, self.n)
-        if not v.is_contiguous():
-            v = v.contiguous()
+        v = self._network_vjp(eps, x_in)
         fixed = self._fixed_scale is not None
         # in place: every element of x is read and written by the same thread of K2
         if self.philox_seed is not None:
@@ -193,17 +206,10 @@ class DPSRun:
         if self._graph is not None:
             return self._replay(k, z)
         sc = self.plan[k]
-        x_in = self.x.view(self.view.flat_shape).detach().requires_grad_()
-        eps = self.net.forward(x_in, sc.t)                                   # graph kept for the VJP
-        eps_flat = eps.detach().reshape(self.L, self.n)
-        if not eps_flat.is_contiguous():
-            eps_flat = eps_flat.contiguous()
+        x_in, eps, eps_flat = self._network_eps(sc.t)                        # graph kept for the VJP
         _native.dps_pre(self.op, self.x, eps_flat, self.y, self.obs_repeat, sc.sqrt_acp, sc.sqrt_1m_acp,
                         self.weight, self.cot, self.err_part, self.ws)
-        (v,) = torch.autograd.grad(eps, x_in, grad_outputs=self.cot.view_as(eps))
-        v = v.reshape(self.L, self.n)
-        if not v.is_contiguous():
-            v = v.contiguous()
+        v = self._network_vjp(eps, x_in)
         if self.philox_seed is not None and z is None:
             fixed = self._fixed_scale is not None
             _native.dps_post_philox(self.x, eps_flat, self.cot, v, None if fixed else self.err_part,
@@ -231,7 +237,9 @@ class DPSRun:
         t = self.timesteps[1]
         sa, s1 = tweedie_scalars(self.net.alphas_cumprod, t)
         with torch.no_grad():
-            eps = self.net.forward(self.x.view(self.view.flat_shape), t).reshape(self.L, self.n).contiguous()
+            x = self.x.view(self.view.flat_shape)
+            eps = self.net.forward(x if self.net_dtype == torch.float32 else x.to(self.net_dtype), t)
+            eps = eps.reshape(self.L, self.n).float().contiguous()
         out = torch.empty((self.L, self.n), device=self.device, dtype=torch.float32) if out is None else out
         _native.tweedie(self.x, eps, sa, s1, out, total, total_sq)
         return out

@@ -98,8 +98,13 @@ class PSLDSampler(PosteriorSampler, Generic[Condition_co]):
             device, dtype = net.device, net.dtype
             if torch.device(device).type != "cuda":
                 raise RuntimeError("PSLDSampler needs the network on a CUDA device (no CPU path)")
-            if dtype != torch.float32:
-                raise TypeError(f"PSLDSampler state is float32; network dtype {dtype} is not supported yet")
+            # state and kernels are fp32; a half-precision network / VAE (scripts/run_psld.py:14 runs bf16) gets casts
+            if dtype not in (torch.float32, torch.bfloat16, torch.float16):
+                raise TypeError(f"PSLDSampler supports float32 / bfloat16 / float16 networks, got {dtype}")
+            net_dtype, dtype = dtype, torch.float32
+
+            def to_net(t: Tensor) -> Tensor:
+                return t if net_dtype == torch.float32 else t.to(net_dtype)
             nat = op._native_cached(device)
             y = op._dense_observation(inverse_problem.observation.to(device=device, dtype=torch.float32))
             obs_repeat = num_reconstructions if x_view.batch_size > 1 else L
@@ -113,12 +118,12 @@ class PSLDSampler(PosteriorSampler, Generic[Condition_co]):
             z_next = torch.empty_like(z)
             for sc in plan:
                 z_in = z.detach().requires_grad_()
-                eps = net.forward(z_in, sc.t)
+                eps = net.forward(to_net(z_in), sc.t).float()
                 z0 = _TweedieFn.apply(z_in, eps, sc.sqrt_acp, sc.sqrt_1m_acp)
-                x0 = net.decode(z0, differentiable=True)
+                x0 = net.decode(to_net(z0), differentiable=True).float()
                 lik, x_eff = _PsldDataTerm.apply(x0.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, zeros_y,
                                                  self.process_group)
-                z_eff = net.encode(x_eff.view(L, *x_shape), differentiable=True)
+                z_eff = net.encode(to_net(x_eff.view(L, *x_shape)), differentiable=True).float()
                 glue = global_norm(z0 - z_eff, self.process_group)
                 (grad,) = torch.autograd.grad(omega * lik + gamma * glue, z_in)
                 noise = self.draw(tuple(z.shape), device, dtype) if sc.std != 0.0 else None
@@ -129,11 +134,11 @@ class PSLDSampler(PosteriorSampler, Generic[Condition_co]):
             t1 = timesteps[1]
             sa, s1 = tweedie_scalars(net.alphas_cumprod, t1)
             with torch.no_grad():
-                eps = net.forward(z, t1).contiguous()
+                eps = net.forward(to_net(z), t1).float().contiguous()
                 z0 = torch.empty_like(z)
                 _native.tweedie(z.view(L, -1), eps.view(L, -1), sa, s1, z0.view(L, -1))
                 if decode_output:
-                    return x_view.unflatten(net.decode(z0, differentiable=False))
+                    return x_view.unflatten(net.decode(to_net(z0), differentiable=False).float())
             return z_view.unflatten(z0)
         finally:
             net.clear_condition()

@@ -121,7 +121,8 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
         window: list[float] = []
         for itr in range(max_iters):
             leaf = z.detach().requires_grad_()
-            x = net.decode(leaf, differentiable=True)
+            nd = getattr(self, "_net_dtype", torch.float32)
+            x = net.decode(leaf if nd == torch.float32 else leaf.to(nd), differentiable=True).float()
             loss = _ResidualTerm.apply(x.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, "mse",
                                        self.process_group)
             (g,) = torch.autograd.grad(loss, leaf)
@@ -159,8 +160,14 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
             device, dtype = net.device, net.dtype
             if torch.device(device).type != "cuda":
                 raise RuntimeError("ReSampleSampler needs the network on a CUDA device (no CPU path)")
-            if dtype != torch.float32:
-                raise TypeError(f"ReSampleSampler state is float32; network dtype {dtype} is not supported yet")
+            # state and kernels are fp32; a half-precision network / VAE gets casts at its boundary
+            if dtype not in (torch.float32, torch.bfloat16, torch.float16):
+                raise TypeError(f"ReSampleSampler supports float32 / bfloat16 / float16 networks, got {dtype}")
+            net_dtype, dtype = dtype, torch.float32
+            self._net_dtype = net_dtype
+
+            def to_net(t: Tensor) -> Tensor:
+                return t if net_dtype == torch.float32 else t.to(net_dtype)
             nat = op._native_cached(device)
             y = op._dense_observation(inverse_problem.observation.to(device=device, dtype=torch.float32))
             obs_repeat = num_reconstructions if x_view.batch_size > 1 else L
@@ -175,7 +182,7 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
 
             def eps_ddim(z_cur: Tensor, t: int, t_prev: int):
                 with torch.no_grad():
-                    e = net.predict_noise(z_cur, t).contiguous()
+                    e = net.predict_noise(to_net(z_cur), t).float().contiguous()
                 sc = ddim_eps_scalars(acp, t, t_prev, eta)
                 noise = self.draw(tuple(z_cur.shape), device, dtype) if sc["sigma_t"] != 0.0 else None
                 z_prev, pseudo = torch.empty_like(z_cur), torch.empty_like(z_cur)
@@ -188,7 +195,7 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
                 z_next, pseudo = eps_ddim(z, t, tp)
                 # DPS conditioning: d||y - A D(pseudo)|| / d z_t, with d pseudo / d z_t = 1/sqrt(acp_t)
                 leaf = pseudo.requires_grad_()
-                x = net.decode(leaf, differentiable=True)
+                x = net.decode(to_net(leaf), differentiable=True).float()
                 norm = _ResidualTerm.apply(x.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, "norm",
                                            self.process_group)
                 (g_pseudo,) = torch.autograd.grad(norm, leaf)
@@ -205,9 +212,9 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
                         z, pseudo = eps_ddim(z, ts[k], ts[k - 1])
                     c_p, c_x, den, k_n = resample_scalars(acp, t, tp, sigma_scale)
                     if idx >= index_split:
-                        x_pix = net.decode(pseudo, differentiable=False).reshape(L, nat.n).contiguous()
+                        x_pix = net.decode(to_net(pseudo), differentiable=False).float().reshape(L, nat.n).contiguous()
                         x_opt = self._pixel_optimization(nat, y, obs_repeat, ws, x_pix, eps, max_optimization_iters)
-                        z_opt = net.encode(x_opt.view(L, *x_shape), differentiable=False).contiguous()
+                        z_opt = net.encode(to_net(x_opt.view(L, *x_shape)), differentiable=False).float().contiguous()
                     else:
                         z_opt = self._latent_optimization(net, nat, y, obs_repeat, ws, pseudo, x_shape, eps,
                                                           max_optimization_iters)
@@ -217,7 +224,7 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
 
             z0 = self._latent_optimization(net, nat, y, obs_repeat, ws, z, x_shape, eps, max_optimization_iters)
             if decode_output:
-                return x_view.unflatten(net.decode(z0, differentiable=False))
+                return x_view.unflatten(net.decode(to_net(z0), differentiable=False).float())
             return z_view.unflatten(z0)
         finally:
             net.clear_condition()

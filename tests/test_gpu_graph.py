@@ -179,3 +179,30 @@ def test_network_that_syncs_on_the_timestep_fails_loudly_under_capture():
     # the device is still usable afterwards, eagerly
     out = DPSSampler(net)(_problem("identity"), num_sampling_steps=10, num_reconstructions=1)
     assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_half_precision_network_with_fp32_state(graph):
+    """A bf16 network (the reference's latent pipelines run in bf16) on the fp32 state: same trajectory as the fp32
+    network up to the network's own rounding; eager and graph."""
+    from samplers_b200.networks import DDPMNetwork
+    from samplers_b200.samplers import DPSSampler
+    prob = _problem("blur")
+    outs = {}
+    for dt in (torch.float32, torch.bfloat16):
+        torch.manual_seed(1234)
+        net = DDPMNetwork.from_config("tiny", device=DEV, torch_dtype=dt)
+        s = DPSSampler(net, cuda_graph=graph, philox_seed=3)
+        x_init = torch.randn(2, *SHAPE, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+        s.draw = lambda shape, device, dtype: x_init.clone()
+        run = s.prepare(prob, num_sampling_steps=6, num_reconstructions=2, gamma=0.05)
+        try:
+            if graph:
+                run.capture()
+            run.step(0)
+            outs[dt] = run.x.clone()
+            assert run.x.dtype == torch.float32 and run.cot.dtype == torch.float32
+            assert torch.isfinite(run.finalize()).all()
+        finally:
+            s.release()
+    assert rel_err(outs[torch.bfloat16].cpu(), outs[torch.float32].cpu()) < 5e-2
