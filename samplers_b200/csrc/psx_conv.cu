@@ -1,10 +1,15 @@
 // psx_conv.cu -- shared-memory-tiled convolution kernels (sm_100a):
 //   separable blur  A = V . H  (rows then columns), adjoint = H^T . V^T,
-//   sparse-tap depthwise 2-D correlation (motion PSFs),
-//   and K1 (psx_dps_pre) built from them:
-//     rows<TWEEDIE>  : x0 = (x_t - s1 eps)/sa on the fly, h1 = H x0           -> workspace
-//     cols<RESIDUAL> : r = y - V h1, |r|^2 partials, h2 = V^T r  (strip-local) -> workspace (in place)
-//     rows<COT>      : cot = w * H^T h2 / sa                                   -> d_cot
+//   depthwise 2-D correlation with an arbitrary PSF as row segments (motion blur),
+//   and K1 (psx_dps_pre) built from them.  Default K1 for a separable blur (W % 32 == 0, H % 16 == 0, both <= 256):
+//     conv_rows_pipe<TWEEDIE> : x0 = (x_t - s1 eps)/sa on the fly, h1 = H x0              -> workspace
+//     conv_cols16             : r = y - V h1, |r|^2 partials, h2 = V^T r (strip-local)     -> workspace, in place,
+//                               row-pair interleaved
+//     conv_rows_il            : cot = (w / sa) * H^T h2                                    -> d_cot
+//   persistent CTAs fed by TMA (cp.async.bulk / cp.async.bulk.tensor.2d + mbarriers), packed FFMA2 register blocks
+//   with the tap pairs in uniform registers; inside a stream capture (and from L = 32) the batch runs as two sample
+//   groups on two streams (launch_pre_sepblur).  Other shapes / tap counts fall back to conv_cols_pipe + conv_rows_pipe
+//   <COT> or the one-tile-per-CTA conv_rows / conv_cols; blur_k1_fused is the opt-in single-launch cluster variant.
 // All passes are zero-padded "same" cross-correlations; halos are zero-filled in shared memory.
 #include <cooperative_groups.h>
 #include <cuda.h>

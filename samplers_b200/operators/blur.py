@@ -6,7 +6,7 @@ taps for every channel.
 
 * ``SeparableBlurOperator``  y = V(H(x))  -- rows then columns (psx_op_create_sepblur)
 * ``GaussianBlurOperator``   separable with taps exp(-k^2 / 2 sigma^2) / sum (61 taps, sigma 3 by default)
-* ``MotionBlurOperator``     arbitrary k x k PSF, zero taps skipped (psx_op_create_conv2d)
+* ``MotionBlurOperator``     arbitrary k x k PSF, evaluated row segment by row segment (psx_op_create_conv2d)
 """
 from __future__ import annotations
 
