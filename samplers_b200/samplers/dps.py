@@ -177,6 +177,8 @@ class DPSRun:
         torch.cuda.current_stream(dev).wait_stream(side)
         self.x.copy_(keep)
         self.k_dev.zero_()
+        torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()   # hand the warm-up's activation memory back before the graph's private pool grows
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self._timestep_body()
