@@ -298,7 +298,7 @@ def run_own(args):
                      "traffic": NCU_DRAM_BYTES_PER_STEP if (L, n) == (16, 3 * 256 * 256) else None,
                      "traffic_source": "profiles/r01_ncu_full_summary.csv (ncu --set full, cold cache: "
                                        "dram read+write of the 3 K1 launches + K2)",
-                     "peak_source": peak_src, "kernel": "fused DPS step = K1 (3 launches) + K2",
+                     "peak_source": peak_src, "kernel": "fused DPS step = K1 (3 kernels per sample group) + K2",
                      "algorithmic_bytes": alg_bytes, "k1_ms": k1_ms, "k2_ms": k2_ms,
                      "kernel_timing": ("external CUDA events inside the replayed graph, mean of K replays read "
                                        "one by one right after the timed region; last timed step: "
