@@ -127,3 +127,27 @@ def test_psld_and_resample_accept_a_bf16_network_on_fp32_state():
     except StopIteration:       # bf16 rounding may change the number of optimiser iterations / draws
         out = None
     assert out is None or (out.dtype == torch.float32 and torch.isfinite(out).all())
+
+
+def test_psld_and_resample_run_on_the_stable_diffusion_adapter():
+    """The SD-shaped adapter (narrow random-init config) through both latent samplers: shapes, finiteness, clean-up."""
+    from samplers_b200 import operators as P
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.networks import StableDiffusionCondition, StableDiffusionNetwork
+    from samplers_b200.noise import GaussianNoise
+    from samplers_b200.samplers import PSLDSampler, ReSampleSampler
+    net = StableDiffusionNetwork.from_config("sd15-tiny", device=DEV)
+    shape = (3, 64, 64)
+    op = P.GaussianBlurOperator(shape, 9, 1.5).to(DEV)
+    x = torch.rand(shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0)) * 2 - 1
+    prob = InverseProblem.from_clean_data(x, operator=op, noise=GaussianNoise(sigma=0.05),
+                                          rng=torch.Generator(device=DEV).manual_seed(1))
+    cond = StableDiffusionCondition(guidance_scale=2.0, prompt_embeds=torch.zeros(1, 7, 32))
+    out = PSLDSampler(net)(prob, num_sampling_steps=6, num_reconstructions=2, condition=cond)
+    assert out.shape == (2, *shape) and torch.isfinite(out).all()
+    lat = PSLDSampler(net)(prob, num_sampling_steps=4, decode_output=False)
+    assert lat.shape == (1, 4, 8, 8)
+    out = ReSampleSampler(net)(prob, num_sampling_steps=8, num_reconstructions=2, max_optimization_iters=3,
+                               time_travel_interval=2, inter_timesteps=2)
+    assert out.shape == (2, *shape) and torch.isfinite(out).all()
+    assert not net.is_condition_initialized and not net.are_sampling_parameters_initialized

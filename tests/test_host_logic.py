@@ -211,3 +211,51 @@ def test_step_rows_hold_the_by_value_scalars():
         assert rows[k].tolist() == [float(np.float32(v)) for v in want]
     per_step = step_rows(plan, 2.0, lambda sc: 0.5 * sc.sqrt_1m_acp)
     assert per_step[3, 6].item() == float(np.float32(0.5 * plan[3].sqrt_1m_acp))
+
+
+def test_stable_diffusion_network_surface():
+    """StableDiffusionNetwork mirrors samplers/networks/diffusers/stable_diffusion.py: latent shape rule, ascending
+    timesteps, conditioning life cycle, CFG batch doubling, VAE scaling factor -- on the narrow random-init config."""
+    from samplers_b200.networks import LatentEpsilonNetwork, StableDiffusionCondition, StableDiffusionNetwork
+    from samplers_b200.networks.sd15 import SD15, AutoencoderKLLite, UNet2DConditionLite
+    with torch.device("meta"):    # the full SD-1.5 shapes, without allocating them
+        unet, vae = UNet2DConditionLite(**SD15["unet"]), AutoencoderKLLite(**SD15["vae"])
+    assert sum(p.numel() for p in unet.parameters()) == 859_520_964      # the published SD-1.5 UNet size
+    assert abs(sum(p.numel() for p in vae.parameters()) - 83_653_863) < 4096
+    net = StableDiffusionNetwork.from_config("sd15-tiny")
+    assert isinstance(net, LatentEpsilonNetwork) and net.dtype == torch.float32
+    assert float(net.alphas_cumprod[0]) == 1.0 and net.alphas_cumprod.numel() == 1001
+    with pytest.raises(RuntimeError):
+        net.set_condition(None)                      # before set_sampling_parameters, as the reference
+    with pytest.raises(ValueError):
+        net.get_latent_shape((3, 60, 64))
+    assert net.get_latent_shape((3, 64, 64)) == (4, 8, 8)
+    net.set_sampling_parameters(10, batch_size=1, num_reconstructions=2)
+    assert net.timesteps.tolist() == sorted(net.timesteps.tolist()) and net.are_sampling_parameters_initialized
+    z = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(0))
+    with pytest.raises(RuntimeError):
+        net.forward(z, 500)                          # before set_condition
+    net.set_condition(None)
+    e0 = net.forward(z, 500)
+    assert e0.shape == z.shape and torch.equal(e0, net.forward(z, torch.tensor([500])))
+    x = net.decode(z)
+    assert x.shape == (2, 3, 64, 64) and not x.requires_grad
+    assert net.encode(x).shape == z.shape
+    zg = z.clone().requires_grad_()
+    assert net.decode(zg, differentiable=True).requires_grad
+    # decode(z) = vae.decode(z / scaling_factor); encode = mean * scaling_factor
+    assert torch.allclose(net.vae.decode(z / 0.18215), x, atol=1e-6)
+    emb = torch.randn(1, 7, 32, generator=torch.Generator().manual_seed(1))
+    net.set_condition(StableDiffusionCondition(guidance_scale=3.0, prompt_embeds=emb))
+    assert net._conditioning.prompt_embeds.shape == (4, 7, 32) and net._conditioning.do_classifier_free_guidance
+    e1 = net.forward(z, 500)
+    net.set_condition(StableDiffusionCondition(guidance_scale=1.0, prompt_embeds=emb))
+    e_text = net.forward(z, 500)
+    assert torch.allclose(e1, e0 + 3.0 * (e_text - e0), atol=1e-5)       # CFG formula
+    with pytest.raises(NotImplementedError):
+        net.set_condition(StableDiffusionCondition(prompt="a photo"))      # no text encoder in this build
+    with pytest.raises(ValueError):
+        net.set_condition(StableDiffusionCondition(prompt_embeds=torch.zeros(1, 5, 32)))
+    net.clear_condition()
+    net.clear_sampling_parameters()
+    assert not net.is_condition_initialized and not net.are_sampling_parameters_initialized

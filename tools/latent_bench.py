@@ -1,0 +1,73 @@
+"""PSLD / ReSample timesteps at BASELINE.json configs 4-5 shapes with the SD-1.5-shaped random-init network
+(x 3x512x512, z 4x64x64): ms per step and the share of it spent in libpsx kernels (CUDA events around the ABI calls).
+
+    python tools/latent_bench.py [--config sd15|sd15-tiny] [--size 512] [--batch 1] [--steps 3] [--dtype fp32|bf16]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="sd15")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    a = ap.parse_args()
+    from samplers_b200 import _native, operators as P
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.networks import StableDiffusionNetwork
+    from samplers_b200.noise import GaussianNoise
+    from samplers_b200.samplers import PSLDSampler
+    dev = "cuda:0"
+    shape = (3, a.size, a.size)
+    net = StableDiffusionNetwork.from_config(a.config, device=dev,
+                                             torch_dtype=torch.bfloat16 if a.dtype == "bf16" else None)
+    op = P.GaussianBlurOperator(shape, 61, 3.0).to(dev)
+    x = torch.rand(shape, device=dev) * 2 - 1
+    prob = InverseProblem.from_clean_data(x, operator=op, noise=GaussianNoise(sigma=0.05))
+    # time the ABI calls
+    spans = []
+    wrapped = {}
+    for name in ("dps_pre", "lincomb3", "bridge_update", "tweedie"):
+        fn = getattr(_native, name)
+        wrapped[name] = fn
+
+        def make(fn):
+            def w(*args, **kw):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); r = fn(*args, **kw); e.record()
+                spans.append((s, e))
+                return r
+            return w
+        setattr(_native, name, make(fn))
+    sampler = PSLDSampler(net)
+    total_steps = 1000 // max(1, 1000 // (a.steps + 2))
+    for rep in range(2):    # first call warms cuDNN up
+        spans.clear()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sampler(prob, num_sampling_steps=a.steps + 2, num_reconstructions=a.batch, decode_output=False)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    for name, fn in wrapped.items():
+        setattr(_native, name, fn)
+    kern_ms = sum(s.elapsed_time(e) for s, e in spans)
+    guided = a.steps
+    print(json.dumps({"sampler": "psld", "config": a.config, "dtype": a.dtype, "x_shape": list(shape), "batch": a.batch,
+                      "guided_steps": guided, "ms_per_step": round(1e3 * wall / (guided + 1), 2),
+                      "libpsx_ms_per_step": round(kern_ms / guided, 4), "libpsx_calls": len(spans),
+                      "libpsx_share": round(kern_ms / (1e3 * wall), 5),
+                      "mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}))
+
+
+if __name__ == "__main__":
+    main()
