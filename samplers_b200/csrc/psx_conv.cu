@@ -742,16 +742,16 @@ __device__ __forceinline__ void col_block16(float2 (&acc)[16], const float* __re
 }
 
 // ---- columns, fused V / residual / V^T, 16 rows x 2 columns per task, h2 written row-pair interleaved.
-// Needs W % 32 == 0, H % 16 == 0, H <= 256 (at most one task per thread and pass), tf.k == ta.k == K.
-template <int K>
+// Strip width TC = 32 for planes up to 256 rows, 16 for up to 512 rows (at most one task per thread and pass:
+// (H / 16) * (TC / 2) <= 256); needs W % TC == 0, H % 16 == 0, tf.k == ta.k == K.
+template <int K, int TC>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ y, float* __restrict__ out_il,
             float* __restrict__ err_part, int C, int H, int W, int strips, int64_t num_tiles, int64_t obs_repeat,
-            int64_t sample0, const __grid_constant__ Taps tf, const __grid_constant__ Taps ta) {
+            int64_t sample0, int box_h, const __grid_constant__ Taps tf, const __grid_constant__ Taps ta) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float red[32];
   PSX_TRK(1, 0)
-  constexpr int TC = kColTC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw + kPipeHdr);
   const int rowsA = H + K;
@@ -770,7 +770,9 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
       const int64_t pl = tile / strips;
       const int c0 = (int)(tile - pl * strips) * TC;
       mbar_expect_tx(&bars[stage], (uint32_t)H * TC * 4u);
-      tma_load_2d(smem + (size_t)stage * stage_floats - (size_t)tf.lo * TC, &tmap, c0, (int)(pl * H), &bars[stage]);
+      float* dst = smem + (size_t)stage * stage_floats - (size_t)tf.lo * TC;
+      for (int h0 = 0; h0 < H; h0 += box_h)  // a TMA box holds at most 256 rows: taller planes take two boxes
+        tma_load_2d(dst + (size_t)h0 * TC, &tmap, c0, (int)(pl * H) + h0, &bars[stage]);
     }
   };
 
@@ -784,7 +786,7 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
 #pragma unroll
   for (int t = 0; t < 5; ++t) {  // zero the halo rows once, while the first box load is in flight (the TMA
     const int i = threadIdx.x + t * kThreads;  // writes interior rows only): (136 + 8) rows * 8 float4 <= 5 * 256
-    const int r = i >> 3, c4 = i & 7;
+    const int r = i / (TC / 4), c4 = i % (TC / 4);
     if (r < K) {
       const int ra = r < -tf.lo ? r : r + H, rb = r < -ta.lo ? r : r + H;
       *reinterpret_cast<float4*>(smem + (size_t)ra * TC + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -850,7 +852,7 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
 constexpr int kIlThreads = 128;
 constexpr int kIlStages = 3;
 
-template <int K>
+template <int K, int ROUNDS>
 __global__ void __launch_bounds__(kIlThreads)
 conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t total_rows, int W, int pitch2,
              int64_t num_tiles, const __grid_constant__ Taps taps, float coef,
@@ -884,10 +886,7 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
     }
   };
 
-  const int ncg = W >> 4;
-  const bool q_ok = (int)threadIdx.x < 8 * ncg;
-  const int q = q_ok ? threadIdx.x : 8 * ncg - 1;
-  const int rp = q & 7, cg = q >> 3;
+  const int ncg = W >> 4;  // ROUNDS * kIlThreads >= 8 * ncg tasks: row pair rp = q & 7, 16-column group cg = q >> 3
   int64_t tile = blockIdx.x;
 #pragma unroll
   for (int d = 0; d < kIlStages - 1; ++d)
@@ -914,23 +913,30 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
     if (nxt < num_tiles) issue(nxt, (it + kIlStages - 1) % kIlStages);
     mbar_wait(&bars[stage], (uint32_t)(it / kIlStages) & 1u);
     if (it == 0) { PSX_TRK(2, 2) }
-    float2 acc[16];
-    row_block16<K>(acc, stages + (size_t)stage * stage_f2 + rp * pitch2 + 16 * cg, taps);
-    if (it == 0) { PSX_TRK(2, 3) }
-    const int64_t pair = tile * (kPipeRows / 2) + rp;
-    if (q_ok && pair < total_pairs) {
-      step_scalars_coef(dsc, coef);  // after the FFMA2 block: keeps the tap pairs on the uniform datapath
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float* dst = out + (2 * pair + h) * W + 16 * cg;
+    for (int round = 0; round < ROUNDS; ++round) {
+      const int q_raw = threadIdx.x + round * kIlThreads;
+      const bool q_ok = q_raw < 8 * ncg;
+      const int q = q_ok ? q_raw : 8 * ncg - 1;  // every thread computes (uniform control flow); stores are guarded
+      const int rp = q & 7, cg = q >> 3;
+      float2 acc[16];
+      row_block16<K>(acc, stages + (size_t)stage * stage_f2 + rp * pitch2 + 16 * cg, taps);
+      if (it == 0 && round == 0) { PSX_TRK(2, 3) }
+      const int64_t pair = tile * (kPipeRows / 2) + rp;
+      if (q_ok && pair < total_pairs) {
+        step_scalars_coef(dsc, coef);  // after the FFMA2 block: keeps the tap pairs on the uniform datapath
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          float4 v;
-          v.x = __fmul_rn(coef, h ? acc[4 * m].y : acc[4 * m].x);
-          v.y = __fmul_rn(coef, h ? acc[4 * m + 1].y : acc[4 * m + 1].x);
-          v.z = __fmul_rn(coef, h ? acc[4 * m + 2].y : acc[4 * m + 2].x);
-          v.w = __fmul_rn(coef, h ? acc[4 * m + 3].y : acc[4 * m + 3].x);
-          st_stream4(dst + 4 * m, v);
+        for (int h = 0; h < 2; ++h) {
+          float* dst = out + (2 * pair + h) * W + 16 * cg;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            float4 v;
+            v.x = __fmul_rn(coef, h ? acc[4 * m].y : acc[4 * m].x);
+            v.y = __fmul_rn(coef, h ? acc[4 * m + 1].y : acc[4 * m + 1].x);
+            v.z = __fmul_rn(coef, h ? acc[4 * m + 2].y : acc[4 * m + 2].x);
+            v.w = __fmul_rn(coef, h ? acc[4 * m + 3].y : acc[4 * m + 3].x);
+            st_stream4(dst + 4 * m, v);
+          }
         }
       }
     }
@@ -1176,12 +1182,12 @@ static EncodeTiledFn encode_fn() {
   }
   return fn;
 }
-static bool make_strip_map(CUtensorMap* map, const float* base, int64_t rows, int W, int H) {
+static bool make_strip_map(CUtensorMap* map, const float* base, int64_t rows, int W, int box_w, int box_h) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)W * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)kColTC, (cuuint32_t)H};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1211,6 +1217,10 @@ int sepblur_plan(psx_op* op) {
   for (int tc : {32, 16, 8}) {
     if (cols_smem(op, tc, true, op->fv, op->av) <= limit) { op->col_tc = tc; break; }
   }
+  // planes taller / wider than 256 (up to 512) run the strip kernels with 16-column strips (launch_pre_sepblur)
+  if ((op->H > 256 || op->W > 256) && op->H <= 512 && op->W <= 512 && op->H % 32 == 0 && op->W % 32 == 0 &&
+      op->col_tc >= 16)
+    op->col_tc = 16;
   if (!op->col_tc) return fail(PSX_ERR_UNSUPPORTED, "separable blur: image too tall for the column kernel");
   op->err_parts = op->C * ceil_div(op->W, op->col_tc);
   return PSX_OK;
@@ -1272,7 +1282,7 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
                              8 * kColTC * sizeof(float);  // 8 slack rows for the unconditional window prefetch
     CUtensorMap map;
     if ((op->W % kColTC) == 0 && (op->H % 16) == 0 && op->H <= 256 && !getenv("PSX_NO_PIPE") &&
-        make_strip_map(&map, in, planes * op->H, op->W, op->H)) {
+        make_strip_map(&map, in, planes * op->H, op->W, kColTC, op->H)) {
       const int rounds = (op->H >> 3) * (kColTC >> 1) / kThreads;  // H % 16 == 0  =>  exact
       const int strips = op->W / kColTC;
       const int64_t num_tiles = planes * strips;
@@ -1315,33 +1325,35 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
 }
 
 // cols16 + rows_il tail of K1 (h1 in ws, row-major)  ->  cot.  Returns -1 when the geometry does not qualify.
-template <int K>
+template <int K, int TC>
 static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot, float* err_part, int64_t planes,
                          int64_t sample0, int64_t obs_repeat, float w, float sa, const float* dsc, cudaStream_t st) {
   const int W = op->W, H = op->H;
   CUtensorMap map;
-  if (!make_strip_map(&map, ws, planes * H, W, H)) return -1;
-  const size_t smem_c = kPipeHdr + 3 * ((size_t)H + K) * kColTC * sizeof(float);
+  const int box_h = H > 256 ? H / 2 : H;  // TMA boxes hold at most 256 rows
+  if (!make_strip_map(&map, ws, planes * H, W, TC, box_h)) return -1;
+  constexpr int ROUNDS = TC == 32 ? 1 : 2;  // TC = 16 serves planes up to 512 wide: 256 row tasks per 16-row tile
+  const size_t smem_c = kPipeHdr + 3 * ((size_t)H + K) * TC * sizeof(float);
   const int pitch2 = row_pitch2(W + K);
   const size_t smem_r = kPipeHdr + (size_t)kIlStages * (kPipeRows / 2) * pitch2 * sizeof(float2);
   static int occ_c = 0, occ_r = 0;
   if (!occ_c) {
-    cudaFuncSetAttribute(conv_cols16<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_rows_il<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, conv_cols16<K>, kThreads, smem_c) != cudaSuccess || occ_c < 1)
+    cudaFuncSetAttribute(conv_cols16<K, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_rows_il<K, ROUNDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, conv_cols16<K, TC>, kThreads, smem_c) != cudaSuccess || occ_c < 1)
       occ_c = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, conv_rows_il<K>, kIlThreads, smem_r) != cudaSuccess || occ_r < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, conv_rows_il<K, ROUNDS>, kIlThreads, smem_r) != cudaSuccess || occ_r < 1)
       occ_r = 1;
   }
-  const int strips = W / kColTC;
+  const int strips = W / TC;
   const int64_t tiles_c = planes * strips;
   int64_t grid_c = (int64_t)occ_c * sm_count();
   if (grid_c > tiles_c) grid_c = tiles_c;
   // in place: the strip of h1 is fully in shared memory before the interleaved h2 of the same rows/columns is
   // written; other CTAs never touch this strip's (row pair, column) cells -- but the IL layout moves data
   // ACROSS rows of a pair, so in-place is only safe because both rows of a pair belong to the same strip tile.
-  conv_cols16<K><<<(unsigned)grid_c, kThreads, smem_c, st>>>(map, y, ws, err_part, op->C, H, W, strips, tiles_c,
-                                                             obs_repeat, sample0, op->fv, op->av);
+  conv_cols16<K, TC><<<(unsigned)grid_c, kThreads, smem_c, st>>>(map, y, ws, err_part, op->C, H, W, strips, tiles_c,
+                                                             obs_repeat, sample0, box_h, op->fv, op->av);
   int rc = check_cuda(cudaGetLastError(), "conv_cols16 launch");
   if (rc) return rc;
   const int64_t total_rows = planes * H;
@@ -1349,7 +1361,7 @@ static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot
   int64_t grid_r = (int64_t)occ_r * sm_count();
   if (grid_r > tiles_r) grid_r = tiles_r;
   const float coef = (float)((double)w / (double)sa);
-  conv_rows_il<K><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r, op->ah, coef, dsc);
+  conv_rows_il<K, ROUNDS><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r, op->ah, coef, dsc);
   return check_cuda(cudaGetLastError(), "conv_rows_il launch");
 }
 
@@ -1380,9 +1392,12 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
     return check_cuda(cudaGetLastError(), "blur_k1_fused launch");
   }
   const int kk = op->fv.k;
-  const bool fast = op->W % kColTC == 0 && op->W <= 256 && op->H % 16 == 0 && op->H <= 256 && op->av.k == kk &&
-                    op->ah.k == kk && op->col_tc == kColTC && (kk == 40 || kk == 16) && !getenv("PSX_NO_PIPE") &&
-                    !getenv("PSX_NO_FAST16") && encode_fn() != nullptr;
+  // planes up to 256 x 256: 32-column strips; up to 512 x 512 (configs 4-5): 16-column strips, two TMA boxes per strip
+  const bool small = op->W <= 256 && op->H <= 256;
+  const bool fast = op->W % 32 == 0 && op->W <= 512 && op->H % 16 == 0 && op->H <= 512 && op->av.k == kk &&
+                    op->ah.k == kk && op->col_tc == (small ? 32 : 16) && (kk == 40 || kk == 16) &&
+                    (small || op->H % 32 == 0) && !getenv("PSX_NO_PIPE") && !getenv("PSX_NO_FAST16") &&
+                    encode_fn() != nullptr;
   if (fast) {
     // The three launches of one group leave SMs idle in every kernel's ramp-up and tail (about a third of K1 at
     // L = 16, tools/micro/k1_trace_main.cu).  Samples are independent, so K1 runs as `parts` groups on the caller's
@@ -1409,8 +1424,9 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
       int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x + off, eps + off, ws + off, planes_p, sa, s1, w, dsc, s);
       if (rc) return rc;
       float* part = err_part + l0 * op->err_parts;
-      rc = kk == 40 ? run_fast_tail<40>(op, y, ws + off, cot + off, part, planes_p, l0, obs_repeat, w, sa, dsc, s)
-                    : run_fast_tail<16>(op, y, ws + off, cot + off, part, planes_p, l0, obs_repeat, w, sa, dsc, s);
+#define PSX_TAIL(KK, TCC) run_fast_tail<KK, TCC>(op, y, ws + off, cot + off, part, planes_p, l0, obs_repeat, w, sa, dsc, s)
+      rc = small ? (kk == 40 ? PSX_TAIL(40, 32) : PSX_TAIL(16, 32)) : (kk == 40 ? PSX_TAIL(40, 16) : PSX_TAIL(16, 16));
+#undef PSX_TAIL
       if (rc < 0) return fail(PSX_ERR_CUDA, "blur K1: could not encode the strip tensor map");
       if (rc) return rc;
       if (p > 0) {

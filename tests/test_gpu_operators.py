@@ -169,3 +169,32 @@ def test_cluster_fused_blur_k1_matches_three_launch_path(monkeypatch):
         outs.append((cot.clone(), part.sum(1).clone()))
     assert rel_err(outs[1][0].cpu(), outs[0][0].cpu()) < 2e-6
     assert rel_err(outs[1][1].cpu(), outs[0][1].cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("shape,taps", [((3, 512, 512), (61, 3.0)), ((1, 384, 512), (61, 3.0)), ((2, 512, 256), (61, 3.0)),
+                                        ((3, 288, 320), (9, 1.5)), ((1, 512, 512), (21, 2.0))])
+@pytest.mark.parametrize("L", [2, 5])
+def test_blur_k1_on_planes_up_to_512_matches_oracle(shape, taps, L):
+    """Configs 4-5 run the blur on 512 x 512 pixel planes: the strip kernels with 16-column strips and two TMA boxes
+    per strip, against the oracle's torch expression executed on the device (cuDNN fp32, TF32 off)."""
+    from samplers_b200 import _native, operators as pops
+    torch.backends.cudnn.allow_tf32 = False
+    op = pops.GaussianBlurOperator(shape, kernel_size=taps[0], sigma=taps[1]).to(DEV)
+    ora = oops.OracleGaussianBlur(shape, taps[0], taps[1])
+    nat = op._native_cached(torch.device(DEV))
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(L, *shape, device=DEV, generator=gen)
+    eps = torch.randn(L, *shape, device=DEV, generator=gen)
+    y = torch.randn(1, *shape, device=DEV, generator=gen)
+    sa, s1, w = 0.8, 0.6, 400.0
+    cot = torch.empty(L, nat.n, device=DEV)
+    part = torch.empty(L, nat.err_parts, device=DEV)
+    ws = torch.empty(nat.workspace_bytes(L) // 4, device=DEV)
+    _native.dps_pre(nat, x.view(L, -1), eps.view(L, -1), y.view(1, -1), L, sa, s1, w, cot, part, ws)
+    x0 = (x - s1 * eps) / sa
+    r = y - ora.apply(x0)
+    ref = ora.adjoint(r) * (w / sa)
+    assert rel_err(cot.cpu(), ref.reshape(L, -1).cpu()) < 5e-6
+    assert rel_err(part.sum(1).cpu(), r.double().square().sum((1, 2, 3)).float().cpu()) < 1e-5
+    assert rel_err(op.apply(x).cpu(), ora.apply(x).cpu()) < 2e-6
+    assert rel_err(op.apply_transpose(x).cpu(), ora.adjoint(x).cpu()) < 2e-6

@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 from samplers_b200 import _native, operators as pops  # noqa: E402
 
-SHAPE = (3, 256, 256)
+SHAPE = (3, 256, 256)  # --size changes H = W
 
 
 def peak():
@@ -81,7 +81,10 @@ def main():
     ap.add_argument("--batches", default="16,64")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--mode", default="rotate", choices=["rotate", "flush"])
+    ap.add_argument("--size", type=int, default=256)
     args = ap.parse_args()
+    global SHAPE
+    SHAPE = (3, args.size, args.size)
     dev = torch.device("cuda:0")
     pk = peak()
     flush = torch.empty(128 * 1024 * 1024 if args.mode == "flush" else 1, device=dev)
@@ -131,7 +134,7 @@ def main():
                 m2p, mz = time_flush(k2p, args.iters, flush), time_flush(zgen, args.iters, flush)
             b1, b2 = 16 * L * n, 24 * L * n
             print(json.dumps({
-                "op": kind, "L": L, "mode": args.mode, "nsets": nsets, "k1_us": m1 * 1e3, "k2_us": m2 * 1e3,
+                "op": kind, "size": args.size, "L": L, "mode": args.mode, "nsets": nsets, "k1_us": m1 * 1e3, "k2_us": m2 * 1e3,
                 "k1_gbs": b1 / m1 / 1e6, "k2_gbs": b2 / m2 / 1e6,
                 "fused_gbs": (b1 + b2) / (m1 + m2) / 1e6, "fused_frac": (b1 + b2) / (m1 + m2) / 1e6 / pk,
                 "k1_frac": b1 / m1 / 1e6 / pk, "k2_frac": b2 / m2 / 1e6 / pk, "peak": pk,
