@@ -21,23 +21,26 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--sampler", default="psld", choices=["psld", "resample"])
+    ap.add_argument("--opt-iters", type=int, default=200, help="resample: max optimisation iterations per stage")
     a = ap.parse_args()
     from samplers_b200 import _native, operators as P
     from samplers_b200.inverse_problem import InverseProblem
     from samplers_b200.networks import StableDiffusionNetwork
-    from samplers_b200.noise import GaussianNoise
-    from samplers_b200.samplers import PSLDSampler
+    from samplers_b200.noise import GaussianNoise, PoissonNoise
+    from samplers_b200.samplers import PSLDSampler, ReSampleSampler
     dev = "cuda:0"
     shape = (3, a.size, a.size)
     net = StableDiffusionNetwork.from_config(a.config, device=dev,
                                              torch_dtype=torch.bfloat16 if a.dtype == "bf16" else None)
     op = P.GaussianBlurOperator(shape, 61, 3.0).to(dev)
     x = torch.rand(shape, device=dev) * 2 - 1
-    prob = InverseProblem.from_clean_data(x, operator=op, noise=GaussianNoise(sigma=0.05))
+    noise = GaussianNoise(sigma=0.05) if a.sampler == "psld" else PoissonNoise(rate=4.0)   # config 5: Poisson noise
+    prob = InverseProblem.from_clean_data(x, operator=op, noise=noise)
     # time the ABI calls
     spans = []
     wrapped = {}
-    for name in ("dps_pre", "lincomb3", "bridge_update", "tweedie"):
+    for name in ("dps_pre", "lincomb3", "bridge_update", "tweedie", "ddim_eps_step", "stochastic_resample", "adamw_step"):
         fn = getattr(_native, name)
         wrapped[name] = fn
 
@@ -49,20 +52,26 @@ def main():
                 return r
             return w
         setattr(_native, name, make(fn))
-    sampler = PSLDSampler(net)
-    total_steps = 1000 // max(1, 1000 // (a.steps + 2))
+    if a.sampler == "psld":
+        sampler = PSLDSampler(net)
+        call = lambda: sampler(prob, num_sampling_steps=a.steps + 2, num_reconstructions=a.batch, decode_output=False)
+    else:
+        sampler = ReSampleSampler(net)
+        call = lambda: sampler(prob, num_sampling_steps=a.steps + 2, num_reconstructions=a.batch, decode_output=False,
+                               max_optimization_iters=a.opt_iters, time_travel_interval=2, inter_timesteps=2)
     for rep in range(2):    # first call warms cuDNN up
         spans.clear()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        sampler(prob, num_sampling_steps=a.steps + 2, num_reconstructions=a.batch, decode_output=False)
+        call()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
     for name, fn in wrapped.items():
         setattr(_native, name, fn)
     kern_ms = sum(s.elapsed_time(e) for s, e in spans)
     guided = a.steps
-    print(json.dumps({"sampler": "psld", "config": a.config, "dtype": a.dtype, "x_shape": list(shape), "batch": a.batch,
+    extra = {} if a.sampler == "psld" else {"total_s": round(wall, 2), "max_optimization_iters": a.opt_iters}
+    print(json.dumps({"sampler": a.sampler, **extra, "config": a.config, "dtype": a.dtype, "x_shape": list(shape), "batch": a.batch,
                       "guided_steps": guided, "ms_per_step": round(1e3 * wall / (guided + 1), 2),
                       "libpsx_ms_per_step": round(kern_ms / guided, 4), "libpsx_calls": len(spans),
                       "libpsx_share": round(kern_ms / (1e3 * wall), 5),
