@@ -37,7 +37,7 @@ GUIDED_STEPS = SAMPLING_STEPS - 2        # range(len(ts)-1, 1, -1)
 SIGMA_Y = 0.05
 # dram__bytes_read.sum + dram__bytes_write.sum per step from the committed ncu --set full capture of the four
 # launches at this exact shape (L = 16): 25.19 + 13.41 + 12.61 (K1) + 62.93 + 1.25 (K2) MB
-NCU_DRAM_BYTES_PER_STEP = int((25.19 + 13.41 + 12.61 + 62.93 + 1.25) * 1e6)
+NCU_DRAM_BYTES_PER_STEP = int((25.19 + 13.41 + 12.60 + 62.93 + 2.06) * 1e6)  # rows + cols + rows_il + K2 read, K2 write
 METRIC = "dps_posterior_samples_per_s_256"
 WORKLOAD = "cfg2: DPS gaussian-blur 61x61 sigma3, ddpm-celebahq-256 UNet, 1000 steps, batch 16/GPU, 3x256x256"
 
