@@ -1404,7 +1404,8 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
     // stream plus side streams: one group's tails and launch gaps are filled by the other groups' kernels.
     // Measured (profiles/README.md): inside a replayed CUDA graph the fork/join is free and two groups cut K1 by 8 %
     // at L = 16; launched eagerly the extra event calls cost more than the overlap returns until L >= 32.
-    static const int forced = [] { const char* e = getenv("PSX_SPLIT"); return e ? atoi(e) : 0; }();
+    const char* env_split = getenv("PSX_SPLIT");  // read per call: the tests switch it
+    const int forced = env_split ? atoi(env_split) : 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     const int want = forced ? forced : ((cap == cudaStreamCaptureStatusActive || L >= 32) ? 2 : 1);

@@ -198,3 +198,36 @@ def test_blur_k1_on_planes_up_to_512_matches_oracle(shape, taps, L):
     assert rel_err(part.sum(1).cpu(), r.double().square().sum((1, 2, 3)).float().cpu()) < 1e-5
     assert rel_err(op.apply(x).cpu(), ora.apply(x).cpu()) < 2e-6
     assert rel_err(op.apply_transpose(x).cpu(), ora.adjoint(x).cpu()) < 2e-6
+
+
+@pytest.mark.parametrize("env", [{}, {"PSX_SPLIT": "2"}, {"PSX_SPLIT": "4"}, {"PSX_NO_FAST16": "1"}, {"PSX_NO_PIPE": "1"},
+                                 {"PSX_FUSED": "1"}])
+def test_every_blur_k1_code_path_gives_the_same_answer(monkeypatch, env):
+    """The default strip kernels, the multi-group schedule, the 8-output pipelined kernels, the one-tile-per-CTA
+    kernels and the cluster kernel are five implementations of one function."""
+    from samplers_b200 import _native, operators as pops
+    for k in ("PSX_SPLIT", "PSX_NO_FAST16", "PSX_NO_PIPE", "PSX_FUSED"):
+        monkeypatch.delenv(k, raising=False)
+    op = pops.GaussianBlurOperator(FULL).to(DEV)
+    nat = op._native_cached(torch.device(DEV))
+    L = 8
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(L, nat.n, device=DEV, generator=gen)
+    eps = torch.randn(L, nat.n, device=DEV, generator=gen)
+    y = torch.randn(2, nat.n_y, device=DEV, generator=gen)          # two observations, 4 samples each
+    ws = torch.empty(nat.workspace_bytes(L) // 4, device=DEV)
+
+    def run():
+        cot, part = torch.empty_like(x), torch.empty(L, nat.err_parts, device=DEV)
+        _native.dps_pre(nat, x, eps, y, 4, 0.8, 0.6, 400.0, cot, part, ws)
+        torch.cuda.synchronize()
+        return cot, part.sum(1)
+
+    base = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    if "PSX_SPLIT" in env:                  # same kernels, same tiles per sample: bit-identical
+        assert torch.equal(got[0], base[0]) and torch.equal(got[1], base[1])
+    else:
+        assert rel_err(got[0].cpu(), base[0].cpu()) < 2e-6 and rel_err(got[1].cpu(), base[1].cpu()) < 1e-6
