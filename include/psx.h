@@ -212,6 +212,24 @@ PSX_API int psx_dps_post_philox_dev(const float* d_x_t, const float* d_eps, cons
                                     float* d_err_out, void* stream);
 PSX_API int psx_philox_normal(float* d_out, int64_t numel, uint64_t seed, uint64_t step, void* stream);
 
+/* ------------------------------------------------------------------ bf16 state (production mode)
+ * K1 / K2 with the sampler state, eps, the cotangent, the network VJP and the noise tensor stored as bf16
+ * (d_* void pointers below are __nv_bfloat16 arrays; d_y, d_err_part, d_err_out stay fp32).  Values are widened
+ * to fp32 on load, the arithmetic is that of psx_dps_pre / psx_dps_post, results are rounded to bf16 on store:
+ *     K_bf16(inputs) == bf16_rn(K_fp32(float(inputs)))   bit for bit.
+ * 18 B/element per step with in-kernel noise against 40 B/element in fp32; the tolerance against
+ * the fp32 reference is bf16's own rounding, 2^-9 relative per stored value.  Identity and mask operators only.
+ * d_step_row (nullable) overrides the by-value scalars as in the *_dev entry points; use_philox != 0 draws the
+ * noise in the kernel from (seed, step) or, when d_seed_step is not NULL, from that device pair. */
+PSX_API int psx_dps_pre_bf16(const psx_op* op, const void* d_x_t, const void* d_eps, const float* d_y, int64_t L,
+                             int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight,
+                             const float* d_step_row, void* d_cot, float* d_err_part, void* stream);
+PSX_API int psx_dps_post_bf16(const void* d_x_t, const void* d_eps, const void* d_cot, const void* d_vjp,
+                              const void* d_z, const float* d_err_part, int err_parts, int64_t L, int64_t n,
+                              float sqrt_acp, float sqrt_1m_acp, float c_ell, float c_s, float std, float gamma,
+                              const float* d_step_row, int use_philox, uint64_t seed, uint64_t step,
+                              const uint64_t* d_seed_step, void* d_x_next, float* d_err_out, void* stream);
+
 /* ------------------------------------------------------------- latent samplers (PSLD)
  * psx_bridge_update -- bridge (DDIM/DDPM) update with an additive correction, the tail of a PSLD step:
  *   x_next = c_ell*x + c_s*x0 + std*z + grad_scale*grad,   x0 = (x - s1*eps)/sa

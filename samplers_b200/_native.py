@@ -56,6 +56,9 @@ PROTOTYPES = {
                                       C.c_uint64, C.c_uint64, _f32p, _f32p, _vp]),
     "psx_dps_post_philox_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _vp, _f32p,
                                           _f32p, _vp]),
+    "psx_dps_pre_bf16": (C.c_int, [_opp, _vp, _vp, _f32p, _i64, _i64, _f, _f, _f, _f32p, _vp, _f32p, _vp]),
+    "psx_dps_post_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32p, C.c_int, _i64, _i64, _f, _f, _f, _f, _f, _f, _f32p,
+                                    C.c_int, C.c_uint64, C.c_uint64, _vp, _vp, _f32p, _vp]),
     "psx_philox_normal": (C.c_int, [_f32p, _i64, C.c_uint64, C.c_uint64, _vp]),
     "psx_tweedie": (C.c_int, [_f32p, _f32p, _i64, _i64, _f, _f, _f32p, _f32p, _f32p, _vp]),
     "psx_bridge_update": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, _f, _f32p, _vp]),
@@ -297,6 +300,34 @@ def dps_post_philox_dev(x_t, eps, cot, vjp, err_part, err_parts: int, n: int, st
                                              ptr(err_part), err_parts if err_part is not None else 0, L, n,
                                              step_row.data_ptr(), seed_step.data_ptr(), x_next.data_ptr(),
                                              ptr(err_out), stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def dps_pre_bf16(op: NativeOp, x_t, eps, y, obs_repeat: int, sa: float, s1: float, weight: float, cot, err_part,
+                 step_row=None) -> None:
+    """K1 on a bf16 state (x_t, eps, cot bf16; y, err_part fp32); ``step_row`` overrides the by-value scalars."""
+    global launch_count
+    L = x_t.shape[0]
+    with torch.cuda.device(x_t.device):
+        check(load().psx_dps_pre_bf16(op.handle, x_t.data_ptr(), eps.data_ptr(), y.data_ptr(), L, obs_repeat, sa, s1,
+                                      weight, ptr(step_row), cot.data_ptr(), err_part.data_ptr(),
+                                      stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def dps_post_bf16(x_t, eps, cot, vjp, z, err_part, err_parts: int, n: int, sa: float, s1: float, c_ell: float,
+                  c_s: float, std: float, gamma: float, x_next, err_out=None, step_row=None, philox=None,
+                  seed_step=None) -> None:
+    """K2 on a bf16 state.  Noise: ``z`` (bf16 tensor), or ``philox=(seed, step)`` / ``seed_step`` (device pair)."""
+    global launch_count
+    L = x_t.shape[0]
+    use_philox = philox is not None or seed_step is not None
+    seed, step = philox if philox is not None else (0, 0)
+    with torch.cuda.device(x_t.device):
+        check(load().psx_dps_post_bf16(x_t.data_ptr(), eps.data_ptr(), cot.data_ptr(), vjp.data_ptr(), ptr(z),
+                                       ptr(err_part), err_parts if err_part is not None else 0, L, n, sa, s1, c_ell,
+                                       c_s, std, gamma, ptr(step_row), int(use_philox), seed & (2 ** 64 - 1), step,
+                                       ptr(seed_step), x_next.data_ptr(), ptr(err_out), stream_ptr(x_t.device)))
     launch_count += 1
 
 

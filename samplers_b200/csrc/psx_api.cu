@@ -29,6 +29,11 @@ int launch_post(const float*, const float*, const float*, const float*, const fl
                 int64_t, int64_t, float, float, float, float, float, float, const float*, float*, float*, int,
                 uint64_t, uint64_t, const uint64_t*, cudaStream_t);
 int launch_philox_normal(float*, int64_t, uint64_t, uint64_t, cudaStream_t);
+int launch_pre_pointwise_bf16(const psx_op*, const void*, const void*, const float*, int64_t, int64_t, float, float, float,
+                              const float*, void*, float*, cudaStream_t);
+int launch_post_bf16(const void*, const void*, const void*, const void*, const void*, const float*, int, int64_t, int64_t,
+                     float, float, float, float, float, float, const float*, void*, float*, int, uint64_t, uint64_t,
+                     const uint64_t*, cudaStream_t);
 int launch_tweedie(const float*, const float*, int64_t, int64_t, float, float, float*, float*, float*,
                    cudaStream_t);
 int launch_add_noise(float*, const float*, int64_t, float, float, cudaStream_t);
@@ -406,6 +411,40 @@ PSX_API int psx_dps_post_philox_dev(const float* d_x_t, const float* d_eps, cons
               "psx_dps_post_philox_dev: d_err_part and err_parts must agree");
   return launch_post(d_x_t, d_eps, d_cot, d_vjp, nullptr, d_err_part, err_parts, L, n, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f,
                      d_step_row, d_x_next, d_err_out, 2, 0, 0, d_seed_step, (cudaStream_t)stream);
+}
+
+PSX_API int psx_dps_pre_bf16(const psx_op* op, const void* d_x_t, const void* d_eps, const float* d_y, int64_t L,
+                             int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight,
+                             const float* d_step_row, void* d_cot, float* d_err_part, void* stream) {
+  PSX_REQUIRE(op && d_x_t && d_eps && d_y && d_cot && d_err_part, "psx_dps_pre_bf16: null pointer");
+  PSX_REQUIRE(L > 0 && L <= 65535 && obs_repeat > 0, "psx_dps_pre_bf16: bad sizes");
+  PSX_REQUIRE(d_step_row || (sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(sqrt_1m_acp) &&
+                             std::isfinite(lik_weight)),
+              "psx_dps_pre_bf16: non-finite or non-positive schedule scalar");
+  if (op->kind != PSX_OP_IDENTITY && op->kind != PSX_OP_MASK)
+    return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre_bf16: the bf16 state path covers identity and mask operators");
+  const bool dev = d_step_row != nullptr;
+  return launch_pre_pointwise_bf16(op, d_x_t, d_eps, d_y, L, obs_repeat, dev ? 1.f : sqrt_acp, dev ? 0.f : sqrt_1m_acp,
+                                   dev ? 1.f : lik_weight, d_step_row, d_cot, d_err_part, (cudaStream_t)stream);
+}
+
+PSX_API int psx_dps_post_bf16(const void* d_x_t, const void* d_eps, const void* d_cot, const void* d_vjp, const void* d_z,
+                              const float* d_err_part, int err_parts, int64_t L, int64_t n, float sqrt_acp,
+                              float sqrt_1m_acp, float c_ell, float c_s, float std_, float gamma,
+                              const float* d_step_row, int use_philox, uint64_t seed, uint64_t step,
+                              const uint64_t* d_seed_step, void* d_x_next, float* d_err_out, void* stream) {
+  PSX_REQUIRE(d_x_t && d_eps && d_cot && d_vjp && d_x_next, "psx_dps_post_bf16: null pointer");
+  PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts >= 0, "psx_dps_post_bf16: bad sizes");
+  PSX_REQUIRE((err_parts > 0) == (d_err_part != nullptr), "psx_dps_post_bf16: d_err_part and err_parts must agree");
+  const bool dev = d_step_row != nullptr;
+  PSX_REQUIRE(dev || (sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(c_ell) && std::isfinite(c_s) &&
+                      std::isfinite(std_) && std::isfinite(gamma)),
+              "psx_dps_post_bf16: non-finite scalar");
+  PSX_REQUIRE(use_philox || d_z || (!dev && std_ == 0.f), "psx_dps_post_bf16: need d_z, Philox noise or std == 0");
+  const int zmode = use_philox ? 2 : (d_z && (dev || std_ != 0.f) ? 1 : 0);
+  return launch_post_bf16(d_x_t, d_eps, d_cot, d_vjp, d_z, d_err_part, err_parts, L, n, dev ? 1.f : sqrt_acp,
+                          dev ? 0.f : sqrt_1m_acp, c_ell, c_s, std_, gamma, d_step_row, d_x_next, d_err_out, zmode, seed,
+                          step, d_seed_step, (cudaStream_t)stream);
 }
 
 PSX_API int psx_philox_normal(float* d_out, int64_t numel, uint64_t seed, uint64_t step, void* stream) {

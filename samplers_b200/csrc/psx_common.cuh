@@ -134,6 +134,37 @@ __device__ __forceinline__ void step_scalars_k2(const float* dsc, float& sa, flo
   }
 }
 
+// ---------------------------------------------------------------- in-kernel noise (Philox4x32-10 + Box-Muller)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r) {
+      k.x += 0x9E3779B9u;
+      k.y += 0xBB67AE85u;
+    }
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+  }
+  return c;
+}
+__device__ __forceinline__ float philox_u01(uint32_t x) {  // (x + 0.5) * 2^-32 in (0, 1]
+  return __fadd_rn(__fmul_rn(__uint2float_rn(x), 2.3283064365386963e-10f), 1.1641532182693481e-10f);
+}
+__device__ __forceinline__ float2 box_muller(float ua, float ub) {
+  const float r = sqrtf(-2.f * logf(ua));
+  float sn, cs;
+  sincospif(2.f * ub, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+__device__ __forceinline__ float4 philox_normal4(uint64_t group, uint64_t seed, uint64_t step) {
+  const uint4 b = philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), (uint32_t)step, (uint32_t)(step >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float2 p = box_muller(philox_u01(b.x), philox_u01(b.y)), q = box_muller(philox_u01(b.z), philox_u01(b.w));
+  return make_float4(p.x, p.y, q.x, q.y);
+}
+
+
 // ---------------------------------------------------------------- reductions (fixed order => deterministic)
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

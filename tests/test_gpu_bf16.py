@@ -1,0 +1,80 @@
+"""bf16 state through the C ABI: K_bf16(inputs) == bf16_rn(K_fp32(float(inputs))) bit for bit, for K1
+(identity, mask) and K2 (tensor noise, in-kernel Philox noise, fixed scale), vector and ragged sizes."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BF = torch.bfloat16
+
+
+@pytest.mark.parametrize("kind", ["identity", "mask"])
+@pytest.mark.parametrize("shape", [(3, 32, 32), (3, 7, 9)])          # n % 8 == 0 and ragged
+def test_k1_bf16_is_the_rounded_fp32_kernel(kind, shape):
+    from samplers_b200 import _native, operators as P
+    op = (P.IdentityOperator(shape) if kind == "identity" else P.RandomInpaintingOperator(shape, 0.7, seed=0, flatten=False)).to(DEV)
+    nat = op._native_cached(torch.device(DEV))
+    L, n = 5, nat.n
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x, e = (torch.randn(L, n, device=DEV, generator=gen).to(BF) for _ in range(2))
+    y = torch.randn(2, n, device=DEV, generator=gen)
+    if kind == "mask":
+        y = y * (~op.mask).float().reshape(1, -1).to(DEV)
+    sa, s1, w = 0.8366600275039673, 0.547722578048706, 400.0
+    cot32, part32 = torch.empty(L, n, device=DEV), torch.empty(L, nat.err_parts, device=DEV)
+    _native.dps_pre(nat, x.float(), e.float(), y, 3, sa, s1, w, cot32, part32, None)
+    cot16, part16 = torch.empty(L, n, device=DEV, dtype=BF), torch.empty(L, nat.err_parts, device=DEV)
+    _native.dps_pre_bf16(nat, x, e, y, 3, sa, s1, w, cot16, part16)
+    assert torch.equal(cot16, cot32.to(BF))
+    # the partial sums are fp32 sums of the same fp32 residuals (the split into parts may differ)
+    assert torch.allclose(part16.sum(1), part32.sum(1), rtol=1e-6)
+    row = torch.tensor([[sa, s1, float(torch.tensor(w) / torch.tensor(sa)), 0, 0, 0, 0, 0]], device=DEV)
+    cot_dev = torch.empty_like(cot16)
+    _native.dps_pre_bf16(nat, x, e, y, 3, 1.0, 0.0, 1.0, cot_dev, part16, step_row=row)
+    assert torch.equal(cot_dev, cot16)
+
+
+@pytest.mark.parametrize("n", [3 * 32 * 32, 1001])
+@pytest.mark.parametrize("noise", ["tensor", "philox", "none", "fixed"])
+def test_k2_bf16_is_the_rounded_fp32_kernel(n, noise):
+    from samplers_b200 import _native
+    L, parts = 3, 64
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x, e, c, v, z = (torch.randn(L, n, device=DEV, generator=gen).to(BF) for _ in range(5))
+    part = torch.rand(L, parts, device=DEV, generator=gen)
+    sc = dict(sa=0.83666, s1=0.54772, c_ell=0.97, c_s=0.021, std=0.0 if noise == "none" else 0.11, gamma=1.3)
+    f = [t.float() for t in (x, e, c, v)]
+    out32, err32 = torch.empty(L, n, device=DEV), torch.empty(L, device=DEV)
+    out16, err16 = torch.empty(L, n, device=DEV, dtype=BF), torch.empty(L, device=DEV)
+    fixed = noise == "fixed"
+    ep, np_ = (None, 0) if fixed else (part, parts)
+    if noise == "philox":
+        _native.dps_post_philox(*f, ep, np_, n, *sc.values(), 77, 5, out32, err32)
+        _native.dps_post_bf16(x, e, c, v, None, ep, np_, n, *sc.values(), out16, err16, philox=(77, 5))
+        ss = torch.tensor([77, 5], dtype=torch.int64, device=DEV)
+        row = torch.tensor([[sc["sa"], sc["s1"], 0.0, sc["c_ell"], sc["c_s"], sc["std"], sc["gamma"], 0.0]], device=DEV)
+        out_dev = torch.empty_like(out16)
+        _native.dps_post_bf16(x, e, c, v, None, ep, np_, n, 1, 0, 0, 0, 0, 0, out_dev, None, step_row=row, seed_step=ss)
+        assert torch.equal(out_dev, out16)
+    else:
+        zz = None if noise == "none" else z
+        _native.dps_post(*f, None if zz is None else zz.float(), ep, np_, n, *sc.values(), out32, None if fixed else err32)
+        _native.dps_post_bf16(x, e, c, v, zz, ep, np_, n, *sc.values(), out16, None if fixed else err16)
+    assert torch.equal(out16, out32.to(BF))
+    if not fixed:
+        assert torch.equal(err16, err32)
+    # in place, as the graphed step uses it
+    xa = x.clone()
+    if noise != "philox":
+        _native.dps_post_bf16(xa, e, c, v, None if noise == "none" else z, ep, np_, n, *sc.values(), xa, None)
+        assert torch.equal(xa, out16)
+
+
+def test_bf16_k1_rejects_operators_without_a_bf16_kernel():
+    from samplers_b200 import _native, operators as P
+    op = P.BoxDownsampleOperator((3, 32, 32), 4).to(DEV)
+    nat = op._native_cached(torch.device(DEV))
+    x = torch.zeros(2, nat.n, device=DEV, dtype=BF)
+    with pytest.raises(NotImplementedError):
+        _native.dps_pre_bf16(nat, x, x, torch.zeros(1, nat.n_y, device=DEV), 2, 0.8, 0.6, 1.0, torch.empty_like(x),
+                             torch.empty(2, nat.err_parts, device=DEV))
