@@ -7,7 +7,7 @@ from ..networks import EpsilonNetwork
 
 class PosteriorSampler(ABC):
     def __init__(self, network: EpsilonNetwork, cuda_graph: bool = False, process_group=None,
-                 philox_seed: int | None = None):
+                 philox_seed: int | None = None, state_dtype=None):
         """``network`` as in the reference.  ``cuda_graph=True`` (DPS / PGDM) records one guided timestep as a CUDA
         graph and replays it for the whole loop; it needs a network whose ``forward`` takes the timestep as a
         device tensor without synchronising, and fails loudly otherwise (there is no silent eager fallback).
@@ -19,6 +19,10 @@ class PosteriorSampler(ABC):
         #: PSLD / ReSample: ranks over which the batch-global norms are all-reduced (None: rank-local norms)
         self.process_group = process_group
         self.philox_seed = philox_seed
+        #: DPS / PGDM: torch.bfloat16 stores the sampler state, eps, cotangent and VJP as bf16 (18 instead of 40
+        #: B/element per step; identity / mask operators); default float32
+        import torch
+        self.state_dtype = torch.float32 if state_dtype is None else state_dtype
 
     @staticmethod
     def _flatten_leading(x: Tensor, *, x_shape: Shape) -> tuple[Tensor, Shape]:

@@ -52,7 +52,8 @@ class DPSRun:
     """
 
     def __init__(self, network, inverse_problem: InverseProblem, view: BatchView, gamma: float, eta: float,
-                 draw: Draw, weight: float | None = None, fixed_scale=None, philox_seed: int | None = None):
+                 draw: Draw, weight: float | None = None, fixed_scale=None, philox_seed: int | None = None,
+                 state_dtype: torch.dtype = torch.float32):
         op, noise = inverse_problem.operator, inverse_problem.noise
         if not isinstance(noise, NoiseModel):
             raise NotImplementedError(f"no fused likelihood for noise model {type(noise).__name__}")
@@ -65,6 +66,12 @@ class DPSRun:
         # pipelines in bf16, scripts/run_psld.py:14) is fed a cast of the state and its eps / VJP are cast back.
         if self.net_dtype not in (torch.float32, torch.bfloat16, torch.float16):
             raise TypeError(f"DPSSampler supports float32 / bfloat16 / float16 networks, got {self.net_dtype}")
+        # state_dtype = bfloat16 (production mode): x, eps, cot, vjp and the noise are STORED as bf16 and the bf16
+        # kernels run (same fp32 arithmetic, results rounded on store; identity / mask operators) -- 18 instead of
+        # 40 B/element per step.  draws stay fp32 and are rounded once.
+        if state_dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"DPSSampler state is float32 or bfloat16, got {state_dtype}")
+        self.state_dtype, self._bf16 = state_dtype, state_dtype == torch.bfloat16
         self.op = op._native_cached(self.device)
         # `weight` / `fixed_scale` turn the same two kernels into the PGDM update (see samplers/pgdm.py)
         self.weight = float(noise._likelihood_weight()) if weight is None else float(weight)
@@ -83,9 +90,9 @@ class DPSRun:
         self.num_steps = len(self.plan)
 
         flat = (self.L, self.n)
-        self.x = draw(view.flat_shape, self.device, self.dtype).reshape(flat).contiguous()
-        self.cot = torch.empty(flat, device=self.device, dtype=torch.float32)
-        self.x_next = torch.empty(flat, device=self.device, dtype=torch.float32)
+        self.x = draw(view.flat_shape, self.device, self.dtype).reshape(flat).to(state_dtype).contiguous()
+        self.cot = torch.empty(flat, device=self.device, dtype=state_dtype)
+        self.x_next = torch.empty(flat, device=self.device, dtype=state_dtype)
         self.err_part = torch.empty((self.L, self.op.err_parts), device=self.device, dtype=torch.float32)
         self.err = torch.empty((self.L,), device=self.device, dtype=torch.float32)
         wsb = self.op.workspace_bytes(self.L)
@@ -93,20 +100,20 @@ class DPSRun:
         self._graph: torch.cuda.CUDAGraph | None = None
 
     def _network_eps(self, t):
-        """(fp32 leaf over the state, eps in the network's dtype with its graph, eps as contiguous fp32 (L, n))."""
+        """(leaf over the state, eps in the network's dtype with its graph, eps as contiguous (L, n) in the state dtype)."""
         x_in = self.x.view(self.view.flat_shape).detach().requires_grad_()
-        eps = self.net.forward(x_in if self.net_dtype == torch.float32 else x_in.to(self.net_dtype), t)
+        eps = self.net.forward(x_in if self.net_dtype == self.state_dtype else x_in.to(self.net_dtype), t)
         eps_flat = eps.detach().reshape(self.L, self.n)
-        if eps_flat.dtype != torch.float32:
-            eps_flat = eps_flat.float()
+        if eps_flat.dtype != self.state_dtype:
+            eps_flat = eps_flat.to(self.state_dtype)
         if not eps_flat.is_contiguous():
             eps_flat = eps_flat.contiguous()
         return x_in, eps, eps_flat
 
     def _network_vjp(self, eps, x_in) -> Tensor:
-        """VJP of the network at the cotangent K1 left in ``self.cot``, as contiguous fp32 (L, n)."""
+        """VJP of the network at the cotangent K1 left in ``self.cot``, as contiguous (L, n) in the state dtype."""
         cot = self.cot.view_as(eps)
-        (v,) = torch.autograd.grad(eps, x_in, grad_outputs=cot if eps.dtype == torch.float32 else cot.to(eps.dtype))
+        (v,) = torch.autograd.grad(eps, x_in, grad_outputs=cot if eps.dtype == cot.dtype else cot.to(eps.dtype))
         v = v.reshape(self.L, self.n)
         return v if v.is_contiguous() else v.contiguous()
 
@@ -120,10 +127,23 @@ class DPSRun:
         torch.index_select(self.table, 0, self.k_dev, out=self.row)
         torch.index_select(self.t_table, 0, self.k_dev, out=self.t_dev)
         x_in, eps, eps_flat = self._network_eps(self.t_dev)
+        fixed = self._fixed_scale is not None
+        if self._bf16:
+            _native.dps_pre_bf16(self.op, self.x, eps_flat, self.y, self.obs_repeat, 1.0, 0.0, 1.0, self.cot,
+                                 self.err_part, step_row=self.row)
+            v = self._network_vjp(eps, x_in)
+            philox = self.philox_seed is not None
+            if self._draw_in_graph and not philox:
+                self.z.normal_()
+            _native.dps_post_bf16(self.x, eps_flat, self.cot, v, None if philox else self.z,
+                                  None if fixed else self.err_part, 0 if fixed else self.op.err_parts, self.n,
+                                  1.0, 0.0, 0.0, 0.0, 0.0, 0.0, self.x, None if fixed else self.err, step_row=self.row,
+                                  seed_step=self.seed_step if philox else None)
+            self.k_dev.add_(1)
+            return
         _native.dps_pre_dev(self.op, self.x, eps_flat, self.y, self.obs_repeat, self.row, self.cot, self.err_part,
                             self.ws)
         v = self._network_vjp(eps, x_in)
-        fixed = self._fixed_scale is not None
         # in place: every element of x is read and written by the same thread of K2
         if self.philox_seed is not None:
             _native.dps_post_philox_dev(self.x, eps_flat, self.cot, v, None if fixed else self.err_part,
@@ -158,7 +178,7 @@ class DPSRun:
         self.seed_step = torch.tensor([self.philox_seed or 0, 0], dtype=torch.int64, device=dev)
         self.k_dev = self.seed_step[1:]
         philox = self.philox_seed is not None
-        self.z = None if philox else torch.zeros((self.L, self.n), dtype=torch.float32, device=dev)
+        self.z = None if philox else torch.zeros((self.L, self.n), dtype=self.state_dtype, device=dev)
         self._draw_in_graph = philox or ((self.draw is _default_draw) if draw_in_graph is None else bool(draw_in_graph))
         self._k_host = 0
         keep = self.x.clone()
@@ -209,6 +229,8 @@ class DPSRun:
             return self._replay(k, z)
         sc = self.plan[k]
         x_in, eps, eps_flat = self._network_eps(sc.t)                        # graph kept for the VJP
+        if self._bf16:
+            return self._step_bf16(k, sc, x_in, eps, eps_flat, z)
         _native.dps_pre(self.op, self.x, eps_flat, self.y, self.obs_repeat, sc.sqrt_acp, sc.sqrt_1m_acp,
                         self.weight, self.cot, self.err_part, self.ws)
         v = self._network_vjp(eps, x_in)
@@ -232,6 +254,23 @@ class DPSRun:
                              sc.c_ell, sc.c_s, sc.std, self._fixed_scale(sc), self.x_next, None)
         self.x, self.x_next = self.x_next, self.x
 
+    def _step_bf16(self, k: int, sc: StepScalars, x_in, eps, eps_flat, z) -> None:
+        """The eager timestep on the bf16 state (psx_dps_pre_bf16 / psx_dps_post_bf16)."""
+        _native.dps_pre_bf16(self.op, self.x, eps_flat, self.y, self.obs_repeat, sc.sqrt_acp, sc.sqrt_1m_acp,
+                             self.weight, self.cot, self.err_part)
+        v = self._network_vjp(eps, x_in)
+        fixed = self._fixed_scale is not None
+        philox = (self.philox_seed, k) if (self.philox_seed is not None and z is None) else None
+        if philox is None and z is None and sc.std != 0.0:
+            z = self.draw(self.view.flat_shape, self.device, self.dtype)
+        if z is not None:
+            z = z.reshape(self.L, self.n).to(self.state_dtype)
+        _native.dps_post_bf16(self.x, eps_flat, self.cot, v, z, None if fixed else self.err_part,
+                              0 if fixed else self.op.err_parts, self.n, sc.sqrt_acp, sc.sqrt_1m_acp, sc.c_ell, sc.c_s,
+                              sc.std, self._fixed_scale(sc) if fixed else self.gamma, self.x_next,
+                              None if fixed else self.err, philox=philox)
+        self.x, self.x_next = self.x_next, self.x
+
     def finalize(self, out: Tensor | None = None, total: Tensor | None = None,
                  total_sq: Tensor | None = None) -> Tensor:
         """Final Tweedie estimate at timesteps[1] (dps.py:125-126) -> (L, n); optionally written into a
@@ -240,10 +279,10 @@ class DPSRun:
         sa, s1 = tweedie_scalars(self.net.alphas_cumprod, t)
         with torch.no_grad():
             x = self.x.view(self.view.flat_shape)
-            eps = self.net.forward(x if self.net_dtype == torch.float32 else x.to(self.net_dtype), t)
+            eps = self.net.forward(x if self.net_dtype == x.dtype else x.to(self.net_dtype), t)
             eps = eps.reshape(self.L, self.n).float().contiguous()
         out = torch.empty((self.L, self.n), device=self.device, dtype=torch.float32) if out is None else out
-        _native.tweedie(self.x, eps, sa, s1, out, total, total_sq)
+        _native.tweedie(self.x if not self._bf16 else self.x.float(), eps, sa, s1, out, total, total_sq)
         return out
 
 
@@ -263,7 +302,8 @@ class DPSSampler(PosteriorSampler, Generic[Condition_co]):
                                     num_reconstructions=num_reconstructions, batch_size=view.batch_size)
         net.set_condition(condition=condition)
         try:
-            return DPSRun(net, inverse_problem, view, gamma, eta, self.draw, philox_seed=self.philox_seed)
+            return DPSRun(net, inverse_problem, view, gamma, eta, self.draw, philox_seed=self.philox_seed,
+                          state_dtype=self.state_dtype)
         except Exception:
             self.release()
             raise

@@ -50,7 +50,7 @@ class PGDMSampler(PosteriorSampler, Generic[Condition_co]):
                 return float(gw * torch.tensor(sc.sqrt_1m_acp, dtype=torch.float32))
 
             run = DPSRun(net, inverse_problem, view, 0.0, eta, self.draw, weight=2.0 * gain, fixed_scale=scale,
-                         philox_seed=self.philox_seed)
+                         philox_seed=self.philox_seed, state_dtype=self.state_dtype)
             if self.cuda_graph:
                 run.capture()
             for k in range(run.num_steps):

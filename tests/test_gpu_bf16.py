@@ -78,3 +78,57 @@ def test_bf16_k1_rejects_operators_without_a_bf16_kernel():
     with pytest.raises(NotImplementedError):
         _native.dps_pre_bf16(nat, x, x, torch.zeros(1, nat.n_y, device=DEV), 2, 0.8, 0.6, 1.0, torch.empty_like(x),
                              torch.empty(2, nat.err_parts, device=DEV))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("net_dtype", [torch.float32, torch.bfloat16])
+def test_sampler_on_a_bf16_state(graph, net_dtype):
+    """DPSSampler(state_dtype=bfloat16): the run stays close to the fp32-state run of the same network (stated
+    tolerance: bf16 rounding of the stored state, a few 2^-9 per step), eager and graph, fp32 and bf16 networks."""
+    from samplers_b200 import operators as P
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.networks import DDPMNetwork
+    from samplers_b200.noise import GaussianNoise
+    from samplers_b200.samplers import DPSSampler
+    from tests._golden import rel_err
+    shape = (3, 32, 32)
+    op = P.RandomInpaintingOperator(shape, 0.5, seed=0, flatten=False).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x_true = torch.rand(shape, device=DEV, generator=gen) * 2 - 1
+    y = op.apply(x_true[None])[0] + 0.05 * torch.randn(shape, device=DEV, generator=gen) * (~op.mask).float().to(DEV)
+    prob = InverseProblem(operator=op, observation=y, noise=GaussianNoise(sigma=0.05))
+    torch.manual_seed(1234)
+    net = DDPMNetwork.from_config("tiny", device=DEV, torch_dtype=net_dtype)
+    x_init = torch.randn(2, *shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    outs = {}
+    for sd in (torch.float32, torch.bfloat16):
+        s = DPSSampler(net, cuda_graph=graph, philox_seed=9, state_dtype=sd)
+        s.draw = lambda shape_, device, dtype: x_init.clone()
+        run = s.prepare(prob, num_sampling_steps=8, num_reconstructions=2, gamma=0.05)
+        try:
+            if graph:
+                run.capture()
+            for k in range(3):
+                run.step(k)
+            assert run.x.dtype == sd and run.cot.dtype == sd
+            outs[sd] = run.x.float().clone()
+            fin = run.finalize()
+            assert fin.dtype == torch.float32 and torch.isfinite(fin).all()
+        finally:
+            s.release()
+    assert rel_err(outs[torch.bfloat16].cpu(), outs[torch.float32].cpu()) < 3e-2
+
+
+def test_bf16_state_needs_a_pointwise_operator():
+    from samplers_b200 import operators as P
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.networks import DDPMNetwork
+    from samplers_b200.noise import GaussianNoise
+    from samplers_b200.samplers import DPSSampler
+    shape = (3, 32, 32)
+    op = P.GaussianBlurOperator(shape, 9, 1.5).to(DEV)
+    prob = InverseProblem(operator=op, observation=torch.zeros(shape, device=DEV), noise=GaussianNoise(sigma=0.05))
+    net = DDPMNetwork.from_config("tiny", device=DEV)
+    with pytest.raises(NotImplementedError):
+        DPSSampler(net, state_dtype=BF)(prob, num_sampling_steps=5)
+    assert not net.are_sampling_parameters_initialized

@@ -106,6 +106,9 @@ def main():
                          part=torch.empty(L, nat.err_parts, device=dev))
                 wsb = nat.workspace_bytes(L)
                 d["ws"] = torch.empty(wsb // 4, device=dev) if wsb else None
+                if kind in ("identity", "mask"):
+                    for a, b in (("xh", "x"), ("eh", "eps"), ("vh", "v"), ("ch", "cot"), ("oh", "out")):
+                        d[a] = d[b].to(torch.bfloat16)
                 S.append(d)
             y = torch.randn(1, nat.n_y, device=dev, generator=gen)
 
@@ -123,6 +126,12 @@ def main():
                 _native.dps_post_philox(d["x"], d["eps"], d["cot"], d["v"], d["part"], nat.err_parts, n, 0.8, 0.6,
                                         0.99, 0.01, 0.05, 1.0, 1234, i, d["out"], None)
 
+            def k12h(i):  # bf16 state: K1 + K2 with in-kernel noise (18 B/elem); identity / mask only
+                d = S[i]
+                _native.dps_pre_bf16(nat, d["xh"], d["eh"], y, L, 0.8, 0.6, 400.0, d["ch"], d["part"])
+                _native.dps_post_bf16(d["xh"], d["eh"], d["ch"], d["vh"], None, d["part"], nat.err_parts, n, 0.8, 0.6,
+                                      0.99, 0.01, 0.05, 1.0, d["oh"], None, philox=(1234, i))
+
             def zgen(i):  # what the Philox K2 replaces: the generator kernel that writes z
                 S[i]["z"].normal_()
 
@@ -134,13 +143,19 @@ def main():
             else:
                 m1, m2 = time_flush(k1, args.iters, flush), time_flush(k2, args.iters, flush)
                 m2p, mz = time_flush(k2p, args.iters, flush), time_flush(zgen, args.iters, flush)
+            mh = None
+            if kind in ("identity", "mask"):
+                for i in range(nsets):
+                    k12h(i)
+                mh = time_rotate(k12h, nsets, args.iters) if args.mode == "rotate" else time_flush(k12h, args.iters, flush)
             b1, b2 = 16 * L * n, 24 * L * n
             print(json.dumps({
                 "op": kind, "size": args.size, "L": L, "mode": args.mode, "nsets": nsets, "k1_us": m1 * 1e3, "k2_us": m2 * 1e3,
                 "k1_gbs": b1 / m1 / 1e6, "k2_gbs": b2 / m2 / 1e6,
                 "fused_gbs": (b1 + b2) / (m1 + m2) / 1e6, "fused_frac": (b1 + b2) / (m1 + m2) / 1e6 / pk,
                 "k1_frac": b1 / m1 / 1e6 / pk, "k2_frac": b2 / m2 / 1e6 / pk, "peak": pk,
-                "k2_philox_us": m2p * 1e3, "torch_normal_us": mz * 1e3}), flush=True)
+                "k2_philox_us": m2p * 1e3, "torch_normal_us": mz * 1e3,
+                **({"bf16_step_us": mh * 1e3, "bf16_step_gbs": 18 * L * n / mh / 1e6} if mh else {})}), flush=True)
             del S
 
 
