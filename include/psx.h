@@ -218,7 +218,7 @@ PSX_API int psx_philox_normal(float* d_out, int64_t numel, uint64_t seed, uint64
  * to fp32 on load, the arithmetic is that of psx_dps_pre / psx_dps_post, results are rounded to bf16 on store:
  *     K_bf16(inputs) == bf16_rn(K_fp32(float(inputs)))   bit for bit.
  * 18 B/element per step with in-kernel noise against 40 B/element in fp32; the tolerance against
- * the fp32 reference is bf16's own rounding, 2^-9 relative per stored value.  Identity and mask operators only.
+ * the fp32 reference is bf16's own rounding, 2^-9 relative per stored value.  Identity, mask and 4x box operators.
  * d_step_row (nullable) overrides the by-value scalars as in the *_dev entry points; use_philox != 0 draws the
  * noise in the kernel from (seed, step) or, when d_seed_step is not NULL, from that device pair. */
 PSX_API int psx_dps_pre_bf16(const psx_op* op, const void* d_x_t, const void* d_eps, const float* d_y, int64_t L,

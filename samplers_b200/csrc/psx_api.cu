@@ -31,6 +31,8 @@ int launch_post(const float*, const float*, const float*, const float*, const fl
 int launch_philox_normal(float*, int64_t, uint64_t, uint64_t, cudaStream_t);
 int launch_pre_pointwise_bf16(const psx_op*, const void*, const void*, const float*, int64_t, int64_t, float, float, float,
                               const float*, void*, float*, cudaStream_t);
+int launch_pre_box_bf16(const psx_op*, const void*, const void*, const float*, int64_t, int64_t, float, float, float,
+                        const float*, void*, float*, cudaStream_t);
 int launch_post_bf16(const void*, const void*, const void*, const void*, const void*, const float*, int, int64_t, int64_t,
                      float, float, float, float, float, float, const float*, void*, float*, int, uint64_t, uint64_t,
                      const uint64_t*, cudaStream_t);
@@ -421,9 +423,12 @@ PSX_API int psx_dps_pre_bf16(const psx_op* op, const void* d_x_t, const void* d_
   PSX_REQUIRE(d_step_row || (sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(sqrt_1m_acp) &&
                              std::isfinite(lik_weight)),
               "psx_dps_pre_bf16: non-finite or non-positive schedule scalar");
-  if (op->kind != PSX_OP_IDENTITY && op->kind != PSX_OP_MASK)
-    return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre_bf16: the bf16 state path covers identity and mask operators");
   const bool dev = d_step_row != nullptr;
+  if (op->kind == PSX_OP_BOX)
+    return launch_pre_box_bf16(op, d_x_t, d_eps, d_y, L, obs_repeat, dev ? 1.f : sqrt_acp, dev ? 0.f : sqrt_1m_acp,
+                               dev ? 1.f : lik_weight, d_step_row, d_cot, d_err_part, (cudaStream_t)stream);
+  if (op->kind != PSX_OP_IDENTITY && op->kind != PSX_OP_MASK)
+    return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre_bf16: the bf16 state path covers identity, mask and 4x box operators");
   return launch_pre_pointwise_bf16(op, d_x_t, d_eps, d_y, L, obs_repeat, dev ? 1.f : sqrt_acp, dev ? 0.f : sqrt_1m_acp,
                                    dev ? 1.f : lik_weight, d_step_row, d_cot, d_err_part, (cudaStream_t)stream);
 }

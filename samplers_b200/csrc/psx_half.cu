@@ -1,4 +1,4 @@
-// psx_half.cu -- bf16-state variants of K1 (identity / mask) and K2: the sampler state, eps, the
+// psx_half.cu -- bf16-state variants of K1 (identity / mask / 4x box) and K2: the sampler state, eps, the
 // cotangent and the network VJP are stored as bf16 (2 B/element), every value is widened to fp32 on load, the
 // arithmetic is the fp32 kernels' arithmetic instruction for instruction, and results are rounded to bf16 (RN) on
 // store.  Hence   K_bf16(inputs) == bf16_rn( K_fp32( float(inputs) ) )   bit for bit -- the property the tests check.
@@ -163,6 +163,74 @@ int launch_pre_pointwise_bf16(const psx_op* op, const void* x, const void* eps, 
   }
 #undef PSX_K1H
   return check_cuda(cudaGetLastError(), "k1_pointwise bf16 launch");
+}
+
+// ---- K1 for the 4 x 4 box (super-resolution): one thread per coarse pixel, 4 rows x 4 bf16 (8 B) of x_t / eps in,
+// one fp32 y in, 4 rows x 4 bf16 cotangents out; the arithmetic (incl. the summation order) is k1_box<4>'s.
+__global__ void __launch_bounds__(kThreads)
+k1_box4_h(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ eps, const float* __restrict__ y,
+          __nv_bfloat16* __restrict__ cot, float* __restrict__ err_part, int slots, int planes, int H, int W,
+          int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef, const float* __restrict__ dsc) {
+  step_scalars_k1(dsc, sa, s1, coef);
+  const TweedieC tc = make_tc(s1, sa);
+  __shared__ float red[32];
+  constexpr int F = 4;
+  const int Hc = H / F, Wc = W / F;
+  const int64_t n = (int64_t)planes * H * W, ny = (int64_t)planes * Hc * Wc;
+  const int64_t l = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, ny);
+  const float inv = 1.0f / (float)(F * F);
+  float acc = 0.f;
+  for (int64_t q = beg + threadIdx.x; q < end; q += kThreads) {
+    const int cx = (int)(q % Wc);
+    const int64_t t = q / Wc;
+    const int cy = (int)(t % Hc);
+    const int pl = (int)(t / Hc);
+    const int64_t off = l * n + ((int64_t)pl * H + (int64_t)cy * F) * W + (int64_t)cx * F;
+    uint2 xr[F], er[F];
+#pragma unroll
+    for (int dy = 0; dy < F; ++dy) {
+      xr[dy] = __ldg(reinterpret_cast<const uint2*>(x + off + (int64_t)dy * W));
+      er[dy] = __ldg(reinterpret_cast<const uint2*>(eps + off + (int64_t)dy * W));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < F; ++dy) {
+      const uint32_t xw[2] = {xr[dy].x, xr[dy].y}, ew[2] = {er[dy].x, er[dy].y};
+#pragma unroll
+      for (int dx = 0; dx < F; ++dx) {
+        const float xv = __uint_as_float(dx & 1 ? xw[dx >> 1] & 0xffff0000u : xw[dx >> 1] << 16);
+        const float ev = __uint_as_float(dx & 1 ? ew[dx >> 1] & 0xffff0000u : ew[dx >> 1] << 16);
+        s = __fadd_rn(s, tweedie(xv, ev, tc));
+      }
+    }
+    const float avg = __fmul_rn(s, inv);
+    const float r = __fsub_rn(__ldg(y + (l / obs_repeat) * ny + q), avg);
+    acc = fmaf(r, r, acc);
+    const float d = __fmul_rn(coef, __fmul_rn(r, inv));
+    const uint32_t dd = pack2(d, d);
+#pragma unroll
+    for (int dy = 0; dy < F; ++dy) *reinterpret_cast<uint2*>(cot + off + (int64_t)dy * W) = make_uint2(dd, dd);
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) err_part[l * slots + blockIdx.x] = tot;
+  if (blockIdx.x == 0)
+    for (int i = gridDim.x + threadIdx.x; i < slots; i += kThreads) err_part[l * slots + i] = 0.f;
+}
+
+int launch_pre_box_bf16(const psx_op* op, const void* x, const void* eps, const float* y, int64_t L, int64_t obs_repeat,
+                        float sa, float s1, float w, const float* dsc, void* cot, float* err_part, cudaStream_t st) {
+  if (op->factor != 4 || op->W % 4 != 0) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre_bf16: box factor 4 (W % 4 == 0) only");
+  const int slots = op->err_parts;
+  const float coef = (float)((double)w / (double)sa);
+  static int rs = 0;
+  if (!rs) rs = resident_slots_h(k1_box4_h);
+  const int parts = one_wave_parts(rs, L, op->n_y, slots);
+  const int64_t chunk = (op->n_y + parts - 1) / parts;
+  k1_box4_h<<<dim3(parts, (unsigned)L), kThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)eps, y,
+                                                          (__nv_bfloat16*)cot, err_part, slots, op->C, op->H, op->W, chunk,
+                                                          obs_repeat, sa, s1, coef, dsc);
+  return check_cuda(cudaGetLastError(), "k1_box bf16 launch");
 }
 
 // ------------------------------------------------------------------------------------------------ K2

@@ -67,7 +67,7 @@ class DPSRun:
         if self.net_dtype not in (torch.float32, torch.bfloat16, torch.float16):
             raise TypeError(f"DPSSampler supports float32 / bfloat16 / float16 networks, got {self.net_dtype}")
         # state_dtype = bfloat16 (production mode): x, eps, cot, vjp and the noise are STORED as bf16 and the bf16
-        # kernels run (same fp32 arithmetic, results rounded on store; identity / mask operators) -- 18 instead of
+        # kernels run (same fp32 arithmetic, results rounded on store; identity / mask / 4x box operators) -- 18 instead of
         # 40 B/element per step.  draws stay fp32 and are rounded once.
         if state_dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"DPSSampler state is float32 or bfloat16, got {state_dtype}")

@@ -70,9 +70,27 @@ def test_k2_bf16_is_the_rounded_fp32_kernel(n, noise):
         assert torch.equal(xa, out16)
 
 
+@pytest.mark.parametrize("shape", [(3, 32, 32), (1, 8, 20)])
+def test_k1_box_bf16_is_the_rounded_fp32_kernel(shape):
+    from samplers_b200 import _native, operators as P
+    op = P.BoxDownsampleOperator(shape, 4).to(DEV)
+    nat = op._native_cached(torch.device(DEV))
+    L, n = 4, nat.n
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    x, e = (torch.randn(L, n, device=DEV, generator=gen).to(BF) for _ in range(2))
+    y = torch.randn(2, nat.n_y, device=DEV, generator=gen)
+    sa, s1, w = 0.8366600275039673, 0.547722578048706, 400.0
+    cot32, part32 = torch.empty(L, n, device=DEV), torch.empty(L, nat.err_parts, device=DEV)
+    _native.dps_pre(nat, x.float(), e.float(), y, 2, sa, s1, w, cot32, part32, None)
+    cot16, part16 = torch.empty(L, n, device=DEV, dtype=BF), torch.empty(L, nat.err_parts, device=DEV)
+    _native.dps_pre_bf16(nat, x, e, y, 2, sa, s1, w, cot16, part16)
+    assert torch.equal(cot16, cot32.to(BF))
+    assert torch.allclose(part16.sum(1), part32.sum(1), rtol=1e-6)
+
+
 def test_bf16_k1_rejects_operators_without_a_bf16_kernel():
     from samplers_b200 import _native, operators as P
-    op = P.BoxDownsampleOperator((3, 32, 32), 4).to(DEV)
+    op = P.GaussianBlurOperator((3, 32, 32), 9, 1.5).to(DEV)
     nat = op._native_cached(torch.device(DEV))
     x = torch.zeros(2, nat.n, device=DEV, dtype=BF)
     with pytest.raises(NotImplementedError):

@@ -49,6 +49,10 @@ def make_op(kind):
         return pops.GaussianBlurOperator(SHAPE, 13, 1.5)
     if kind == "motion61":
         return pops.MotionBlurOperator(SHAPE, kernel_size=61, angle_deg=30.0)
+    if kind == "motion61s":  # steep line: 61 segments of 1-2 chunks
+        return pops.MotionBlurOperator(SHAPE, kernel_size=61, angle_deg=80.0)
+    if kind == "walk61":     # random camera-shake trajectory
+        return pops.MotionBlurOperator(SHAPE, kernel_size=61, intensity=0.5, seed=0)
     raise ValueError(kind)
 
 
