@@ -70,3 +70,74 @@ def test_sharded_run_with_global_norms_reproduces_full_batch_reference(kind, nam
     for rank, shape, want_shape, err in results:
         assert shape == want_shape
         assert err < 2e-4, (rank, err)
+
+
+def _dps_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from samplers_b200 import operators as P
+    from samplers_b200.distributed import sample_posterior
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.networks import DDPMNetwork
+    from samplers_b200.noise import GaussianNoise
+    from samplers_b200.samplers import DPSSampler
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        shape, R = (3, 32, 32), 6
+        torch.manual_seed(1234)
+        net = DDPMNetwork.from_config("tiny", device=dev)
+        op = P.GaussianBlurOperator(shape, 9, 1.5).to(dev)
+        g = torch.Generator().manual_seed(0)
+        x_true = (torch.rand(shape, generator=g) * 2 - 1).to(dev)
+        y = op.apply(x_true[None])[0] + 0.05 * torch.randn(shape, generator=g).to(dev)
+        prob = InverseProblem(operator=op, observation=y, noise=GaussianNoise(sigma=0.05))
+        steps = 8
+        tape = [torch.randn(R, *shape, generator=torch.Generator().manual_seed(100 + i)) for i in range(steps)]
+
+        def run(lo, hi, group_world):
+            it = iter(tape)
+            s = DPSSampler(net)
+            s.draw = lambda sh, device, dtype: next(it)[lo:hi].to(device)
+            if group_world:
+                return sample_posterior(s, prob, num_reconstructions=R, num_sampling_steps=steps, gamma=0.05)
+            r = s.prepare(prob, steps, hi - lo, 0.05, 1.0, None)
+            try:
+                for k in range(r.num_steps):
+                    r.step(k)
+                return r.finalize().view(hi - lo, *shape)
+            finally:
+                s.release()
+
+        per = R // world
+        summary = run(rank * per, (rank + 1) * per, True)            # sharded over the two ranks
+        full = run(0, R, False)                                       # all six on this rank alone
+        err = float((summary.samples - full).abs().max() / full.abs().max())
+        merr = float((summary.mean - full.mean(0)).abs().max() / full.abs().max())
+        verr = float((summary.variance - full.var(0, unbiased=True)).abs().max() / max(float(full.var(0).max()), 1e-12))
+        q.put((rank, tuple(summary.samples.shape), err, merr, verr))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dps_samples_sharded_over_two_gpus_equal_the_single_gpu_run():
+    """sample_posterior: 2 ranks x 3 reconstructions, gathered + reduced over NCCL == 6 reconstructions on one GPU
+    (same injected noise rows), including the posterior mean / variance."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dps_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, shape, err, merr, verr in results:
+        assert shape == (6, 3, 32, 32)
+        assert err < 2e-4 and merr < 2e-4 and verr < 2e-3, (rank, err, merr, verr)
