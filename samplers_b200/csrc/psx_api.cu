@@ -1,6 +1,7 @@
 // psx_api.cu -- extern "C" entry points of libpsx (see include/psx.h).
 // Host-side validation, operator descriptors, tap preparation; all device work is asynchronous
 // on the caller's stream.  No CPU implementation exists behind these calls.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -160,11 +161,17 @@ PSX_API int psx_op_create_sepblur(int C, int H, int W, const float* h_taps_h, in
 
 // Row-segment form of a 2-D PSF for one direction: sign = +1 forward (out[p] = sum w in[p + off]),
 // -1 adjoint (the flipped PSF).
-static int make_psf2d(const float* k, int kh, int kw, int sign, Psf2D* out) {
+// Row-segment / column-segment form of a 2-D PSF for one direction: sign = +1 forward (out[p] = sum w in[p + off]),
+// -1 adjoint (the flipped PSF).  Row segments start at a column offset that is a multiple of 4 (vector loads along
+// the row); column segments start at the exact first tap (the window slides down one row per load).  The cheaper
+// form (chunks + segments) is kept: shallow motion lines are row-like, steep ones and camera shake column-like.
+struct PsfBuild {
   std::vector<RowSeg> segs;
   std::vector<float> w;
-  out->dy_lo = out->dx_lo = 1 << 20;
-  out->dy_hi = out->dx_hi = -(1 << 20);
+  int dy_lo = 1 << 20, dy_hi = -(1 << 20), dx_lo = 1 << 20, dx_hi = -(1 << 20);
+};
+
+static void build_rows(const float* k, int kh, int kw, int sign, PsfBuild& b) {
   for (int row = 0; row < kh; ++row) {
     const int jy = sign > 0 ? row : kh - 1 - row;  // ascending dy in both directions
     int lo = kw, hi = -1;
@@ -179,26 +186,61 @@ static int make_psf2d(const float* k, int kh, int kw, int sign, Psf2D* out) {
     const int dx0 = dxa >= 0 ? (dxa / 4) * 4 : -(((-dxa) + 3) / 4) * 4;  // floor to a multiple of 4
     const int nch = (dxb - dx0 + 4) / 4;
     RowSeg sg;
-    sg.dy = (int16_t)dy; sg.dx0 = (int16_t)dx0; sg.nch = (int16_t)nch; sg.w4_off = (uint16_t)(w.size() / 4);
+    sg.dy = (int16_t)dy; sg.dx0 = (int16_t)dx0; sg.nch = (int16_t)nch; sg.w4_off = (uint16_t)(b.w.size() / 4);
     for (int i = 0; i < 4 * nch; ++i) {
-      const int dx = dx0 + i;                       // tap at column offset dx  <->  kernel column sign*dx + kw/2
-      const int jx = sign * dx + kw / 2;
-      w.push_back(jx >= 0 && jx < kw ? k[jy * kw + jx] : 0.f);
+      const int jx = sign * (dx0 + i) + kw / 2;     // tap at column offset dx  <->  kernel column sign*dx + kw/2
+      b.w.push_back(jx >= 0 && jx < kw ? k[jy * kw + jx] : 0.f);
     }
-    segs.push_back(sg);
-    out->dy_lo = dy < out->dy_lo ? dy : out->dy_lo;
-    out->dy_hi = dy > out->dy_hi ? dy : out->dy_hi;
-    out->dx_lo = dx0 < out->dx_lo ? dx0 : out->dx_lo;
-    out->dx_hi = dx0 + 4 * nch > out->dx_hi ? dx0 + 4 * nch : out->dx_hi;
+    b.segs.push_back(sg);
+    b.dy_lo = std::min(b.dy_lo, dy); b.dy_hi = std::max(b.dy_hi, dy);
+    b.dx_lo = std::min(b.dx_lo, dx0); b.dx_hi = std::max(b.dx_hi, dx0 + 4 * nch);
   }
-  if (segs.empty()) return fail(PSX_ERR_INVALID, "psx_op_create_conv2d: kernel is all zeros");
-  if (w.size() / 4 > 65535) return fail(PSX_ERR_UNSUPPORTED, "psx_op_create_conv2d: PSF too large");
-  out->nseg = (int)segs.size();
-  out->nw4 = (int)(w.size() / 4);
-  int rc = check_cuda(cudaMalloc(&out->d_segs, segs.size() * sizeof(RowSeg)), "cudaMalloc PSF segments");
-  if (!rc) rc = check_cuda(cudaMalloc(&out->d_w4, w.size() * sizeof(float)), "cudaMalloc PSF taps");
-  if (!rc) rc = check_cuda(cudaMemcpy(out->d_segs, segs.data(), segs.size() * sizeof(RowSeg), cudaMemcpyHostToDevice), "copy PSF segments");
-  if (!rc) rc = check_cuda(cudaMemcpy(out->d_w4, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice), "copy PSF taps");
+}
+
+static void build_cols(const float* k, int kh, int kw, int sign, PsfBuild& b) {
+  for (int col = 0; col < kw; ++col) {
+    const int jx = sign > 0 ? col : kw - 1 - col;  // ascending dx in both directions
+    int lo = kh, hi = -1;
+    for (int jy = 0; jy < kh; ++jy)
+      if (k[jy * kw + jx] != 0.f) {
+        lo = jy < lo ? jy : lo;
+        hi = jy > hi ? jy : hi;
+      }
+    if (hi < 0) continue;
+    const int dx = sign * (jx - kw / 2);
+    const int dya = sign * ((sign > 0 ? lo : hi) - kh / 2), dyb = sign * ((sign > 0 ? hi : lo) - kh / 2);  // dya <= dyb
+    const int nch = (dyb - dya + 4) / 4;
+    RowSeg sg;
+    sg.dy = (int16_t)dya; sg.dx0 = (int16_t)dx; sg.nch = (int16_t)nch; sg.w4_off = (uint16_t)(b.w.size() / 4);
+    for (int i = 0; i < 4 * nch; ++i) {
+      const int jy = sign * (dya + i) + kh / 2;
+      b.w.push_back(jy >= 0 && jy < kh ? k[jy * kw + jx] : 0.f);
+    }
+    b.segs.push_back(sg);
+    b.dy_lo = std::min(b.dy_lo, dya); b.dy_hi = std::max(b.dy_hi, dya + 4 * nch);
+    b.dx_lo = std::min(b.dx_lo, dx); b.dx_hi = std::max(b.dx_hi, dx);
+  }
+}
+
+static int make_psf2d(const float* k, int kh, int kw, int sign, Psf2D* out) {
+  PsfBuild rows, cols;
+  build_rows(k, kh, kw, sign, rows);
+  build_cols(k, kh, kw, sign, cols);
+  if (rows.segs.empty()) return fail(PSX_ERR_INVALID, "psx_op_create_conv2d: kernel is all zeros");
+  const char* force = getenv("PSX_PSF_FORM");  // "rows" / "cols": tests and measurements
+  // cost model from the measured kernels (profiles/README.md): one segment costs about as much as one 4-tap chunk
+  bool use_cols = cols.w.size() / 4 + cols.segs.size() < rows.w.size() / 4 + rows.segs.size();
+  if (force) use_cols = force[0] == 'c';
+  const PsfBuild& b = use_cols ? cols : rows;
+  if (b.w.size() / 4 > 65535) return fail(PSX_ERR_UNSUPPORTED, "psx_op_create_conv2d: PSF too large");
+  out->cols = use_cols ? 1 : 0;
+  out->nseg = (int)b.segs.size();
+  out->nw4 = (int)(b.w.size() / 4);
+  out->dy_lo = b.dy_lo; out->dy_hi = b.dy_hi; out->dx_lo = b.dx_lo; out->dx_hi = b.dx_hi;
+  int rc = check_cuda(cudaMalloc(&out->d_segs, b.segs.size() * sizeof(RowSeg)), "cudaMalloc PSF segments");
+  if (!rc) rc = check_cuda(cudaMalloc(&out->d_w4, b.w.size() * sizeof(float)), "cudaMalloc PSF taps");
+  if (!rc) rc = check_cuda(cudaMemcpy(out->d_segs, b.segs.data(), b.segs.size() * sizeof(RowSeg), cudaMemcpyHostToDevice), "copy PSF segments");
+  if (!rc) rc = check_cuda(cudaMemcpy(out->d_w4, b.w.data(), b.w.size() * sizeof(float), cudaMemcpyHostToDevice), "copy PSF taps");
   return rc;
 }
 

@@ -44,8 +44,12 @@ struct Psf2D {              // one direction (forward or adjoint = flipped PSF)
   RowSeg* d_segs;           // device, owned
   float4* d_w4;             // device, owned: zero-padded taps, 4 per chunk
   int nseg, nw4;            // segments, float4 tap groups
-  int dy_lo, dy_hi;         // min / max dy over the segments
-  int dx_lo, dx_hi;         // min dx0 / max (dx0 + 4 * nch) over the segments (multiples of 4)
+  // cols == 0 (row segments): dy_lo/dy_hi = min / max dy, dx_lo/dx_hi = min dx0 / max (dx0 + 4 nch), multiples of 4.
+  // cols == 1 (column segments: RowSeg.dx0 = the column offset, RowSeg.dy = first tap row, taps run down the
+  //            column): dy_lo/dy_hi = min dy / max (dy + 4 nch), dx_lo/dx_hi = min / max column offset.
+  int cols;
+  int dy_lo, dy_hi;
+  int dx_lo, dx_hi;
 };
 
 }  // namespace psx

@@ -1608,6 +1608,153 @@ conv2d_rowseg(const float* __restrict__ in, const float* __restrict__ eps, const
   }
 }
 
+// One chunk of a COLUMN segment: 4 taps x (8 output rows x 2 columns).  The window holds 12 consecutive rows of the
+// thread's column pair and rotates by 4 rows per chunk (R = chunk index modulo 3, as in c2_chunk).  ODD: the pair
+// starts at an odd tile column, i.e. it is not 8-byte aligned and is read as two LDS.32.
+template <bool ODD>
+__device__ __forceinline__ float2 c2_pair(const float* __restrict__ p) {
+  return ODD ? make_float2(p[0], p[1]) : *reinterpret_cast<const float2*>(p);
+}
+template <int R, bool ODD>
+__device__ __forceinline__ void c2_chunk_col(float2 (&acc)[8], float2 (&win)[12], const float* __restrict__ p, int pitch,
+                                             const float4* __restrict__ w4) {
+  constexpr int S = (8 + 4 * R) % 12;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) win[S + i] = c2_pair<ODD>(p + i * pitch);
+  const float4 t = *w4;
+  const float tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      acc[q].x = fmaf(tw[i], win[(q + i + 4 * R) % 12].x, acc[q].x);
+      acc[q].y = fmaf(tw[i], win[(q + i + 4 * R) % 12].y, acc[q].y);
+    }
+}
+template <bool ODD>
+__device__ __forceinline__ void c2_colseg(float2 (&acc)[8], const float* __restrict__ p, int pitch,
+                                          const float4* __restrict__ wp, int nch) {
+  float2 win[12];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) win[i] = c2_pair<ODD>(p + i * pitch);
+  p += 8 * pitch;
+  for (; nch >= 3; nch -= 3, p += 12 * pitch, wp += 3) {
+    c2_chunk_col<0, ODD>(acc, win, p, pitch, wp);
+    c2_chunk_col<1, ODD>(acc, win, p + 4 * pitch, pitch, wp + 1);
+    c2_chunk_col<2, ODD>(acc, win, p + 8 * pitch, pitch, wp + 2);
+  }
+  if (nch >= 1) c2_chunk_col<0, ODD>(acc, win, p, pitch, wp);
+  if (nch >= 2) c2_chunk_col<1, ODD>(acc, win, p + 4 * pitch, pitch, wp + 1);
+}
+
+// Column-segment form (steep motion lines, camera-shake trajectories): every PSF column is a vertical 1-D correlation
+// that starts at its exact first tap -- the window slides down one row per load, so no alignment padding is needed.
+// Thread: column pair cp = lane (a warp reads 256 contiguous bytes per row), 8 output rows of row group warp.
+// dx_lo is a multiple of 4 here (launcher), so the tile is filled with aligned 128-bit loads.
+template <int MODE>
+__global__ void __launch_bounds__(kC2Threads)
+conv2d_colseg(const float* __restrict__ in, const float* __restrict__ eps, const float* __restrict__ y,
+              float* __restrict__ out, float* __restrict__ err_part, const RowSeg* __restrict__ segs,
+              const float4* __restrict__ w4, int nseg, int nw4, int dy_lo, int dy_hi, int dx_lo, int tw, int pitch,
+              int C, int H, int W, int64_t obs_repeat, float sa, float s1, float wgt, const float* __restrict__ dsc) {
+  step_scalars_k1(dsc, sa, s1, wgt);
+  const TweedieC tc = make_tc(s1, sa);
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[32];
+  const int th = kC2TH + dy_hi - dy_lo;  // tile[r][c] = image(r0 + dy_lo + r, c0 + dx_lo + c), c < tw (tw % 4 == 0)
+  const int r0 = blockIdx.y * kC2TH, c0 = blockIdx.x * kC2TW;
+  const int64_t pl = blockIdx.z;
+  const int64_t plane = pl * H * W;
+  if (nw4 > 0) {
+    float4* sw4 = reinterpret_cast<float4*>(smem + th * pitch);
+    RowSeg* ssg = reinterpret_cast<RowSeg*>(sw4 + nw4);
+    for (int i = threadIdx.x; i < nw4; i += kC2Threads) sw4[i] = w4[i];
+    for (int i = threadIdx.x; i < nseg; i += kC2Threads) ssg[i] = segs[i];
+    w4 = sw4;
+    segs = ssg;
+  }
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool vec = (W & 3) == 0;
+#pragma unroll 4
+    for (int r = warp; r < th; r += kC2Threads / 32) {
+      const int gr = r0 + dy_lo + r;
+      const bool row_ok = gr >= 0 && gr < H;
+      for (int c4 = lane; c4 < (tw >> 2); c4 += 32) {
+        const int gc = c0 + dx_lo + 4 * c4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row_ok && vec && gc >= 0 && gc < W) {
+          const int64_t g = plane + (int64_t)gr * W + gc;
+          const float4 a = *reinterpret_cast<const float4*>(in + g);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+          if (MODE == C2_RESIDUAL) {
+            const float4 e = *reinterpret_cast<const float4*>(eps + g);
+            v[0] = tweedie(v[0], e.x, tc); v[1] = tweedie(v[1], e.y, tc);
+            v[2] = tweedie(v[2], e.z, tc); v[3] = tweedie(v[3], e.w, tc);
+          }
+        } else if (row_ok && !vec) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (gc + j >= 0 && gc + j < W) {
+              v[j] = in[plane + (int64_t)gr * W + gc + j];
+              if (MODE == C2_RESIDUAL) v[j] = tweedie(v[j], eps[plane + (int64_t)gr * W + gc + j], tc);
+            }
+        }
+        *reinterpret_cast<float4*>(smem + r * pitch + 4 * c4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+  __syncthreads();
+
+  const int cp = threadIdx.x & 31, rg = threadIdx.x >> 5;  // columns 2cp, 2cp + 1; rows 8rg .. 8rg + 7
+  float2 acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+  RowSeg nxt = segs[0];
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    const RowSeg sg = nxt;
+    if (sgi + 1 < nseg) nxt = segs[sgi + 1];
+    const int dxr = sg.dx0 - dx_lo;
+    const float* p = smem + (8 * rg + sg.dy - dy_lo) * pitch + 2 * cp + dxr;
+    if (dxr & 1) c2_colseg<true>(acc, p, pitch, w4 + sg.w4_off, sg.nch);
+    else c2_colseg<false>(acc, p, pitch, w4 + sg.w4_off, sg.nch);
+  }
+
+  float e2 = 0.f;
+  const bool pair_ok = (W & 1) == 0;  // both columns of a pair are inside together and 8-byte aligned
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int gr = r0 + 8 * rg + j, gc = c0 + 2 * cp;
+    if (gr >= H || gc >= W) continue;
+    const int64_t g = plane + (int64_t)gr * W + gc;
+    const int64_t yo = ((pl / C) / obs_repeat * C + pl % C) * (int64_t)H * W + (int64_t)gr * W + gc;
+    float2 o = acc[j];
+    if (MODE == C2_RESIDUAL) {
+      float2 yv;
+      if (pair_ok) yv = __ldg(reinterpret_cast<const float2*>(y + yo));
+      else { yv.x = __ldg(y + yo); yv.y = gc + 1 < W ? __ldg(y + yo + 1) : 0.f; }
+      o.x = __fsub_rn(yv.x, o.x);
+      o.y = gc + 1 < W ? __fsub_rn(yv.y, o.y) : 0.f;
+      e2 = fmaf(o.x, o.x, e2);
+      e2 = fmaf(o.y, o.y, e2);
+    } else if (MODE == C2_COT) {
+      o.x = __fmul_rn(wgt, o.x);
+      o.y = __fmul_rn(wgt, o.y);
+    }
+    if (pair_ok) *reinterpret_cast<float2*>(out + g) = o;
+    else { out[g] = o.x; if (gc + 1 < W) out[g + 1] = o.y; }
+  }
+  if (MODE == C2_RESIDUAL) {
+    const float tot = block_sum(e2, red);
+    if (threadIdx.x == 0) {
+      const int tiles = gridDim.x * gridDim.y;
+      const int64_t l = pl / C;
+      const int ch = (int)(pl % C);
+      err_part[l * (int64_t)(C * tiles) + (int64_t)ch * tiles + blockIdx.y * gridDim.x + blockIdx.x] = tot;
+    }
+  }
+}
+
 int conv2d_err_parts(const psx_op* op) {
   return op->C * ceil_div(op->W, kC2TW) * ceil_div(op->H, kC2TH);
 }
@@ -1617,11 +1764,30 @@ static int run_conv2d(const psx_op* op, const float* in, const float* eps, const
                       float* err_part, int64_t planes, int64_t obs_repeat, float sa, float s1, float w, const float* dsc,
                       cudaStream_t st) {
   const Psf2D& psf = ADJ ? op->psf_a : op->psf_f;
+  dim3 grid(ceil_div(op->W, kC2TW), ceil_div(op->H, kC2TH), (unsigned)planes);
+  const float wgt = MODE == C2_COT ? (float)((double)w / (double)sa) : w;
+  const size_t tab = (size_t)psf.nw4 * sizeof(float4) + (size_t)psf.nseg * sizeof(RowSeg);
+  if (psf.cols) {
+    const int dx_lo4 = psf.dx_lo >= 0 ? (psf.dx_lo / 4) * 4 : -(((-psf.dx_lo) + 3) / 4) * 4;  // aligned tile origin
+    const int tw = (kC2TW + psf.dx_hi - dx_lo4 + 1 + 3) & ~3;  // columns c0 + dx_lo4 .. c0 + 63 + dx_hi, rounded to 4
+    const int pitch = tw + 4;   // rows 8 floats apart modulo 32 banks is irrelevant here: a warp reads one row at a time
+    size_t smem = (size_t)(kC2TH + psf.dy_hi - psf.dy_lo) * pitch * sizeof(float);
+    const int nw4 = smem + tab <= 160 * 1024 ? psf.nw4 : 0;
+    if (nw4) smem += tab;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(conv2d_colseg<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_done = true;
+    }
+    conv2d_colseg<MODE><<<grid, kC2Threads, smem, st>>>(in, eps, y, out, err_part, psf.d_segs, psf.d_w4, psf.nseg, nw4,
+                                                         psf.dy_lo, psf.dy_hi, dx_lo4, tw, pitch, op->C, op->H, op->W,
+                                                         obs_repeat, sa, s1, wgt, dsc);
+    return check_cuda(cudaGetLastError(), "conv2d_colseg launch");
+  }
   const int tw = kC2TW + psf.dx_hi - psf.dx_lo;
   int pitch = tw;                      // multiple of 4 with pitch / 4 odd: conflict-free LDS.128 (see the kernel)
   if (((pitch >> 2) & 1) == 0) pitch += 4;
   size_t smem = (size_t)(kC2TH + psf.dy_hi - psf.dy_lo) * pitch * sizeof(float);
-  const size_t tab = (size_t)psf.nw4 * sizeof(float4) + (size_t)psf.nseg * sizeof(RowSeg);
   const int nw4 = smem + tab <= 96 * 1024 ? psf.nw4 : 0;  // huge PSFs read their taps through L1 instead
   if (nw4) smem += tab;
   static bool attr_done = false;
@@ -1629,8 +1795,6 @@ static int run_conv2d(const psx_op* op, const float* in, const float* eps, const
     cudaFuncSetAttribute(conv2d_rowseg<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  dim3 grid(ceil_div(op->W, kC2TW), ceil_div(op->H, kC2TH), (unsigned)planes);
-  const float wgt = MODE == C2_COT ? (float)((double)w / (double)sa) : w;
   conv2d_rowseg<MODE><<<grid, kC2Threads, smem, st>>>(in, eps, y, out, err_part, psf.d_segs, psf.d_w4, psf.nseg, nw4,
                                                        psf.dy_lo, psf.dy_hi, psf.dx_lo, psf.dx_hi, pitch, op->C, op->H,
                                                        op->W, obs_repeat, sa, s1, wgt, dsc);

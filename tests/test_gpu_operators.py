@@ -231,3 +231,42 @@ def test_every_blur_k1_code_path_gives_the_same_answer(monkeypatch, env):
         assert torch.equal(got[0], base[0]) and torch.equal(got[1], base[1])
     else:
         assert rel_err(got[0].cpu(), base[0].cpu()) < 2e-6 and rel_err(got[1].cpu(), base[1].cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("form", ["rows", "cols"])
+@pytest.mark.parametrize("psf", ["line20", "line80", "walk"])
+@pytest.mark.parametrize("shape", [(2, 45, 70), (1, 64, 128)])
+def test_motion_psf_row_and_column_segment_kernels_match_oracle(monkeypatch, form, psf, shape):
+    """The 2-D PSF kernels in both segment forms (PSX_PSF_FORM forces one at descriptor creation): A, A^T against the
+    oracle's conv2d, adjoint identity, and the fused K1 against the stand-alone kernels, ragged sizes included."""
+    from samplers_b200 import _native, operators as pops
+    from samplers_b200.operators.blur import motion_line_kernel, motion_walk_kernel
+    torch.backends.cudnn.allow_tf32 = False
+    monkeypatch.setenv("PSX_PSF_FORM", form)
+    k2d = {"line20": lambda: motion_line_kernel(21, 20.0), "line80": lambda: motion_line_kernel(21, 80.0),
+           "walk": lambda: motion_walk_kernel(21, 0.5, 3)}[psf]()
+    op = pops.MotionBlurOperator(shape, kernel=k2d).to(DEV)
+    ora = oops.OracleConv2dBlur(shape, k2d)
+    nat = op._native_cached(torch.device(DEV))
+    L = 3
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    x = torch.randn(L, *shape, device=DEV, generator=gen)
+    yv = torch.randn(L, *shape, device=DEV, generator=gen)
+    ax, aty = op.apply(x), op.apply_transpose(yv)
+    ora.kernel2d = ora.kernel2d.to(DEV)
+    assert rel_err(ax.cpu(), ora.apply(x).cpu()) < 2e-6
+    assert rel_err(aty.cpu(), ora.adjoint(yv).cpu()) < 2e-6
+    lhs, rhs = (ax.double() * yv.double()).sum(), (x.double() * aty.double()).sum()
+    assert abs(float(lhs - rhs)) < 1e-6 * max(1.0, abs(float(lhs)))
+    eps = torch.randn(L, nat.n, device=DEV, generator=gen)
+    y = torch.randn(1, nat.n_y, device=DEV, generator=gen)
+    sa, s1, w = 0.8, 0.6, 400.0
+    cot, part = torch.empty(L, nat.n, device=DEV), torch.empty(L, nat.err_parts, device=DEV)
+    ws = torch.empty(nat.workspace_bytes(L) // 4, device=DEV)
+    xf = x.reshape(L, -1).contiguous()
+    _native.dps_pre(nat, xf, eps, y, L, sa, s1, w, cot, part, ws)
+    x0 = torch.empty_like(xf)
+    _native.tweedie(xf, eps, sa, s1, x0)
+    r = y - nat.apply(x0)
+    assert rel_err(cot.cpu(), (nat.adjoint(r.contiguous()) * w / sa).cpu()) < 2e-6
+    assert rel_err(part.sum(1).cpu(), r.double().square().sum(1).float().cpu()) < 1e-5
