@@ -1,6 +1,6 @@
 // psx_conv.cu -- shared-memory-tiled convolution kernels (sm_100a):
 //   separable blur  A = V . H  (rows then columns), adjoint = H^T . V^T,
-//   depthwise 2-D correlation with an arbitrary PSF as row segments (motion blur),
+//   depthwise 2-D correlation with an arbitrary PSF as row or column segments (motion blur),
 //   and K1 (psx_dps_pre) built from them.  Default K1 for a separable blur (W % 32 == 0, H % 16 == 0, both <= 256):
 //     conv_rows_pipe<TWEEDIE> : x0 = (x_t - s1 eps)/sa on the fly, h1 = H x0              -> workspace
 //     conv_cols16             : r = y - V h1, |r|^2 partials, h2 = V^T r (strip-local)     -> workspace, in place,
