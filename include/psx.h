@@ -218,12 +218,14 @@ PSX_API int psx_philox_normal(float* d_out, int64_t numel, uint64_t seed, uint64
  * to fp32 on load, the arithmetic is that of psx_dps_pre / psx_dps_post, results are rounded to bf16 on store:
  *     K_bf16(inputs) == bf16_rn(K_fp32(float(inputs)))   bit for bit.
  * 18 B/element per step with in-kernel noise against 40 B/element in fp32; the tolerance against
- * the fp32 reference is bf16's own rounding, 2^-9 relative per stored value.  Identity, mask and 4x box operators.
+ * the fp32 reference is bf16's own rounding, 2^-9 relative per stored value.  Identity, mask, 4x box and separable-blur
+ * operators (the blur's intermediates in d_workspace stay fp32).
  * d_step_row (nullable) overrides the by-value scalars as in the *_dev entry points; use_philox != 0 draws the
  * noise in the kernel from (seed, step) or, when d_seed_step is not NULL, from that device pair. */
 PSX_API int psx_dps_pre_bf16(const psx_op* op, const void* d_x_t, const void* d_eps, const float* d_y, int64_t L,
                              int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight,
-                             const float* d_step_row, void* d_cot, float* d_err_part, void* stream);
+                             const float* d_step_row, void* d_cot, float* d_err_part, void* d_workspace,
+                             size_t workspace_bytes, void* stream);
 PSX_API int psx_dps_post_bf16(const void* d_x_t, const void* d_eps, const void* d_cot, const void* d_vjp,
                               const void* d_z, const float* d_err_part, int err_parts, int64_t L, int64_t n,
                               float sqrt_acp, float sqrt_1m_acp, float c_ell, float c_s, float std, float gamma,

@@ -56,7 +56,8 @@ PROTOTYPES = {
                                       C.c_uint64, C.c_uint64, _f32p, _f32p, _vp]),
     "psx_dps_post_philox_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _vp, _f32p,
                                           _f32p, _vp]),
-    "psx_dps_pre_bf16": (C.c_int, [_opp, _vp, _vp, _f32p, _i64, _i64, _f, _f, _f, _f32p, _vp, _f32p, _vp]),
+    "psx_dps_pre_bf16": (C.c_int, [_opp, _vp, _vp, _f32p, _i64, _i64, _f, _f, _f, _f32p, _vp, _f32p, _vp, C.c_size_t,
+                                   _vp]),
     "psx_dps_post_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32p, C.c_int, _i64, _i64, _f, _f, _f, _f, _f, _f, _f32p,
                                     C.c_int, C.c_uint64, C.c_uint64, _vp, _vp, _f32p, _vp]),
     "psx_philox_normal": (C.c_int, [_f32p, _i64, C.c_uint64, C.c_uint64, _vp]),
@@ -304,14 +305,14 @@ def dps_post_philox_dev(x_t, eps, cot, vjp, err_part, err_parts: int, n: int, st
 
 
 def dps_pre_bf16(op: NativeOp, x_t, eps, y, obs_repeat: int, sa: float, s1: float, weight: float, cot, err_part,
-                 step_row=None) -> None:
+                 step_row=None, ws=None) -> None:
     """K1 on a bf16 state (x_t, eps, cot bf16; y, err_part fp32); ``step_row`` overrides the by-value scalars."""
     global launch_count
     L = x_t.shape[0]
     with torch.cuda.device(x_t.device):
         check(load().psx_dps_pre_bf16(op.handle, x_t.data_ptr(), eps.data_ptr(), y.data_ptr(), L, obs_repeat, sa, s1,
-                                      weight, ptr(step_row), cot.data_ptr(), err_part.data_ptr(),
-                                      stream_ptr(x_t.device)))
+                                      weight, ptr(step_row), cot.data_ptr(), err_part.data_ptr(), ptr(ws),
+                                      0 if ws is None else ws.numel() * 4, stream_ptr(x_t.device)))
     launch_count += 1
 
 

@@ -459,20 +459,27 @@ PSX_API int psx_dps_post_philox_dev(const float* d_x_t, const float* d_eps, cons
 
 PSX_API int psx_dps_pre_bf16(const psx_op* op, const void* d_x_t, const void* d_eps, const float* d_y, int64_t L,
                              int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight,
-                             const float* d_step_row, void* d_cot, float* d_err_part, void* stream) {
+                             const float* d_step_row, void* d_cot, float* d_err_part, void* ws, size_t ws_bytes,
+                             void* stream) {
   PSX_REQUIRE(op && d_x_t && d_eps && d_y && d_cot && d_err_part, "psx_dps_pre_bf16: null pointer");
   PSX_REQUIRE(L > 0 && L <= 65535 && obs_repeat > 0, "psx_dps_pre_bf16: bad sizes");
   PSX_REQUIRE(d_step_row || (sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(sqrt_1m_acp) &&
                              std::isfinite(lik_weight)),
               "psx_dps_pre_bf16: non-finite or non-positive schedule scalar");
   const bool dev = d_step_row != nullptr;
+  const float sa = dev ? 1.f : sqrt_acp, s1 = dev ? 0.f : sqrt_1m_acp, w = dev ? 1.f : lik_weight;
   if (op->kind == PSX_OP_BOX)
-    return launch_pre_box_bf16(op, d_x_t, d_eps, d_y, L, obs_repeat, dev ? 1.f : sqrt_acp, dev ? 0.f : sqrt_1m_acp,
-                               dev ? 1.f : lik_weight, d_step_row, d_cot, d_err_part, (cudaStream_t)stream);
+    return launch_pre_box_bf16(op, d_x_t, d_eps, d_y, L, obs_repeat, sa, s1, w, d_step_row, d_cot, d_err_part,
+                               (cudaStream_t)stream);
+  if (op->kind == PSX_OP_SEPBLUR) {
+    if (int rc = check_ws(op, L, ws, ws_bytes)) return rc;
+    return launch_pre_sepblur(op, (const float*)d_x_t, (const float*)d_eps, d_y, L, obs_repeat, sa, s1, w, d_step_row,
+                              (float*)d_cot, d_err_part, nullptr, (float*)ws, (cudaStream_t)stream, true);
+  }
   if (op->kind != PSX_OP_IDENTITY && op->kind != PSX_OP_MASK)
-    return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre_bf16: the bf16 state path covers identity, mask and 4x box operators");
-  return launch_pre_pointwise_bf16(op, d_x_t, d_eps, d_y, L, obs_repeat, dev ? 1.f : sqrt_acp, dev ? 0.f : sqrt_1m_acp,
-                                   dev ? 1.f : lik_weight, d_step_row, d_cot, d_err_part, (cudaStream_t)stream);
+    return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre_bf16: the bf16 state path covers identity, mask, 4x box and separable-blur operators");
+  return launch_pre_pointwise_bf16(op, d_x_t, d_eps, d_y, L, obs_repeat, sa, s1, w, d_step_row, d_cot, d_err_part,
+                                   (cudaStream_t)stream);
 }
 
 PSX_API int psx_dps_post_bf16(const void* d_x_t, const void* d_eps, const void* d_cot, const void* d_vjp, const void* d_z,

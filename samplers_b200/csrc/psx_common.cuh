@@ -1,5 +1,6 @@
 // psx_common.cuh -- shared device helpers for libpsx (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <mutex>
 #include <stdint.h>
@@ -88,6 +89,15 @@ __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)
                : "memory");
+}
+
+// ---------------------------------------------------------------- bf16 storage (production state)
+// bf16 -> fp32 is a 16-bit shift; fp32 -> bf16 rounds to nearest even.  Two values per 32-bit word, low half first.
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t bf16_pack2(float lo, float hi) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&p);
 }
 
 // ---------------------------------------------------------------- arithmetic with torch's roundings
@@ -215,7 +225,7 @@ int launch_pre_box(const psx_op* op, const float* x, const float* eps, const flo
                    float* x0_out, cudaStream_t st);
 int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                        int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
-                       float* x0_out, float* ws, cudaStream_t st);
+                       float* x0_out, float* ws, cudaStream_t st, bool half = false);
 int launch_pre_conv2d(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                       int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                       float* x0_out, float* ws, cudaStream_t st);

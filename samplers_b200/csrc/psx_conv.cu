@@ -444,7 +444,9 @@ constexpr int kPipeHdr = 128;   // bytes reserved at the start of dynamic smem f
 // stages + one compute tile in the row-pair-interleaved float2 layout of conv_rows (pairs (rho, rho+8);
 // pitch2 % 16 == 2 => conflict-free LDS.128) whose halo columns are zeroed once.  A conversion pass
 // (Tweedie or plain copy) moves a landed stage into the compute tile.  Needs W % 8 == 0, W <= 512.
-template <int MODE, int K>
+// HALF (Tweedie mode only): `in` / `eps` point to bf16 arrays (the bf16 sampler state); the raw stages hold bf16 rows
+// and the conversion pass widens them -- everything after it is unchanged.
+template <int MODE, int K, bool HALF = false>
 __global__ void __launch_bounds__(kThreads)
 conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, float* __restrict__ out,
                int64_t total_rows, int W, int pitch2, int64_t num_tiles, const __grid_constant__ Taps taps,
@@ -457,7 +459,7 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float2* comp = reinterpret_cast<float2*>(smem_raw + kPipeHdr);              // 8 x pitch2 float2
   float* raw = reinterpret_cast<float*>(comp + (kPipeRows / 2) * pitch2);       // 2 stages x kArrays x 16 x W
-  const int tile_floats = kPipeRows * W;
+  const int tile_floats = HALF ? (kPipeRows * W) >> 1 : kPipeRows * W;  // one array of one stage, in 4-byte units
   const int w4 = W >> 2;
 
   if (threadIdx.x == 0) {
@@ -471,11 +473,12 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
     if (threadIdx.x == 0) {
       const int64_t r0 = tile * kPipeRows;
       const int64_t left = total_rows - r0;
-      const uint32_t nb = (uint32_t)(left < kPipeRows ? left : kPipeRows) * (uint32_t)W * 4u;
+      constexpr uint32_t esize = HALF ? 2u : 4u;
+      const uint32_t nb = (uint32_t)(left < kPipeRows ? left : kPipeRows) * (uint32_t)W * esize;
       float* xs = raw + (size_t)stage * kArrays * tile_floats;
       mbar_expect_tx(&bars[stage], nb * kArrays);
-      bulk_g2s(xs, in + r0 * W, nb, &bars[stage]);
-      if (kArrays == 2) bulk_g2s(xs + tile_floats, eps + r0 * W, nb, &bars[stage]);
+      bulk_g2s(xs, reinterpret_cast<const char*>(in) + r0 * W * esize, nb, &bars[stage]);
+      if (kArrays == 2) bulk_g2s(xs + tile_floats, reinterpret_cast<const char*>(eps) + r0 * W * esize, nb, &bars[stage]);
     }
   };
 
@@ -508,12 +511,19 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
       if (rp < kPipeRows / 2) {
         const bool va = rp < rows_valid, vb = rp + 8 < rows_valid;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (va) a = *reinterpret_cast<const float4*>(xs + rp * W + 4 * c4);
-        if (vb) b = *reinterpret_cast<const float4*>(xs + (rp + 8) * W + 4 * c4);
+        auto ld4 = [&](const float* base, int row) {  // 4 consecutive columns of one raw row
+          if (HALF) {
+            const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(base) + ((size_t)row * W + 4 * c4) * 2);
+            return make_float4(bf16_lo(h.x), bf16_hi(h.x), bf16_lo(h.y), bf16_hi(h.y));
+          }
+          return *reinterpret_cast<const float4*>(base + row * W + 4 * c4);
+        };
+        if (va) a = ld4(xs, rp);
+        if (vb) b = ld4(xs, rp + 8);
         if (MODE == ROWS_TWEEDIE) {
           float4 ea = make_float4(0.f, 0.f, 0.f, 0.f), eb = ea;
-          if (va) ea = *reinterpret_cast<const float4*>(xs + tile_floats + rp * W + 4 * c4);
-          if (vb) eb = *reinterpret_cast<const float4*>(xs + tile_floats + (rp + 8) * W + 4 * c4);
+          if (va) ea = ld4(xs + tile_floats, rp);
+          if (vb) eb = ld4(xs + tile_floats, rp + 8);
           a.x = tweedie(a.x, ea.x, tc); a.y = tweedie(a.y, ea.y, tc);
           a.z = tweedie(a.z, ea.z, tc); a.w = tweedie(a.w, ea.w, tc);
           b.x = tweedie(b.x, eb.x, tc); b.y = tweedie(b.y, eb.y, tc);
@@ -852,7 +862,7 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
 constexpr int kIlThreads = 128;
 constexpr int kIlStages = 3;
 
-template <int K, int ROUNDS>
+template <int K, int ROUNDS, bool HALF = false>  // HALF: `out` is a bf16 array (the bf16 cotangent)
 __global__ void __launch_bounds__(kIlThreads)
 conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t total_rows, int W, int pitch2,
              int64_t num_tiles, const __grid_constant__ Taps taps, float coef,
@@ -935,7 +945,12 @@ conv_rows_il(const float* __restrict__ in_il, float* __restrict__ out, int64_t t
             v.y = __fmul_rn(coef, h ? acc[4 * m + 1].y : acc[4 * m + 1].x);
             v.z = __fmul_rn(coef, h ? acc[4 * m + 2].y : acc[4 * m + 2].x);
             v.w = __fmul_rn(coef, h ? acc[4 * m + 3].y : acc[4 * m + 3].x);
-            st_stream4(dst + 4 * m, v);
+            if (HALF) {  // 4 bf16 = 8 bytes at element offset (row * W + 16 cg + 4 m)
+              char* d16 = reinterpret_cast<char*>(out) + (((2 * pair + h) * W + 16 * cg + 4 * m) << 1);
+              *reinterpret_cast<uint2*>(d16) = make_uint2(bf16_pack2(v.x, v.y), bf16_pack2(v.z, v.w));
+            } else {
+              st_stream4(dst + 4 * m, v);
+            }
           }
         }
       }
@@ -1230,7 +1245,34 @@ int sm_count();
 
 template <int MODE>
 static int run_rows(const psx_op* op, const Taps& t, const float* in, const float* eps, float* out,
-                    int64_t planes, float sa, float s1, float w, const float* dsc, cudaStream_t st) {
+                    int64_t planes, float sa, float s1, float w, const float* dsc, cudaStream_t st, bool half = false) {
+  if (half) {  // bf16 inputs: the pipelined Tweedie kernel with the two instantiated tap counts only
+    if (MODE != ROWS_TWEEDIE || (op->W & 7) != 0 || op->W > 512 || (t.k != 40 && t.k != 16))
+      return fail(PSX_ERR_UNSUPPORTED, "blur K1 on a bf16 state: unsupported geometry");
+    const int pitch2 = row_pitch2(op->W + t.k);
+    const size_t smem = kPipeHdr + (size_t)(kPipeRows / 2) * pitch2 * sizeof(float2) +
+                        (size_t)2 * 2 * kPipeRows * op->W * 2;
+    const int64_t total_rows = planes * op->H;
+    const int64_t num_tiles = (total_rows + kPipeRows - 1) / kPipeRows;
+    const float coef = (float)((double)w / (double)sa);
+#define PSX_ROWS_H(KK)                                                                                                   \
+  {                                                                                                                      \
+    static int occ = 0;                                                                                                  \
+    if (!occ) {                                                                                                          \
+      cudaFuncSetAttribute(conv_rows_pipe<ROWS_TWEEDIE, KK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_rows_pipe<ROWS_TWEEDIE, KK, true>, kThreads, smem) !=  \
+              cudaSuccess || occ < 1)                                                                                    \
+        occ = 1;                                                                                                         \
+    }                                                                                                                    \
+    int64_t grid = (int64_t)occ * sm_count();                                                                            \
+    if (grid > num_tiles) grid = num_tiles;                                                                              \
+    conv_rows_pipe<ROWS_TWEEDIE, KK, true><<<(unsigned)grid, kThreads, smem, st>>>(in, eps, out, total_rows, op->W,      \
+                                                                                 pitch2, num_tiles, t, sa, s1, coef, dsc); \
+  }
+    if (t.k == 40) PSX_ROWS_H(40) else PSX_ROWS_H(16)
+#undef PSX_ROWS_H
+    return check_cuda(cudaGetLastError(), "conv_rows_pipe (bf16) launch");
+  }
   if ((op->W & 7) == 0 && op->W <= 512 && !getenv("PSX_NO_PIPE")) {
     const int pitch2 = row_pitch2(op->W + t.k);
     const int arrays = MODE == ROWS_TWEEDIE ? 2 : 1;
@@ -1327,7 +1369,8 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
 // cols16 + rows_il tail of K1 (h1 in ws, row-major)  ->  cot.  Returns -1 when the geometry does not qualify.
 template <int K, int TC>
 static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot, float* err_part, int64_t planes,
-                         int64_t sample0, int64_t obs_repeat, float w, float sa, const float* dsc, cudaStream_t st) {
+                         int64_t sample0, int64_t obs_repeat, float w, float sa, const float* dsc, cudaStream_t st,
+                         bool half = false) {
   const int W = op->W, H = op->H;
   CUtensorMap map;
   const int box_h = H > 256 ? H / 2 : H;  // TMA boxes hold at most 256 rows
@@ -1361,19 +1404,30 @@ static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot
   int64_t grid_r = (int64_t)occ_r * sm_count();
   if (grid_r > tiles_r) grid_r = tiles_r;
   const float coef = (float)((double)w / (double)sa);
-  conv_rows_il<K, ROUNDS><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r, op->ah, coef, dsc);
+  if (half) {  // bf16 cotangent out; same shared-memory footprint, so the occupancy figure carries over
+    static bool attr_h = false;
+    if (!attr_h) {
+      cudaFuncSetAttribute(conv_rows_il<K, ROUNDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_h = true;
+    }
+    conv_rows_il<K, ROUNDS, true><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r,
+                                                                                op->ah, coef, dsc);
+  } else {
+    conv_rows_il<K, ROUNDS><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r, op->ah, coef, dsc);
+  }
   return check_cuda(cudaGetLastError(), "conv_rows_il launch");
 }
 
+// half: x, eps and cot are bf16 arrays (passed through the float* parameters); the intermediates in ws stay fp32.
 int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                        int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
-                       float* x0_out, float* ws, cudaStream_t st) {
+                       float* x0_out, float* ws, cudaStream_t st, bool half) {
   if (x0_out) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: d_x0_out is not produced for blur operators");
   const int64_t planes = L * op->C;
   // cluster-fused single launch for 256 x 256 planes
   if (op->H == kFusedCL * kFusedRB && op->W == kFusedW && op->fh.k == 40 && op->fv.k == 40 && op->ah.k == 40 &&
       op->av.k == 40 && op->fh.lo == op->ah.lo && op->fv.lo == op->av.lo && -op->fv.lo <= kFusedRB &&
-      op->err_parts == op->C * kFusedCL && getenv("PSX_FUSED")) {
+      op->err_parts == op->C * kFusedCL && getenv("PSX_FUSED") && !half) {
     // opt-in: measured 48.0 us vs 46.1 us for the three-launch path at L = 16 (profiles/README.md) -- each CTA runs
     // its nine phases back to back (21 us per CTA, 6 us of it in cluster barriers) and 48 planes need two waves
     // of the 33 clusters that fit, so the single launch does not pay off yet despite its minimal HBM traffic.
@@ -1422,10 +1476,12 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
       if (p > 0)
         if (int rc = check_cuda(cudaStreamWaitEvent(s, op->ev_fork, 0), "K1 fork wait")) return rc;
       const int64_t l0 = p * Lp, off = l0 * op->n;
-      int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x + off, eps + off, ws + off, planes_p, sa, s1, w, dsc, s);
+      const int64_t off_io = half ? off / 2 : off;  // x / eps / cot offsets in float units (n is even for these shapes)
+      int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x + off_io, eps + off_io, ws + off, planes_p, sa, s1, w, dsc, s, half);
       if (rc) return rc;
       float* part = err_part + l0 * op->err_parts;
-#define PSX_TAIL(KK, TCC) run_fast_tail<KK, TCC>(op, y, ws + off, cot + off, part, planes_p, l0, obs_repeat, w, sa, dsc, s)
+#define PSX_TAIL(KK, TCC) \
+  run_fast_tail<KK, TCC>(op, y, ws + off, cot + off_io, part, planes_p, l0, obs_repeat, w, sa, dsc, s, half)
       rc = small ? (kk == 40 ? PSX_TAIL(40, 32) : PSX_TAIL(16, 32)) : (kk == 40 ? PSX_TAIL(40, 16) : PSX_TAIL(16, 16));
 #undef PSX_TAIL
       if (rc < 0) return fail(PSX_ERR_CUDA, "blur K1: could not encode the strip tensor map");
@@ -1437,6 +1493,7 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
     }
     return PSX_OK;
   }
+  if (half) return fail(PSX_ERR_UNSUPPORTED, "blur K1 on a bf16 state needs the strip-kernel geometry (W % 32 == 0, H % 16 == 0, <= 512)");
   int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x, eps, ws, planes, sa, s1, w, dsc, st);
   if (rc) return rc;
   rc = run_cols<true>(op, op->fv, op->av, ws, y, ws, err_part, planes, obs_repeat, st);

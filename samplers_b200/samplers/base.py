@@ -20,7 +20,7 @@ class PosteriorSampler(ABC):
         self.process_group = process_group
         self.philox_seed = philox_seed
         #: DPS / PGDM: torch.bfloat16 stores the sampler state, eps, cotangent and VJP as bf16 (18 instead of 40
-        #: B/element per step; identity / mask / 4x box operators); default float32
+        #: B/element per step; identity / mask / 4x box / separable-blur operators); default float32
         import torch
         self.state_dtype = torch.float32 if state_dtype is None else state_dtype
 

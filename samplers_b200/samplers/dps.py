@@ -67,7 +67,7 @@ class DPSRun:
         if self.net_dtype not in (torch.float32, torch.bfloat16, torch.float16):
             raise TypeError(f"DPSSampler supports float32 / bfloat16 / float16 networks, got {self.net_dtype}")
         # state_dtype = bfloat16 (production mode): x, eps, cot, vjp and the noise are STORED as bf16 and the bf16
-        # kernels run (same fp32 arithmetic, results rounded on store; identity / mask / 4x box operators) -- 18 instead of
+        # kernels run (same fp32 arithmetic, results rounded on store; identity / mask / 4x box / separable-blur operators) -- 18 instead of
         # 40 B/element per step.  draws stay fp32 and are rounded once.
         if state_dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"DPSSampler state is float32 or bfloat16, got {state_dtype}")
@@ -130,7 +130,7 @@ class DPSRun:
         fixed = self._fixed_scale is not None
         if self._bf16:
             _native.dps_pre_bf16(self.op, self.x, eps_flat, self.y, self.obs_repeat, 1.0, 0.0, 1.0, self.cot,
-                                 self.err_part, step_row=self.row)
+                                 self.err_part, step_row=self.row, ws=self.ws)
             v = self._network_vjp(eps, x_in)
             philox = self.philox_seed is not None
             if self._draw_in_graph and not philox:
@@ -257,7 +257,7 @@ class DPSRun:
     def _step_bf16(self, k: int, sc: StepScalars, x_in, eps, eps_flat, z) -> None:
         """The eager timestep on the bf16 state (psx_dps_pre_bf16 / psx_dps_post_bf16)."""
         _native.dps_pre_bf16(self.op, self.x, eps_flat, self.y, self.obs_repeat, sc.sqrt_acp, sc.sqrt_1m_acp,
-                             self.weight, self.cot, self.err_part)
+                             self.weight, self.cot, self.err_part, ws=self.ws)
         v = self._network_vjp(eps, x_in)
         fixed = self._fixed_scale is not None
         philox = (self.philox_seed, k) if (self.philox_seed is not None and z is None) else None

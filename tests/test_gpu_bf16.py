@@ -88,9 +88,34 @@ def test_k1_box_bf16_is_the_rounded_fp32_kernel(shape):
     assert torch.allclose(part16.sum(1), part32.sum(1), rtol=1e-6)
 
 
+@pytest.mark.parametrize("shape,ksize,split", [((3, 256, 256), 61, None), ((3, 256, 256), 61, "2"), ((1, 512, 512), 61, None),
+                                               ((2, 64, 96), 9, None)])
+def test_k1_blur_bf16_is_the_rounded_fp32_kernel(monkeypatch, shape, ksize, split):
+    """Separable blur on a bf16 state: bf16 x_t / eps in, fp32 intermediates, bf16 cotangent out."""
+    from samplers_b200 import _native, operators as P
+    if split:
+        monkeypatch.setenv("PSX_SPLIT", split)
+    else:
+        monkeypatch.delenv("PSX_SPLIT", raising=False)
+    op = P.GaussianBlurOperator(shape, ksize, 3.0 if ksize == 61 else 1.5).to(DEV)
+    nat = op._native_cached(torch.device(DEV))
+    L, n = 4, nat.n
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x, e = (torch.randn(L, n, device=DEV, generator=gen).to(BF) for _ in range(2))
+    y = torch.randn(2, nat.n_y, device=DEV, generator=gen)
+    sa, s1, w = 0.8366600275039673, 0.547722578048706, 400.0
+    ws = torch.empty(nat.workspace_bytes(L) // 4, device=DEV)
+    cot32, part32 = torch.empty(L, n, device=DEV), torch.empty(L, nat.err_parts, device=DEV)
+    _native.dps_pre(nat, x.float(), e.float(), y, 2, sa, s1, w, cot32, part32, ws)
+    cot16, part16 = torch.empty(L, n, device=DEV, dtype=BF), torch.empty(L, nat.err_parts, device=DEV)
+    _native.dps_pre_bf16(nat, x, e, y, 2, sa, s1, w, cot16, part16, ws=ws)
+    assert torch.equal(cot16, cot32.to(BF))
+    assert torch.equal(part16, part32)
+
+
 def test_bf16_k1_rejects_operators_without_a_bf16_kernel():
     from samplers_b200 import _native, operators as P
-    op = P.GaussianBlurOperator((3, 32, 32), 9, 1.5).to(DEV)
+    op = P.MotionBlurOperator((3, 32, 32), kernel_size=9, angle_deg=30.0).to(DEV)
     nat = op._native_cached(torch.device(DEV))
     x = torch.zeros(2, nat.n, device=DEV, dtype=BF)
     with pytest.raises(NotImplementedError):
@@ -100,7 +125,8 @@ def test_bf16_k1_rejects_operators_without_a_bf16_kernel():
 
 @pytest.mark.parametrize("graph", [False, True])
 @pytest.mark.parametrize("net_dtype", [torch.float32, torch.bfloat16])
-def test_sampler_on_a_bf16_state(graph, net_dtype):
+@pytest.mark.parametrize("op_kind", ["mask", "blur"])
+def test_sampler_on_a_bf16_state(graph, net_dtype, op_kind):
     """DPSSampler(state_dtype=bfloat16): the run stays close to the fp32-state run of the same network (stated
     tolerance: bf16 rounding of the stored state, a few 2^-9 per step), eager and graph, fp32 and bf16 networks."""
     from samplers_b200 import operators as P
@@ -110,10 +136,12 @@ def test_sampler_on_a_bf16_state(graph, net_dtype):
     from samplers_b200.samplers import DPSSampler
     from tests._golden import rel_err
     shape = (3, 32, 32)
-    op = P.RandomInpaintingOperator(shape, 0.5, seed=0, flatten=False).to(DEV)
+    op = (P.RandomInpaintingOperator(shape, 0.5, seed=0, flatten=False) if op_kind == "mask"
+          else P.GaussianBlurOperator(shape, 9, 1.5)).to(DEV)
     gen = torch.Generator(device=DEV).manual_seed(1)
     x_true = torch.rand(shape, device=DEV, generator=gen) * 2 - 1
-    y = op.apply(x_true[None])[0] + 0.05 * torch.randn(shape, device=DEV, generator=gen) * (~op.mask).float().to(DEV)
+    keep = (~op.mask).float().to(DEV) if op_kind == "mask" else 1.0
+    y = op.apply(x_true[None])[0] + 0.05 * torch.randn(shape, device=DEV, generator=gen) * keep
     prob = InverseProblem(operator=op, observation=y, noise=GaussianNoise(sigma=0.05))
     torch.manual_seed(1234)
     net = DDPMNetwork.from_config("tiny", device=DEV, torch_dtype=net_dtype)
@@ -144,7 +172,7 @@ def test_bf16_state_needs_a_pointwise_operator():
     from samplers_b200.noise import GaussianNoise
     from samplers_b200.samplers import DPSSampler
     shape = (3, 32, 32)
-    op = P.GaussianBlurOperator(shape, 9, 1.5).to(DEV)
+    op = P.MotionBlurOperator(shape, kernel_size=9, angle_deg=30.0).to(DEV)
     prob = InverseProblem(operator=op, observation=torch.zeros(shape, device=DEV), noise=GaussianNoise(sigma=0.05))
     net = DDPMNetwork.from_config("tiny", device=DEV)
     with pytest.raises(NotImplementedError):

@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 from samplers_b200 import _native, operators as pops  # noqa: E402
 
 SHAPE = (3, 256, 256)  # --size changes H = W
+BF16_OPS = ("identity", "mask", "box4", "gblur61", "gblur13")  # operators with a bf16-state K1
 
 
 def peak():
@@ -110,7 +111,7 @@ def main():
                          part=torch.empty(L, nat.err_parts, device=dev))
                 wsb = nat.workspace_bytes(L)
                 d["ws"] = torch.empty(wsb // 4, device=dev) if wsb else None
-                if kind in ("identity", "mask"):
+                if kind in BF16_OPS:
                     for a, b in (("xh", "x"), ("eh", "eps"), ("vh", "v"), ("ch", "cot"), ("oh", "out")):
                         d[a] = d[b].to(torch.bfloat16)
                 S.append(d)
@@ -132,7 +133,7 @@ def main():
 
             def k12h(i):  # bf16 state: K1 + K2 with in-kernel noise (18 B/elem); identity / mask only
                 d = S[i]
-                _native.dps_pre_bf16(nat, d["xh"], d["eh"], y, L, 0.8, 0.6, 400.0, d["ch"], d["part"])
+                _native.dps_pre_bf16(nat, d["xh"], d["eh"], y, L, 0.8, 0.6, 400.0, d["ch"], d["part"], ws=d["ws"])
                 _native.dps_post_bf16(d["xh"], d["eh"], d["ch"], d["vh"], None, d["part"], nat.err_parts, n, 0.8, 0.6,
                                       0.99, 0.01, 0.05, 1.0, d["oh"], None, philox=(1234, i))
 
@@ -148,7 +149,7 @@ def main():
                 m1, m2 = time_flush(k1, args.iters, flush), time_flush(k2, args.iters, flush)
                 m2p, mz = time_flush(k2p, args.iters, flush), time_flush(zgen, args.iters, flush)
             mh = None
-            if kind in ("identity", "mask"):
+            if kind in BF16_OPS:
                 for i in range(nsets):
                     k12h(i)
                 mh = time_rotate(k12h, nsets, args.iters) if args.mode == "rotate" else time_flush(k12h, args.iters, flush)
