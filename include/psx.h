@@ -41,7 +41,7 @@ extern "C" {
 #define PSX_ERR_UNSUPPORTED 3 /* valid request this build has no kernel for  */
 
 #define PSX_MAX_TAPS 127  /* longest 1-D tap vector of a separable blur       */
-#define PSX_ABI_VERSION 1
+#define PSX_ABI_VERSION 2
 
 /* Operator kinds (psx_op_kind). */
 #define PSX_OP_IDENTITY 0

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libpsx.so")
 
 PSX_OK, PSX_ERR_INVALID, PSX_ERR_CUDA, PSX_ERR_UNSUPPORTED = 0, 1, 2, 3
 OP_IDENTITY, OP_MASK, OP_BOX, OP_SEPBLUR, OP_CONV2D = range(5)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); must list every prototype of include/psx.h
 _f32p, _i64, _vp, _f = C.c_void_p, C.c_int64, C.c_void_p, C.c_float
