@@ -639,9 +639,12 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
     const int64_t yplane = RESIDUAL ? ((pl / C) / obs_repeat * C + pl % C) * (int64_t)H * W : 0;
     float e2 = 0.f;
 
+    const int ntask = (H >> 3) * npair;  // <= ROUNDS * 256; the last round may be partial (H = 144 .. 240)
 #pragma unroll
-    for (int t = 0; t < ROUNDS; ++t) {  // H/8 * 16 tasks = ROUNDS * 256 exactly
-      const int q = threadIdx.x + t * kThreads;
+    for (int t = 0; t < ROUNDS; ++t) {
+      const int q_raw = threadIdx.x + t * kThreads;
+      const bool ok = q_raw < ntask;
+      const int q = ok ? q_raw : ntask - 1;  // every thread computes (uniform control flow); stores are guarded
       const int cp = q % npair, g = q / npair;
       const int gc = c0 + 2 * cp;
       float2 yv[8];
@@ -658,12 +661,12 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
         const int gr = 8 * g + j;
         if (RESIDUAL) {
           float2 r;
-          r.x = __fsub_rn(yv[j].x, acc[j].x);
-          r.y = __fsub_rn(yv[j].y, acc[j].y);
+          r.x = ok ? __fsub_rn(yv[j].x, acc[j].x) : 0.f;
+          r.y = ok ? __fsub_rn(yv[j].y, acc[j].y) : 0.f;
           e2 = fmaf(r.x, r.x, e2);
           e2 = fmaf(r.y, r.y, e2);
-          *reinterpret_cast<float2*>(bufB + (size_t)(gr - ta.lo) * TC + 2 * cp) = r;
-        } else {
+          if (ok) *reinterpret_cast<float2*>(bufB + (size_t)(gr - ta.lo) * TC + 2 * cp) = r;
+        } else if (ok) {
           *reinterpret_cast<float2*>(out + plane + (int64_t)gr * W + gc) = acc[j];
         }
       }
@@ -672,7 +675,9 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
       __syncthreads();
 #pragma unroll
       for (int t = 0; t < ROUNDS; ++t) {
-        const int q = threadIdx.x + t * kThreads;
+        const int q_raw = threadIdx.x + t * kThreads;
+        const bool ok = q_raw < ntask;
+        const int q = ok ? q_raw : ntask - 1;
         const int cp = q % npair, g = q / npair;
         const float* col = bufB + (size_t)(8 * g) * TC + 2 * cp;
         float2 acc[8];
@@ -680,7 +685,7 @@ conv_cols_pipe(const __grid_constant__ CUtensorMap tmap, const float* __restrict
         const int gc = c0 + 2 * cp;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float2*>(out + plane + (int64_t)(8 * g + j) * W + gc) = acc[j];
+          if (ok) *reinterpret_cast<float2*>(out + plane + (int64_t)(8 * g + j) * W + gc) = acc[j];
       }
       const float tot = block_sum(e2, red);  // contains a __syncthreads
       if (threadIdx.x == 0) {
@@ -1323,9 +1328,10 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
     const size_t smem_pipe = kPipeHdr + 2 * stage + (RESIDUAL ? ((size_t)op->H + ta.k) * kColTC * sizeof(float) : 0) +
                              8 * kColTC * sizeof(float);  // 8 slack rows for the unconditional window prefetch
     CUtensorMap map;
-    if ((op->W % kColTC) == 0 && (op->H % 16) == 0 && op->H <= 256 && !getenv("PSX_NO_PIPE") &&
+    // the |r|^2 partials are laid out per strip of op->col_tc columns: the pipelined kernel only runs at that width
+    if ((op->W % kColTC) == 0 && (op->H % 16) == 0 && op->H <= 256 && op->col_tc == kColTC && !getenv("PSX_NO_PIPE") &&
         make_strip_map(&map, in, planes * op->H, op->W, kColTC, op->H)) {
-      const int rounds = (op->H >> 3) * (kColTC >> 1) / kThreads;  // H % 16 == 0  =>  exact
+      const int rounds = ((op->H >> 3) * (kColTC >> 1) + kThreads - 1) / kThreads;  // the last round may be partial
       const int strips = op->W / kColTC;
       const int64_t num_tiles = planes * strips;
 #define PSX_COLS(R, KK)                                                                                      \
