@@ -139,3 +139,78 @@ def test_random_geometries(monkeypatch, kind, env):
         r = y - nat.apply(x0)
         assert rel_err(cot.cpu(), (nat.adjoint(r.contiguous()) * wgt / sa).cpu()) < 3e-6, tag
         assert rel_err(part.sum(1).cpu(), r.double().square().sum(1).float().cpu()) < 1e-5, tag
+
+
+def test_random_sizes_elementwise_family():
+    """K2 (tensor noise / none / fixed scale / Philox-vs-tensor), the final Tweedie with moments, bridge update,
+    lincomb3, eps-DDIM, stochastic resample, gather / scatter at ~60 random (L, n) incl. n % 4 != 0, against the
+    oracle on the CPU (the schedule scalars must come from CPU torch ops, as in the reference's CPU path and the
+    host planner: sqrt of a 0-dim tensor differs between CPU and CUDA torch by an ulp for ~1 % of the timesteps)."""
+    from oracle import dps as odps
+    from oracle import resample as ors
+    from oracle.schedule import ddpm_linear_alphas_cumprod, padded_clipped_acp
+    from samplers_b200 import _native
+    from samplers_b200.samplers.resample import ddim_eps_scalars, resample_scalars
+    acp = padded_clipped_acp(ddpm_linear_alphas_cumprod())
+    rng = random.Random(7)
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    for _ in range(60):
+        L = rng.randint(1, 7)
+        n = rng.choice([1, 2, 3, 5, 17, 64, 100, 1001, 4096, 12289, 3 * 64 * 64, rng.randint(1, 30000)])
+        t = rng.randint(2, 999)
+        tp = rng.randint(1, t - 1)
+        a_t = acp[t]
+        sa, s1 = float(a_t ** 0.5), float((1 - a_t) ** 0.5)
+        x, e, d, v, z = (torch.randn(L, n, device=DEV, generator=gen) for _ in range(5))
+        xc, ec, dc, vc, zc = (q.cpu() for q in (x, e, d, v, z))
+        tag = f"L={L} n={n} t={t}"
+        # ---- K2
+        parts = rng.choice([1, 3, 64])
+        part = torch.rand(L, parts, device=DEV, generator=gen) * n
+        c_ell, c_s, std, gamma = 0.9 + 0.1 * rng.random(), 0.05 * rng.random(), 0.3 * rng.random(), 0.5 + rng.random()
+        out, err = torch.empty(L, n, device=DEV), torch.empty(L, device=DEV)
+        _native.dps_post(x, e, d, v, z, part, parts, n, sa, s1, c_ell, c_s, std, gamma, out, err)
+        ref, _ = odps.k2_reference(xc, ec, dc, vc, zc, part.sum(1).cpu(), acp_t=a_t, c_ell=torch.tensor(c_ell),
+                                   c_s=torch.tensor(c_s), std=torch.tensor(std), gamma=gamma)
+        assert rel_err(out.cpu(), ref) < 2e-6, tag
+        assert rel_err(err.cpu(), part.sum(1).sqrt().cpu()) < 1e-6, tag
+        _native.dps_post(x, e, d, v, None, part, parts, n, sa, s1, c_ell, c_s, 0.0, gamma, out, None)
+        ref0, _ = odps.k2_reference(xc, ec, dc, vc, None, part.sum(1).cpu(), acp_t=a_t, c_ell=torch.tensor(c_ell),
+                                    c_s=torch.tensor(c_s), std=torch.tensor(0.0), gamma=gamma)
+        assert rel_err(out.cpu(), ref0) < 2e-6, tag
+        zp = torch.empty(L, n, device=DEV)
+        _native.philox_normal(zp, 5, t)
+        a, b = torch.empty(L, n, device=DEV), torch.empty(L, n, device=DEV)
+        _native.dps_post(x, e, d, v, zp, None, 0, n, sa, s1, c_ell, c_s, std, gamma, a, None)      # fixed scale
+        _native.dps_post_philox(x, e, d, v, None, 0, n, sa, s1, c_ell, c_s, std, gamma, 5, t, b, None)
+        assert torch.equal(a, b), tag
+        # ---- final Tweedie + moments
+        x0, tot, tsq = torch.empty(L, n, device=DEV), torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+        _native.tweedie(x, e, sa, s1, x0, tot, tsq)
+        want = odps.tweedie_x0(xc, ec, a_t).to(DEV)
+        assert torch.equal(x0, want), tag
+        assert rel_err(tot.cpu(), want.double().sum(0).float().cpu()) < 1e-6, tag
+        assert rel_err(tsq.cpu(), want.double().square().sum(0).float().cpu()) < 1e-6, tag
+        # ---- bridge update / lincomb3
+        _native.bridge_update(x, e, z, d, sa, s1, c_ell, c_s, std, -1.0, out)
+        assert rel_err(out.cpu(), (c_ell * x + c_s * want + std * z - d).cpu()) < 2e-6, tag
+        _native.lincomb3(x, 0.3, e, -1.7, d, 2.0, out)
+        assert rel_err(out.cpu(), (0.3 * x - 1.7 * e + 2.0 * d).cpu()) < 2e-6, tag
+        # ---- eps-DDIM / stochastic resample
+        prev, pseudo = torch.empty_like(x), torch.empty_like(x)
+        _native.ddim_eps_step(x, e, z, ddim_eps_scalars(acp, t, tp, 0.7), prev, None, pseudo)
+        rp, _, rps = ors.ddim_eps_step(xc, ec, acp, t, tp, 0.7, zc)
+        assert rel_err(prev.cpu(), rp) < 2e-6 and rel_err(pseudo.cpu(), rps) < 2e-6, tag
+        sig = ors.compute_sigma(40.0, acp[t], acp[tp])
+        _native.stochastic_resample(x, e, z, *resample_scalars(acp, t, tp, 40.0), out)
+        assert rel_err(out.cpu(), ors.stochastic_resample(xc, ec, acp[tp], sig, zc)) < 2e-6, tag
+        # ---- gather / scatter
+        m = rng.randint(0, n)
+        idx = torch.sort(torch.randperm(n, generator=torch.Generator().manual_seed(n))[:m]).values.to(DEV)
+        if m:
+            gth = _native.gather(x, idx, False, n)
+            assert torch.equal(gth, x.index_select(1, idx)), tag
+            sct = _native.gather(gth, idx, True, n)
+            chk = torch.zeros(L, n, device=DEV)
+            chk[:, idx] = gth
+            assert torch.equal(sct, chk), tag
