@@ -214,3 +214,64 @@ def test_random_sizes_elementwise_family():
             chk = torch.zeros(L, n, device=DEV)
             chk[:, idx] = gth
             assert torch.equal(sct, chk), tag
+
+
+def test_random_sampler_configurations_one_step():
+    """DPSRun.step against the oracle's literal autograd step (CPU) for ~25 random (operator, batch shape,
+    reconstructions, noise model, eta, gamma, timestep) -- the observation tiling, the likelihood weight and the bridge
+    coefficients all vary."""
+    from oracle import dps as odps
+    from oracle.schedule import ddpm_linear_alphas_cumprod, leading_timesteps_ascending, padded_clipped_acp
+    from oracle.tiny_net import TinyEpsNet
+    from samplers_b200 import operators as P
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.noise import GaussianNoise, PoissonNoise
+    from samplers_b200.samplers import DPSSampler
+    from tests.test_gpu_fullsize import _network
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    acp = padded_clipped_acp(ddpm_linear_alphas_cumprod())
+    rng = random.Random(11)
+    for case in range(25):
+        steps = rng.choice([10, 20, 50])
+        ts = leading_timesteps_ascending(steps)
+        shape = (3, 8 * rng.randint(1, 5), 8 * rng.randint(1, 5))
+        kind = rng.choice(["identity", "mask", "box", "blur", "motion"])
+        extra = {"identity": None, "mask": rng.random(), "box": rng.choice([2, 4]), "blur": (rng.choice([5, 9]), 1.2),
+                 "motion": (5, rng.uniform(0, 180))}[kind]
+        op, ora, keep = _build(kind, shape, extra)
+        batch = rng.choice([(), (2,), (3,)])
+        R = rng.choice([1, 2, 3])
+        nb = 1
+        for b in batch:
+            nb *= b
+        L = nb * R
+        noise_kind, param = rng.choice([("gaussian", 0.05), ("gaussian", 0.2), ("poisson", 4.0)])
+        eta, gamma = rng.choice([0.0, 0.5, 1.0]), rng.choice([0.05, 0.3, 1.0])
+        g = torch.Generator().manual_seed(case)
+        y = torch.randn(*batch, *ora.y_shape if hasattr(ora, "y_shape") else shape, generator=g)
+        if keep is not None:
+            y = y * keep
+        net = _network(acp, ts)
+        cpu_core = TinyEpsNet(channels=3)                      # same deterministic weights as net.core
+        x_init = torch.randn(L, *shape, generator=g)
+        z = torch.randn(L, *shape, generator=g)
+        noise = GaussianNoise(sigma=param) if noise_kind == "gaussian" else PoissonNoise(rate=param)
+        prob = InverseProblem(operator=op.to(DEV), observation=y.to(DEV), noise=noise)
+        s = DPSSampler(net)
+        s.draw = lambda shape_, device, dtype: x_init.to(device).view(shape_)
+        run = s.prepare(prob, num_sampling_steps=steps, num_reconstructions=R, gamma=gamma, eta=eta)
+        try:
+            k = rng.randint(0, run.num_steps - 1)
+            sc = run.plan[k]
+            run.step(k, z=z.to(DEV))
+            # the oracle sees the observation tiled over reconstructions (BatchView.repeat_observation)
+            y_l = y.reshape(nb, *y.shape[len(batch):]).repeat_interleave(R, dim=0)
+            ref = odps.dps_step_autograd(lambda xx, tt: cpu_core(xx, int(tt)), x_init, t=sc.t, t_prev=sc.t_prev,
+                                         s=run.timesteps[0], acp=acp, op=ora, y=y_l, noise_kind=noise_kind,
+                                         noise_param=torch.tensor(param), gamma=gamma, eta=eta, z=z)
+            tag = f"case {case}: {kind} {shape} batch={batch} R={R} {noise_kind} eta={eta} gamma={gamma} k={k}"
+            assert rel_err(run.x.view(L, *shape).cpu(), ref["x_next"]) < 2e-5, tag
+            assert rel_err(run.err.cpu(), ref["err"]) < 1e-5, tag
+        finally:
+            s.release()
