@@ -275,3 +275,52 @@ def test_random_sampler_configurations_one_step():
             assert rel_err(run.err.cpu(), ref["err"]) < 1e-5, tag
         finally:
             s.release()
+
+
+def test_random_geometries_latent_sampler_autograd_nodes():
+    """The PSLD data-term node (lik, x_eff) and ReSample's residual node (norm / mse), forward and backward, against
+    the oracle's torch expressions through autograd, for ~30 random operators / shapes / batch sizes."""
+    from samplers_b200.samplers.psld import _PsldDataTerm
+    from samplers_b200.samplers.resample import _ResidualTerm
+    torch.backends.cudnn.allow_tf32 = False
+    rng = random.Random(5)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    for case in range(30):
+        kind = rng.choice(["identity", "mask", "box", "blur", "motion"])
+        c, h, w, L, extra = _cases(kind, 1, seed=100 + case)[0]
+        shape = (c, h, w)
+        op, ora, keep = _build(kind, shape, extra)
+        op = op.to(DEV)
+        for name in ("taps_h", "taps_v", "kernel2d"):
+            if hasattr(ora, name):
+                setattr(ora, name, getattr(ora, name).to(DEV))
+        nat = op._native_cached(torch.device(DEV))
+        tag = f"case {case}: {kind} {shape} L={L}"
+        x0 = torch.randn(L, *shape, device=DEV, generator=gen)
+        y = torch.randn(1, nat.n_y, device=DEV, generator=gen)
+        if keep is not None:
+            y = y * keep.reshape(1, -1).to(DEV)
+        cx = torch.randn(L, nat.n, device=DEV, generator=gen)
+        wsb = nat.workspace_bytes(L)
+        ws = torch.empty(wsb // 4, device=DEV) if wsb else None
+        zeros_y = torch.zeros(1, nat.n_y, device=DEV)
+        # oracle expressions (psld.py:129-136, resample_kernels.py:27,48)
+        xo = x0.clone().requires_grad_()
+        hx = ora.apply(xo).reshape(L, -1)
+        r_o = y - hx
+        lik_o = torch.norm(r_o)
+        aty = ora.adjoint(y.expand(L, -1).reshape(L, *getattr(ora, "y_shape", shape))).reshape(L, -1)
+        xeff_o = aty + xo.reshape(L, -1) - ora.adjoint(hx.reshape(L, *getattr(ora, "y_shape", shape))).reshape(L, -1)
+        (g_o,) = torch.autograd.grad(0.3 * lik_o + (xeff_o * cx).sum() + 2.0 * r_o.square().mean(), xo)
+        # product nodes
+        xd = x0.reshape(L, -1).clone().requires_grad_()
+        lik, xeff = _PsldDataTerm.apply(xd, nat, y, L, ws, zeros_y)
+        mse = _ResidualTerm.apply(xd, nat, y, L, ws, "mse")
+        nrm = _ResidualTerm.apply(xd, nat, y, L, ws, "norm")
+        (g_d,) = torch.autograd.grad(0.3 * lik + (xeff * cx).sum() + 2.0 * mse, xd)
+        scale = max(1.0, float(lik_o.detach()))
+        assert abs(float(lik.detach()) - float(lik_o.detach())) < 1e-5 * scale, tag
+        assert abs(float(nrm.detach()) - float(lik_o.detach())) < 1e-5 * scale, tag
+        assert abs(float(mse.detach()) - float(r_o.detach().square().mean())) < 1e-5 * max(1.0, float(mse.detach())), tag
+        assert rel_err(xeff.detach().cpu(), xeff_o.detach().cpu()) < 5e-6, tag
+        assert rel_err(g_d.cpu(), g_o.reshape(L, -1).cpu()) < 2e-5, tag
