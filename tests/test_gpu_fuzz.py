@@ -324,3 +324,55 @@ def test_random_geometries_latent_sampler_autograd_nodes():
         assert abs(float(mse.detach()) - float(r_o.detach().square().mean())) < 1e-5 * max(1.0, float(mse.detach())), tag
         assert rel_err(xeff.detach().cpu(), xeff_o.detach().cpu()) < 5e-6, tag
         assert rel_err(g_d.cpu(), g_o.reshape(L, -1).cpu()) < 2e-5, tag
+
+
+def test_random_geometries_bf16_state_is_the_rounded_fp32_path():
+    """K_bf16(v) == bf16_rn(K_fp32(float(v))) for ~40 random operators / shapes (identity, mask, 4x box, separable blur
+    incl. planes up to 512 and forced two-group schedules), K1 and K2."""
+    import os
+    from samplers_b200 import _native, operators as P
+    BF = torch.bfloat16
+    rng = random.Random(21)
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    for case in range(40):
+        kind = rng.choice(["identity", "mask", "box", "blur", "blur"])
+        c, L = rng.choice([1, 2, 3]), rng.randint(1, 6)
+        if kind == "box":
+            h, w = 4 * rng.randint(1, 20), 4 * rng.randint(1, 20)
+            op = P.BoxDownsampleOperator((c, h, w), 4)
+        elif kind == "blur":
+            h, w = 16 * rng.randint(1, 32), 32 * rng.randint(1, 16)
+            if (h > 256 or w > 256) and h % 32:
+                h += 16
+            op = P.GaussianBlurOperator((c, h, w), *rng.choice([(61, 3.0), (9, 1.5), (13, 1.5)]))
+        else:
+            h, w = rng.randint(1, 50), rng.randint(1, 50)
+            op = P.IdentityOperator((c, h, w)) if kind == "identity" else P.RandomInpaintingOperator((c, h, w), 0.6, seed=case, flatten=False)
+        op = op.to(DEV)
+        nat = op._native_cached(torch.device(DEV))
+        n = nat.n
+        tag = f"case {case}: {kind} {(c, h, w)} L={L}"
+        os.environ.pop("PSX_SPLIT", None)
+        if kind == "blur" and L % 2 == 0 and L >= 4 and rng.random() < 0.5:
+            os.environ["PSX_SPLIT"] = "2"
+        try:
+            x, e, v, z = (torch.randn(L, n, device=DEV, generator=gen).to(BF) for _ in range(4))
+            y = torch.randn(1, nat.n_y, device=DEV, generator=gen)
+            if kind == "mask":
+                y = y * (~op.mask).float().reshape(1, -1).to(DEV)
+            sa, s1, wgt = 0.8366600275039673, 0.547722578048706, 400.0
+            wsb = nat.workspace_bytes(L)
+            ws = torch.empty(wsb // 4, device=DEV) if wsb else None
+            c32, p32 = torch.empty(L, n, device=DEV), torch.empty(L, nat.err_parts, device=DEV)
+            c16, p16 = torch.empty(L, n, device=DEV, dtype=BF), torch.empty(L, nat.err_parts, device=DEV)
+            _native.dps_pre(nat, x.float(), e.float(), y, L, sa, s1, wgt, c32, p32, ws)
+            _native.dps_pre_bf16(nat, x, e, y, L, sa, s1, wgt, c16, p16, ws=ws)
+            assert torch.equal(c16, c32.to(BF)), tag
+            assert torch.allclose(p16.sum(1), p32.sum(1), rtol=1e-6), tag
+            o32, o16 = torch.empty(L, n, device=DEV), torch.empty(L, n, device=DEV, dtype=BF)
+            _native.dps_post(x.float(), e.float(), c16.float(), v.float(), z.float(), p16, nat.err_parts, n, sa, s1, 0.97,
+                             0.02, 0.1, 1.3, o32, None)
+            _native.dps_post_bf16(x, e, c16, v, z, p16, nat.err_parts, n, sa, s1, 0.97, 0.02, 0.1, 1.3, o16, None)
+            assert torch.equal(o16, o32.to(BF)), tag
+        finally:
+            os.environ.pop("PSX_SPLIT", None)
