@@ -69,6 +69,10 @@ def _build(kind, shape, extra):
             adjoint = apply
 
         return op, Dense(), keep
+    if kind == "maskflat":   # the reference's working inpainting form: gathered (L, m) observations
+        mask = torch.rand(shape, generator=torch.Generator().manual_seed(int(extra * 1000))) < 0.3 + 0.5 * extra
+        mask.view(-1)[0] = False                                   # at least one kept pixel
+        return P.InpaintingOperator(shape, mask, flatten=True), oops.OracleMaskGather(shape, mask), None
     if kind == "box":
         return P.BoxDownsampleOperator(shape, extra), oops.OracleBoxDownsample(shape, extra), None
     if kind == "blur":
@@ -217,7 +221,7 @@ def test_random_sizes_elementwise_family():
 
 
 def test_random_sampler_configurations_one_step():
-    """DPSRun.step against the oracle's literal autograd step (CPU) for ~25 random (operator, batch shape,
+    """DPSRun.step against the oracle's literal autograd step (CPU) for ~36 random (operator, batch shape,
     reconstructions, noise model, eta, gamma, timestep) -- the observation tiling, the likelihood weight and the bridge
     coefficients all vary."""
     from oracle import dps as odps
@@ -232,13 +236,13 @@ def test_random_sampler_configurations_one_step():
     torch.backends.cuda.matmul.allow_tf32 = False
     acp = padded_clipped_acp(ddpm_linear_alphas_cumprod())
     rng = random.Random(11)
-    for case in range(25):
+    for case in range(36):
         steps = rng.choice([10, 20, 50])
         ts = leading_timesteps_ascending(steps)
         shape = (3, 8 * rng.randint(1, 5), 8 * rng.randint(1, 5))
-        kind = rng.choice(["identity", "mask", "box", "blur", "motion"])
-        extra = {"identity": None, "mask": rng.random(), "box": rng.choice([2, 4]), "blur": (rng.choice([5, 9]), 1.2),
-                 "motion": (5, rng.uniform(0, 180))}[kind]
+        kind = rng.choice(["identity", "mask", "maskflat", "box", "blur", "motion"])
+        extra = {"identity": None, "mask": rng.random(), "maskflat": rng.random(), "box": rng.choice([2, 4]),
+                 "blur": (rng.choice([5, 9]), 1.2), "motion": (5, rng.uniform(0, 180))}[kind]
         op, ora, keep = _build(kind, shape, extra)
         batch = rng.choice([(), (2,), (3,)])
         R = rng.choice([1, 2, 3])
