@@ -380,3 +380,45 @@ def test_random_geometries_bf16_state_is_the_rounded_fp32_path():
             assert torch.equal(o16, o32.to(BF)), tag
         finally:
             os.environ.pop("PSX_SPLIT", None)
+
+
+def test_random_pgdm_runs():
+    """PGDMSampler (K1 with weight 2c, fixed-scale K2) against the oracle's whole PGDM run (CPU) for ~12 random
+    (operator with a pseudo-inverse, shape, reconstructions, guidance weight, eta); eager and graph."""
+    from oracle import pgdm as opg
+    from oracle.schedule import ddpm_linear_alphas_cumprod, leading_timesteps_ascending, padded_clipped_acp
+    from oracle.tiny_net import TinyEpsNet
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.noise import GaussianNoise
+    from samplers_b200.samplers import PGDMSampler
+    from tests.test_gpu_fullsize import _network
+    torch.backends.cudnn.allow_tf32 = False
+    acp = padded_clipped_acp(ddpm_linear_alphas_cumprod())
+    rng = random.Random(13)
+    for case in range(12):
+        steps = rng.choice([6, 8, 12])
+        ts = leading_timesteps_ascending(steps)
+        kind = rng.choice(["identity", "maskflat", "box"])
+        shape = (3, 8 * rng.randint(1, 4), 8 * rng.randint(1, 4))
+        extra = {"identity": None, "maskflat": rng.random(), "box": rng.choice([2, 4])}[kind]
+        op, ora, _ = _build(kind, shape, extra)
+        R = rng.choice([1, 2, 3])
+        gw, eta = rng.choice([0.2, 0.5, 1.0]), rng.choice([0.0, 1.0])
+        g = torch.Generator().manual_seed(200 + case)
+        y = torch.randn(*ora.y_shape, generator=g)
+        draws = [torch.randn(R, *shape, generator=g) for _ in range(steps)]
+        net = _network(acp, ts)
+        cpu_core = TinyEpsNet(channels=3)
+        it = iter(draws)
+        ref = opg.pgdm_sample(lambda xx, tt: cpu_core(xx, int(tt)), acp=acp, timesteps=ts.tolist(), op=ora,
+                              y_flat=y.reshape(1, *ora.y_shape).expand(R, *ora.y_shape), leading=R, guidance_weight=gw,
+                              eta=eta, draw=lambda sh: next(it))
+        prob = InverseProblem(operator=op.to(DEV), observation=y.to(DEV), noise=GaussianNoise(sigma=0.05))
+        it2 = iter(draws)
+        s = PGDMSampler(net)
+        s.draw = lambda sh, device, dtype: next(it2).to(device)
+        out = s(prob, num_sampling_steps=steps, num_reconstructions=R, guidance_weight=gw, eta=eta,
+                keep_reconstruction_dim=True)
+        tag = f"case {case}: {kind} {shape} R={R} gw={gw} eta={eta} steps={steps}"
+        assert out.shape == (R, *shape), tag
+        assert rel_err(out.cpu(), ref) < 1e-4, tag
