@@ -422,3 +422,80 @@ def test_random_pgdm_runs():
         tag = f"case {case}: {kind} {shape} R={R} gw={gw} eta={eta} steps={steps}"
         assert out.shape == (R, *shape), tag
         assert rel_err(out.cpu(), ref) < 1e-4, tag
+
+
+def test_random_psld_runs():
+    """PSLDSampler against the oracle's whole PSLD run (CPU) for ~8 random (operator, shape, batch, reconstructions,
+    omega, gamma, eta) with the tiny deterministic latent network."""
+    from oracle import psld as ops_
+    from oracle.schedule import ddpm_linear_alphas_cumprod, leading_timesteps_ascending, padded_clipped_acp
+    from oracle.tiny_latent_net import TinyLatentCore
+    from samplers_b200.inverse_problem import InverseProblem
+    from samplers_b200.networks.base import LatentEpsilonNetwork
+    from samplers_b200.noise import GaussianNoise
+    from samplers_b200.samplers import PSLDSampler
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    acp = padded_clipped_acp(ddpm_linear_alphas_cumprod())
+
+    class Net(LatentEpsilonNetwork):
+        def __init__(self, ts):
+            super().__init__(alphas_cumprod=acp)
+            self.core, self._ts = TinyLatentCore(channels=3), ts
+
+        def forward(self, x, t):
+            return self.core.eps(x, int(t))
+
+        @classmethod
+        def from_pretrained(cls, *a, **k):
+            raise NotImplementedError
+
+        def set_sampling_parameters(self, num_sampling_steps, batch_size=1, num_reconstructions=1):
+            self._batch_size, self._num_sampling_steps = batch_size, num_sampling_steps
+            self._num_reconstructions = num_reconstructions
+            self.register_buffer("timesteps", self._ts.to(self.alphas_cumprod.device))
+
+        @property
+        def is_condition_initialized(self):
+            return True
+
+        def get_latent_shape(self, x_shape):
+            return (4, x_shape[1] // 2, x_shape[2] // 2)
+
+        def _decode(self, z, *, differentiable=False):
+            return self.core.decode(z)
+
+        def _encode(self, x, *, differentiable=False):
+            return self.core.encode(x)
+
+    rng = random.Random(17)
+    for case in range(8):
+        steps = rng.choice([5, 6, 8])
+        ts = leading_timesteps_ascending(steps)
+        kind = rng.choice(["identity", "box", "blur"])
+        shape = (3, 8 * rng.randint(1, 3), 8 * rng.randint(1, 3))
+        extra = {"identity": None, "box": 2, "blur": (rng.choice([5, 9]), 1.2)}[kind]
+        op, ora, _ = _build(kind, shape, extra)
+        batch = rng.choice([(), (2,)])
+        R = rng.choice([1, 2])
+        nb = 2 if batch else 1
+        L = nb * R
+        omega, gamma, eta = rng.choice([0.1, 0.3]), rng.choice([0.5, 1.0]), rng.choice([0.0, 0.5, 1.0])
+        g = torch.Generator().manual_seed(300 + case)
+        y = torch.randn(*batch, *ora.y_shape, generator=g)
+        lat = (4, shape[1] // 2, shape[2] // 2)
+        draws = [torch.randn(L, *lat, generator=g) for _ in range(steps)]
+        core = TinyLatentCore(channels=3)
+        it = iter(draws)
+        y_flat = y.reshape(nb, *ora.y_shape).repeat_interleave(R, dim=0)
+        ref = ops_.psld_sample(core.eps, core.decode, core.encode, acp=acp, timesteps=ts.tolist(), op=ora, y_flat=y_flat,
+                               latent_shape=lat, leading=L, omega=omega, gamma=gamma, eta=eta, draw=lambda sh: next(it))
+        net = Net(ts).to(DEV)
+        prob = InverseProblem(operator=op.to(DEV), observation=y.to(DEV), noise=GaussianNoise(sigma=0.05))
+        it2 = iter(draws)
+        s = PSLDSampler(net)
+        s.draw = lambda sh, device, dtype: next(it2).to(device)
+        out = s(prob, num_sampling_steps=steps, num_reconstructions=R, gamma=gamma, omega=omega, eta=eta)
+        tag = f"case {case}: {kind} {shape} batch={batch} R={R} omega={omega} gamma={gamma} eta={eta}"
+        assert out.shape == (*batch, R, *shape), tag
+        assert rel_err(out.reshape(L, *shape).cpu(), ref) < 2e-4, tag
