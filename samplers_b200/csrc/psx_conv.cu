@@ -1,7 +1,7 @@
 // psx_conv.cu -- shared-memory-tiled convolution kernels (sm_100a):
 //   separable blur  A = V . H  (rows then columns), adjoint = H^T . V^T,
 //   depthwise 2-D correlation with an arbitrary PSF as row or column segments (motion blur),
-//   and K1 (psx_dps_pre) built from them.  Default K1 for a separable blur (W % 32 == 0, H % 16 == 0, both <= 256):
+//   and K1 (psx_dps_pre) built from them.  Default K1 for a separable blur (W % 32 == 0, H % 16 == 0, both <= 512):
 //     conv_rows_pipe<TWEEDIE> : x0 = (x_t - s1 eps)/sa on the fly, h1 = H x0              -> workspace
 //     conv_cols16             : r = y - V h1, |r|^2 partials, h2 = V^T r (strip-local)     -> workspace, in place,
 //                               row-pair interleaved
@@ -574,7 +574,7 @@ conv_rows_pipe(const float* __restrict__ in, const float* __restrict__ eps, floa
 // ---- columns.  Tile = one 32-column strip (all H rows) of one plane, fetched by ONE 2-D TMA box load
 // (cp.async.bulk.tensor.2d, box = 32 x H) into a stage whose zero halo rows persist across tiles; a
 // lane owns a column pair and 8 output rows.  r lives in one extra buffer; y is prefetched straight from
-// global (it is shared by all samples: L2 hits).  Needs W % 32 == 0, H % 8 == 0, H <= 256.
+// global (it is shared by all samples: L2 hits).  Needs W % 32 == 0, H % 16 == 0, H <= 256 (partial last round guarded).
 constexpr int kColTC = 32;
 
 template <bool RESIDUAL, int ROUNDS, int K>  // ROUNDS = H / 8 * 16 / kThreads: tasks per thread and pass (1 or 2)
@@ -863,7 +863,7 @@ conv_cols16(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ 
 
 // ---- last row pass on row-pair-interleaved input: the TMA bulk copies land directly in the compute
 // layout (no conversion pass, no second barrier), 3 stages, 16 outputs x 2 rows per task, 128 threads.
-// Needs W % 16 == 0, W <= 256, (planes * H) % 2 == 0.
+// Needs W % 16 == 0, W <= 256 * ROUNDS (ROUNDS task rounds per tile), (planes * H) % 2 == 0.
 constexpr int kIlThreads = 128;
 constexpr int kIlStages = 3;
 
