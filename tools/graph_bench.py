@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--op", default="identity")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--net-dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--state-dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--philox", type=int, default=0)
     a = ap.parse_args()
     from samplers_b200 import operators as P
     from samplers_b200.inverse_problem import InverseProblem
@@ -29,15 +32,17 @@ def main():
     from samplers_b200.samplers import DPSSampler
     dev = "cuda:0"
     shape = (3, a.size, a.size)
-    net = DDPMNetwork.from_config(a.config, device=dev)
+    net = DDPMNetwork.from_config(a.config, device=dev, torch_dtype=torch.bfloat16 if a.net_dtype == "bf16" else None)
     op = (P.IdentityOperator(shape) if a.op == "identity" else P.GaussianBlurOperator(shape)).to(dev)
     gen = torch.Generator(device=dev).manual_seed(0)
     x = torch.rand(shape, device=dev, generator=gen) * 2 - 1
     y = op.apply(x[None])[0] + 0.05 * torch.randn(op.y_shape, device=dev, generator=gen)
     prob = InverseProblem(operator=op, observation=y, noise=GaussianNoise(sigma=0.05))
-    out = {"config": a.config, "shape": list(shape), "batch": a.batch, "operator": a.op, "steps": a.steps}
+    out = {"config": a.config, "shape": list(shape), "batch": a.batch, "operator": a.op, "steps": a.steps,
+           "net_dtype": a.net_dtype, "state_dtype": a.state_dtype, "philox": bool(a.philox)}
     for mode in ("eager", "graph"):
-        s = DPSSampler(net, cuda_graph=mode == "graph")
+        s = DPSSampler(net, cuda_graph=mode == "graph", philox_seed=0 if a.philox else None,
+                       state_dtype=torch.bfloat16 if a.state_dtype == "bf16" else None)
         run = s.prepare(prob, num_sampling_steps=1000, num_reconstructions=a.batch)
         try:
             if mode == "graph":

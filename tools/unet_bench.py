@@ -12,15 +12,17 @@ sys.path.insert(0, ROOT)
 from samplers_b200.networks.unet2d import CELEBAHQ_256, UNet2DModel  # noqa: E402
 
 
-def run(name, channels_last, matmul_tf32, autocast=None, batch=16, iters=5):
+def run(name, channels_last, matmul_tf32, autocast=None, batch=16, iters=5, param_dtype=None):
     torch.backends.cuda.matmul.allow_tf32 = matmul_tf32
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)
     net = UNet2DModel(**CELEBAHQ_256).cuda().eval().requires_grad_(False)
+    if param_dtype is not None:
+        net = net.to(param_dtype)
     if channels_last:
         net = net.to(memory_format=torch.channels_last)
-    x = torch.randn(batch, 3, 256, 256, device="cuda")
-    g = torch.randn(batch, 3, 256, 256, device="cuda")
+    x = torch.randn(batch, 3, 256, 256, device="cuda", dtype=param_dtype or torch.float32)
+    g = torch.randn(batch, 3, 256, 256, device="cuda", dtype=param_dtype or torch.float32)
 
     def step():
         xi = x.detach().requires_grad_()
@@ -54,3 +56,6 @@ if __name__ == "__main__":
     run("fp32 channels_last", True, False)
     run("fp32 channels_last + matmul tf32", True, True)
     run("bf16 autocast channels_last (info)", True, True, torch.bfloat16)
+    run("bf16 autocast NCHW (info)", False, True, torch.bfloat16)
+    run("bf16 weights NCHW (info)", False, True, param_dtype=torch.bfloat16)
+    run("bf16 weights channels_last (info)", True, True, param_dtype=torch.bfloat16)
