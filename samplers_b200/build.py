@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpsx.so")
-SOURCES = ["psx_api.cu", "psx_pointwise.cu", "psx_conv.cu", "psx_io.cu", "psx_half.cu"]
+SOURCES = ["psx_api.cu", "psx_pointwise.cu", "psx_conv.cu", "psx_io.cu", "psx_half.cu", "psx_tcblur.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--shared", "-Xptxas", "-v",

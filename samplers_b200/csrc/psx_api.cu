@@ -145,6 +145,7 @@ PSX_API int psx_op_create_sepblur(int C, int H, int W, const float* h_taps_h, in
   if (!rc) rc = make_taps(h_taps_v, kv, true, &op->av);
   if (!rc) rc = sepblur_plan(op);
   if (rc) { delete op; return rc; }
+  tcblur_plan(op);
   // Side streams / events for the split K1 (launch_pre_sepblur).  Without a device (host-only use of the
   // descriptor) or on any failure the descriptor simply has none and K1 runs on the caller's stream alone.
   op->aux_mu = new (std::nothrow) std::mutex();
@@ -278,6 +279,7 @@ PSX_API int psx_op_destroy(psx_op* op) {
     cudaEventDestroy(op->ev_join[i]);
   }
   if (op->ev_fork) cudaEventDestroy(op->ev_fork);
+  tcblur_release(op);
   delete op->aux_mu;
   delete op;
   return PSX_OK;

@@ -72,6 +72,10 @@ struct psx_op {
   cudaStream_t aux_stream[3];
   cudaEvent_t ev_fork, ev_join[3];
   std::mutex* aux_mu;         // serialises the fork/join sequence of concurrent callers
+  // sepblur on the tensor cores (psx_tcblur.cu): 0 = not applicable, else the zero padding (K window = 64 + 2 pad)
+  int tc_pad;
+  uint8_t* d_tc_img;          // device, owned: fp16 hi/lo shared-memory image of the Toeplitz block
+  float tc_inv_scale;         // 1 / (power-of-two scale applied to the taps in the image)
 };
 
 namespace psx {
@@ -84,6 +88,18 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
+}
+// the same load as a plain (non-volatile) asm: the compiler may batch several of them ahead of their uses
+__device__ __forceinline__ float4 ld_nc4(const float* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// 256-bit streaming load (sm_100): 32 bytes = one sector per lane
+__device__ __forceinline__ void ld_nc8(const float* p, float4& a, float4& b) {
+  asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
 }
 __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
@@ -232,6 +248,12 @@ int launch_pre_conv2d(const psx_op* op, const float* x, const float* eps, const 
 int launch_op(const psx_op* op, bool adjoint, const float* in, float* out, int64_t L, float* ws,
               cudaStream_t st);
 int sepblur_plan(psx_op* op);
+void tcblur_plan(psx_op* op);
+void tcblur_release(psx_op* op);
+bool tcblur_available(const psx_op* op);
+int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
+                          int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot,
+                          float* err_part, cudaStream_t st);
 int conv2d_err_parts(const psx_op* op);
 
 }  // namespace psx

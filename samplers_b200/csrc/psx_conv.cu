@@ -1430,6 +1430,9 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
                        float* x0_out, float* ws, cudaStream_t st, bool half) {
   if (x0_out) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: d_x0_out is not produced for blur operators");
   const int64_t planes = L * op->C;
+  // tensor-core single launch (psx_tcblur.cu): 256 x 256 planes, symmetric taps shared by rows and columns
+  if (!half && tcblur_available(op) && !getenv("PSX_NO_TC"))
+    return launch_pre_sepblur_tc(op, x, eps, y, L, obs_repeat, sa, s1, w, dsc, cot, err_part, st);
   // cluster-fused single launch for 256 x 256 planes
   if (op->H == kFusedCL * kFusedRB && op->W == kFusedW && op->fh.k == 40 && op->fv.k == 40 && op->ah.k == 40 &&
       op->av.k == 40 && op->fh.lo == op->ah.lo && op->fv.lo == op->av.lo && -op->fv.lo <= kFusedRB &&
