@@ -41,7 +41,7 @@ extern "C" {
 #define PSX_ERR_UNSUPPORTED 3 /* valid request this build has no kernel for  */
 
 #define PSX_MAX_TAPS 127  /* longest 1-D tap vector of a separable blur       */
-#define PSX_ABI_VERSION 2
+#define PSX_ABI_VERSION 3
 
 /* Operator kinds (psx_op_kind). */
 #define PSX_OP_IDENTITY 0
@@ -54,6 +54,11 @@ typedef struct psx_op psx_op; /* opaque host-side operator descriptor */
 
 PSX_API int psx_abi_version(void);
 PSX_API const char* psx_last_error(void);
+/* The kernel-selection switches (environment: PSX_SPLIT, PSX_FUSED, PSX_NO_TC, PSX_NO_PIPE, PSX_NO_FAST16; all
+ * default to the measured-best path) are read ONCE, at the first launch.  A process that changes them afterwards
+ * (the tests and measurement tools do) calls this to have them read again.  No reference counterpart: the
+ * reference has one code path per operator. */
+PSX_API void psx_reload_env(void);
 
 /* ---------------------------------------------------------------- operators
  * Degradation operators A (forward) / A^T (adjoint).  Replaces

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libpsx.so")
 
 PSX_OK, PSX_ERR_INVALID, PSX_ERR_CUDA, PSX_ERR_UNSUPPORTED = 0, 1, 2, 3
 OP_IDENTITY, OP_MASK, OP_BOX, OP_SEPBLUR, OP_CONV2D = range(5)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); must list every prototype of include/psx.h
 _f32p, _i64, _vp, _f = C.c_void_p, C.c_int64, C.c_void_p, C.c_float
@@ -23,6 +23,7 @@ _opp = C.c_void_p
 PROTOTYPES = {
     "psx_abi_version": (C.c_int, []),
     "psx_last_error": (C.c_char_p, []),
+    "psx_reload_env": (None, []),
     "psx_op_create_identity": (C.c_int, [_i64, C.POINTER(_opp)]),
     "psx_op_create_mask": (C.c_int, [_i64, _vp, C.POINTER(_opp)]),
     "psx_op_create_box": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_opp)]),
@@ -104,6 +105,11 @@ def load() -> C.CDLL:
                 raise RuntimeError("libpsx.so ABI version mismatch; rebuild with `python -m samplers_b200.build --force`")
             _lib = lib
     return _lib
+
+
+def reload_env() -> None:
+    """Have libpsx read its PSX_* kernel-selection switches again (they are cached at the first launch)."""
+    load().psx_reload_env()
 
 
 def check(code: int) -> None:

@@ -3,6 +3,7 @@
 // on the caller's stream.  No CPU implementation exists behind these calls.
 #include <algorithm>
 #include <cmath>
+#include <atomic>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -77,6 +78,32 @@ static int make_taps(const float* w, int k, bool flip, Taps* out) {
   return PSX_OK;
 }
 
+namespace {
+EnvOpts g_env;
+std::atomic<bool> g_env_read{false};
+std::mutex g_env_mu;
+void read_env() {
+  EnvOpts e;
+  e.no_pipe = getenv("PSX_NO_PIPE") != nullptr;
+  e.no_fast16 = getenv("PSX_NO_FAST16") != nullptr;
+  e.no_tc = getenv("PSX_NO_TC") != nullptr;
+  e.fused = getenv("PSX_FUSED") != nullptr;
+  const char* sp = getenv("PSX_SPLIT");
+  e.split = sp ? atoi(sp) : 0;
+  g_env = e;
+}
+}  // namespace
+const EnvOpts& env_opts() {
+  if (!g_env_read.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lock(g_env_mu);
+    if (!g_env_read.load(std::memory_order_relaxed)) {
+      read_env();
+      g_env_read.store(true, std::memory_order_release);
+    }
+  }
+  return g_env;
+}
+
 }  // namespace psx
 
 using namespace psx;
@@ -84,6 +111,11 @@ using namespace psx;
 extern "C" {
 
 PSX_API int psx_abi_version(void) { return PSX_ABI_VERSION; }
+PSX_API void psx_reload_env(void) {
+  std::lock_guard<std::mutex> lock(g_env_mu);
+  read_env();
+  g_env_read.store(true, std::memory_order_release);
+}
 PSX_API const char* psx_last_error(void) { return g_last_error.c_str(); }
 
 static psx_op* new_op(int kind) {

@@ -256,4 +256,11 @@ int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, co
                           float* err_part, cudaStream_t st);
 int conv2d_err_parts(const psx_op* op);
 
+// Kernel-selection switches of the environment, read once (psx_reload_env re-reads them).
+struct EnvOpts {
+  bool no_pipe, no_fast16, no_tc, fused;
+  int split;  // PSX_SPLIT: forced number of K1 sample groups, 0 = automatic
+};
+const EnvOpts& env_opts();
+
 }  // namespace psx

@@ -1278,7 +1278,7 @@ static int run_rows(const psx_op* op, const Taps& t, const float* in, const floa
 #undef PSX_ROWS_H
     return check_cuda(cudaGetLastError(), "conv_rows_pipe (bf16) launch");
   }
-  if ((op->W & 7) == 0 && op->W <= 512 && !getenv("PSX_NO_PIPE")) {
+  if ((op->W & 7) == 0 && op->W <= 512 && !env_opts().no_pipe) {
     const int pitch2 = row_pitch2(op->W + t.k);
     const int arrays = MODE == ROWS_TWEEDIE ? 2 : 1;
     const size_t smem = kPipeHdr + (size_t)(kPipeRows / 2) * pitch2 * sizeof(float2) +
@@ -1329,7 +1329,7 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
                              8 * kColTC * sizeof(float);  // 8 slack rows for the unconditional window prefetch
     CUtensorMap map;
     // the |r|^2 partials are laid out per strip of op->col_tc columns: the pipelined kernel only runs at that width
-    if ((op->W % kColTC) == 0 && (op->H % 16) == 0 && op->H <= 256 && op->col_tc == kColTC && !getenv("PSX_NO_PIPE") &&
+    if ((op->W % kColTC) == 0 && (op->H % 16) == 0 && op->H <= 256 && op->col_tc == kColTC && !env_opts().no_pipe &&
         make_strip_map(&map, in, planes * op->H, op->W, kColTC, op->H)) {
       const int rounds = ((op->H >> 3) * (kColTC >> 1) + kThreads - 1) / kThreads;  // the last round may be partial
       const int strips = op->W / kColTC;
@@ -1431,12 +1431,12 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
   if (x0_out) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: d_x0_out is not produced for blur operators");
   const int64_t planes = L * op->C;
   // tensor-core single launch (psx_tcblur.cu): 256 x 256 planes, symmetric taps shared by rows and columns
-  if (!half && tcblur_available(op) && !getenv("PSX_NO_TC"))
+  if (!half && tcblur_available(op) && !env_opts().no_tc)
     return launch_pre_sepblur_tc(op, x, eps, y, L, obs_repeat, sa, s1, w, dsc, cot, err_part, st);
   // cluster-fused single launch for 256 x 256 planes
   if (op->H == kFusedCL * kFusedRB && op->W == kFusedW && op->fh.k == 40 && op->fv.k == 40 && op->ah.k == 40 &&
       op->av.k == 40 && op->fh.lo == op->ah.lo && op->fv.lo == op->av.lo && -op->fv.lo <= kFusedRB &&
-      op->err_parts == op->C * kFusedCL && getenv("PSX_FUSED") && !half) {
+      op->err_parts == op->C * kFusedCL && env_opts().fused && !half) {
     // opt-in: measured 48.0 us vs 46.1 us for the three-launch path at L = 16 (profiles/README.md) -- each CTA runs
     // its nine phases back to back (21 us per CTA, 6 us of it in cluster barriers) and 48 planes need two waves
     // of the 33 clusters that fit, so the single launch does not pay off yet despite its minimal HBM traffic.
@@ -1459,7 +1459,7 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
   const bool small = op->W <= 256 && op->H <= 256;
   const bool fast = op->W % 32 == 0 && op->W <= 512 && op->H % 16 == 0 && op->H <= 512 && op->av.k == kk &&
                     op->ah.k == kk && op->col_tc == (small ? 32 : 16) && (kk == 40 || kk == 16) &&
-                    (small || op->H % 32 == 0) && !getenv("PSX_NO_PIPE") && !getenv("PSX_NO_FAST16") &&
+                    (small || op->H % 32 == 0) && !env_opts().no_pipe && !env_opts().no_fast16 &&
                     encode_fn() != nullptr;
   if (fast) {
     // The three launches of one group leave SMs idle in every kernel's ramp-up and tail (about a third of K1 at
@@ -1467,8 +1467,7 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
     // stream plus side streams: one group's tails and launch gaps are filled by the other groups' kernels.
     // Measured (profiles/README.md): inside a replayed CUDA graph the fork/join is free and two groups cut K1 by 8 %
     // at L = 16; launched eagerly the extra event calls cost more than the overlap returns until L >= 32.
-    const char* env_split = getenv("PSX_SPLIT");  // read per call: the tests switch it
-    const int forced = env_split ? atoi(env_split) : 0;
+    const int forced = env_opts().split;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     const int want = forced ? forced : ((cap == cudaStreamCaptureStatusActive || L >= 32) ? 2 : 1);

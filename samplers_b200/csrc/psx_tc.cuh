@@ -61,9 +61,52 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded spin: a protocol error must surface as a trap (launch failure), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++n > (1u << 22)) __trap();
   }
+}
+// the same for a barrier that a peer CTA of the cluster arrives on (acquire at cluster scope)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++n > (1u << 22)) __trap();
+  }
+}
+// Polling wait (mbarrier.test_wait never suspends the thread) for the single-lane specialist warps: a suspended
+// try_wait was measured to notice a completion up to ~1 us late (profiles/r02_tc_phase_trace_v3.txt).
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok, n = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (++n > (1u << 26)) __trap();
+  } while (!ok);
+}
+// pure signal (orders no data of the arriving thread): 64-96 ns to the peer against 224 ns for the release form, and
+// the sender is not held up (profiles/r02_dsmem_probe.txt)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t caddr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+// arrive (release at cluster scope) on a barrier in a peer CTA; `caddr` is a shared::cluster address (mapa)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t caddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------ proxies / fences
@@ -93,6 +136,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same with the accumulate flag fixed to 1 (no register, ptxas folds the predicate)
+__device__ __forceinline__ void umma_f16_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc)
       : "memory");
 }
 // all tcgen05.mma issued so far by this thread -> one arrival on `bar` when they have completed
@@ -133,6 +184,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// shared (this CTA) -> shared of a peer CTA of the cluster (linear); `cdst` and `cbar` are shared::cluster addresses
+// (mapa), completion is counted in bytes on the PEER's barrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t cdst, const void* smem_src, uint32_t bytes, uint32_t cbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cdst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "r"(cbar)
+               : "memory");
+}
 // shared -> global (linear), bulk-group completion
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
@@ -163,6 +221,13 @@ __device__ __forceinline__ void cluster_arrive_release() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// one lane of a converged warp (ptxas then knows the guarded tcgen05 / bulk-copy code runs in exactly one thread)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 
 // ------------------------------------------------------------------------------------------ fp16 splitting
 // x ~= hi + lo with hi = fp16_rn(x), lo = fp16_rn(x - hi): 22 significant bits, the three-product scheme

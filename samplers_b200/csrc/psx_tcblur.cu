@@ -3,39 +3,48 @@
 // Replaces, for A = V H (separable blur, 256 x 256 planes), the reference lines K1 stands for
 // (samplers/networks/base.py:41-43, samplers/inverse_problem.py:17-21, samplers/noise.py:77-79 / 121-123 and
 // their autograd mirror samplers/samplers/dps.py:102-103,117-120):
-//     cot = (w / sa) * H^T V^T (y - V H x0),   x0 = (x_t - s1 eps) / sa,   |r|^2 partial sums.
+//     cot = (w / sa) * A^T (y - A x0),   x0 = (x_t - s1 eps) / sa,   |r|^2 partial sums.
 //
-// Formulation.  Each of the four 1-D passes is a banded-Toeplitz matrix product, evaluated as N-tiles of 64 outputs
-// whose K window is the 64 + 2 PAD inputs the band touches.  The Toeplitz block B[n][k] = tap[(k - PAD) - n - lo] is
-// the same for every tile (the operands are zero-padded by PAD, so the image border needs no special case) and is
-// always the B operand of the UMMA; the image data is always the A operand (M = 128 TMEM lanes):
-//     P1  H1 [i , j'] = sum_j  X [i , j ] Bh [j', j ]      A = X   K-major   (lanes = image rows)
-//     P2  AXt[j', i'] = sum_i  H1[i , j'] Bv [i', i ]      A = H1  MN-major  (lanes = image columns)
-//     P3  H2t[j', i ] = sum_i' R [i', j'] Bvt[i , i']      A = Rt  K-major   (lanes = image columns)
-//     P4  cot[i , j ] = sum_j' H2[i , j'] Bht[j , j']      A = H2  MN-major  (lanes = image rows)
-// so that the thread that reads row m of an accumulator from TMEM always writes 16-byte pieces of the next operand
-// (its values run along K for a K-major operand and along M for an MN-major one): no transposes, and eight
-// consecutive lanes fill one contiguous 128-byte core matrix (conflict-free shared-memory stores).
+// Formulation.  Each 1-D pass is a banded-Toeplitz product evaluated in K-steps of 16 inputs: the 16 inputs
+// k = 16 s .. 16 s + 15 (zero-padded coordinates, PAD = 24) reach the outputs n = 16 s - 48 .. 16 s + 15 only, so
+// one K-step is ONE 64-wide UMMA window  D[:, 16 s - 48 .. 16 s + 16) += A[:, 16 s .. 16 s + 16) Bw^T  with the
+// SAME 64 x 16 Toeplitz block Bw[n'][k'] = tap[k' - n' + 24 - lo] for every step (clipped at the borders by moving
+// the start of the B descriptor and shrinking N).  The image is always the A operand (M = 128 TMEM lanes), the
+// accumulators are cleared by one UMMA against a zero block, and the separable factors are applied in the order
+//     P1  V   (columns pass)   A = x_t - s1 eps       MN-major, lanes = image columns, K = rows
+//     P2  H   (rows pass)      A = V x0               MN-major, lanes = image rows,    K = columns (+ halo)
+//     P3  H^T (rows pass)      A = r = y - H V x0     K-major,  lanes = image rows,    K = columns (+ halo)
+//     P4  V^T (columns pass)   A = H^T r              MN-major, lanes = image columns, K = rows
+// (V and H commute).  The thread that reads lane m of an accumulator always writes 16-byte pieces of the next
+// operand, x_t / eps stream in row by row behind the first pass's K loop and cot leaves the last accumulator as
+// full 128-byte lines: no transposes, no staging buffers.
 //
 // Precision.  Operands are fp16 pairs x = hi + lo (22 significant bits); a product is the three UMMAs
-// A_hi B_hi + A_lo B_hi + A_hi B_lo accumulated in fp32 in TMEM: measured 4e-7 relative (profiles/r02_umma_probe.txt).
-// The taps are scaled by a power of two into fp16's normal range, x0 enters as x_t - s1 eps (the 1/sa is applied to the
-// accumulator) and the residual is scaled by 64, so that fp16's range is not an issue for |x_t - s1 eps| < 6e4.
+// A_hi B_hi + A_lo B_hi + A_hi B_lo accumulated in fp32 in TMEM: 4e-7 relative (profiles/r02_umma_probe.txt).
+// The taps are scaled by a power of two into fp16's normal range, x0 enters as x_t - s1 eps (the 1/sa is applied to
+// the accumulator) and the residual is scaled by 64, so that fp16's range is not an issue for |x_t - s1 eps| < 6e4.
 //
 // Work split.  One thread-block CLUSTER of two CTAs per plane; CTA `rank` owns the 128 image columns
-// [128 rank, 128 rank + 128) and all 256 rows.  The column passes P2 / P3 are local to a column range; P1 reads its
-// PAD halo columns of x_t / eps straight from global memory; only P4 needs the neighbour's H2 halo columns, which the
-// neighbour's P3 epilogue writes into this CTA's operand buffer through distributed shared memory (one exchange,
-// two cluster barriers, both split into arrive / wait so that nobody blocks on them in the common case).
+// [128 rank, 128 rank + 128) and all 256 rows.  The column passes are local; each row pass needs 24 halo columns
+// from the neighbour: 3 contiguous K blocks per row tile, moved by ONE bulk copy (cp.async.bulk shared::cta ->
+// shared::cluster) straight into this CTA's operand buffer, completing on this CTA's mbarrier; two more mbarriers
+// per exchange that the CTAs arrive on remotely say "your slot is free" and "your copy has been received".
 //
-// Shared memory: one operand buffer (A1 -> A2 -> A3 -> A4 in place, 176 KB for PAD = 24) + the Toeplitz block
-// (28 KB); TMEM: 2 x 256 columns, alternating between passes.  Warps 0-15 load / convert / run the epilogues,
-// warp 16 allocates TMEM, fetches the Toeplitz block with a bulk copy and issues the UMMAs from one lane.
+// Pipeline.  One operand buffer (176 KB) is rewritten in place A1 -> A2 -> A3 -> A4; the layouts are chosen so that
+// the half of the next operand that is complete first never overlaps what the running pass still reads:
+//     column-pass operand (A1, A4)  [38 K blocks of 8 padded rows][hi | lo][16 column groups][128 B]      152 KB
+//     row-pass operand    (A2, A3)  [2 row tiles of 128][22 K blocks of 8 padded columns][hi | lo][16][128 B]
+// and every hand-over is an mbarrier of its own: x_t / eps arrive in 8 chunks of 32 rows (P1 starts on the first),
+// P1 commits after the K-step that completes rows 0..127, the row passes run per 128-row tile and commit per 64
+// output columns, P4 commits per 64 output rows.  Warps 0-15 load / convert / run the epilogues (each task is
+// split over all 16 warps), warp 16 allocates TMEM and issues the UMMAs from one lane, warp 17 issues the
+// halo copies, warp 18 sends the "slot is free" signals.
 #include <cuda_fp16.h>
 
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "psx_common.cuh"
@@ -46,373 +55,487 @@ namespace psx {
 using namespace tc;
 
 #ifdef PSX_TRACE
-// phase timeline (tools/micro/tc_trace_main.cu): [CTA][role: 0 = epilogue warp 0, 1 = UMMA warp][slot] = %globaltimer
-__device__ long long psx_trace_tc[1024 * 2 * 16];
+// phase timeline (tools/micro/tc_trace_main.cu): [CTA][role: 0 = epilogue warp 0, 1 = UMMA thread][slot] = %globaltimer
+// role 0 = epilogue warp 0, 1 = UMMA thread, 2 = halo-copy thread, 3 = slot-free signal thread
+__device__ long long psx_trace_tc[1024 * 4 * 32];
 #define PSX_TCTICK(role, slot)                                                             \
-  if (lane == 0 && warp == ((role) ? 16 : 0) && blockIdx.x < 1024) {                        \
+  if (warp == ((role) ? kTcWarps + (role) - 1 : 0) && blockIdx.x < 1024 && ((role) ? true : lane == 0)) { \
     long long t_;                                                                          \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
-    psx_trace_tc[(blockIdx.x * 2 + (role)) * 16 + (slot)] = t_;                            \
+    psx_trace_tc[(blockIdx.x * 4 + (role)) * 32 + (slot)] = t_;                            \
   }
+#define PSX_TCCLOCK(slot)                                                      \
+  if (tid == 0 && blockIdx.x < 1024) psx_trace_tc[(blockIdx.x * 4) * 32 + (slot)] = clock64();
 #else
 #define PSX_TCTICK(role, slot)
+#define PSX_TCCLOCK(slot)
 #endif
 
 namespace {
 
-constexpr int kTcN = 256;        // plane side
-constexpr int kTcNT = 64;        // outputs per N-tile
+constexpr int kTcN = 256;                  // plane side
+constexpr int kTcPad = 24;                 // zero padding / halo width = largest supported tap offset
 constexpr int kTcWarps = 16;               // loader / epilogue warps
 constexpr int kTcEpi = 32 * kTcWarps;      // loader / epilogue threads
-constexpr int kTcThreads = kTcEpi + 32;    // + the UMMA warp
+constexpr int kTcThreads = kTcEpi + 96;    // + the UMMA warp, the halo-copy warp, the slot-free signal warp
+constexpr int kHaloBytes = (kTcPad / 8) * 4096;  // 24 halo columns of one row tile: 3 K blocks
 constexpr float kTcRScale = 64.f;
 
-template <int PAD>
-struct TcGeo {
-  static constexpr int KW = kTcNT + 2 * PAD;        // K window of one N-tile
-  static constexpr int KS = KW / 16;                // UMMA k-steps per tile
-  static constexpr int KC_ROW = (128 + 2 * PAD) / 8;  // K core columns of A1 / A4 (own columns + halo)
-  static constexpr int KC_COL = (256 + 2 * PAD) / 8;  // K core columns of A2 / A3 (all rows + zero pad)
-  // operand layout: [K core column][part: hi, lo][M group][128-byte core matrix]
-  static constexpr int LBO_ROW = 2 * 32 * 128;      // A1 / A4: 256 rows = 32 M groups
-  static constexpr int LBO_COL = 2 * 16 * 128;      // A2 / A3: 128 columns = 16 M groups
-  static constexpr int LO_ROW = 32 * 128, LO_COL = 16 * 128;  // offset of the lo part
-  static constexpr int OP_BYTES = KC_ROW * LBO_ROW;
-  static constexpr int COL_BYTES = KC_COL * LBO_COL;
-  static constexpr int HALO_BYTES = (PAD / 8) * LBO_ROW;  // the K core columns of A4 the neighbour writes
-  static constexpr int B_BYTES = (KW / 8) * 2048;   // [K core column][16 N groups: 8 hi + 8 lo][128]
-  static constexpr int SMEM = OP_BYTES + B_BYTES + 256;
-  static_assert(PAD % 8 == 0 && KW % 16 == 0, "PAD must be a multiple of 8");
-  static_assert(OP_BYTES - COL_BYTES == HALO_BYTES, "A2 / A3 must fit beside the halo slot");
-  static_assert(SMEM <= 227 * 1024, "shared memory");
+constexpr int kKc = 4096;                  // one K block: 8 K values x 128 M values, [hi 2 KB | lo 2 KB]
+constexpr int kLo = 2048;                  // offset of the lo part inside a K block
+constexpr int kCpKc = (kTcN + 2 * kTcPad) / 8;        // 38 K blocks of the column-pass operand
+constexpr int kRpKc = (128 + 2 * kTcPad) / 8;         // 22 K blocks of one row tile of the row-pass operand
+constexpr int kRpTile = kRpKc * kKc;                  // 88 KB
+constexpr int kOpBytes = 2 * kRpTile;                 // 176 KB (the column-pass operand, 152 KB, fits inside)
+constexpr int kBBytes = 4096;              // Toeplitz block: [2 K core columns][hi: 8 N groups | lo: 8 N groups][128 B]
+constexpr int kZBytes = 8192;              // zero block (clears up to 256 accumulator columns)
+constexpr int kTcSmem = kOpBytes + kBBytes + kZBytes + 1024;
+constexpr int kCpSteps = kCpKc / 2;        // 19 K-steps of a column pass (the first and the last are all padding)
+constexpr int kRpSteps = kRpKc / 2;        // 11 K-steps of a row pass
+static_assert(kCpKc * kKc <= kOpBytes && kTcSmem <= 227 * 1024, "shared memory");
+
+// mbarriers
+enum {
+  kBLd = 0,      // [8]    chunk c of x_t / eps is in A1                       (16 warps)
+  kBImg = 8,     //        Toeplitz block has landed                            (bulk copy)
+  kBD1 = 9,      // [2]    P1: rows of tile m are complete                      (commit)
+  kBE1 = 11,     // [2]    A2 tile m written locally                            (16 warps)
+  kBH1 = 13,     // [2]    A2 tile m: the neighbour's halo columns have landed  (bulk copy from the neighbour)
+  kBF1 = 15,     // [2]    the NEIGHBOUR's halo slot of tile m is free (A1 consumed there)   (1 remote thread)
+  kBD2 = 17,     // [2][2] P2 tile m: output columns of half h are complete     (commit)
+  kBE2 = 21,     // [2]    A3 tile m written locally                            (2 x 16 warps)
+  kBH2 = 23,     // [2]    A3 tile m: the neighbour's halo columns have landed  (bulk copy from the neighbour)
+  kBF2 = 25,     // [2]    the NEIGHBOUR's halo slot of tile m is free (its P2 is done)      (1 remote thread)
+  kBD3 = 27,     // [2]    P3 tile m complete                                   (commit)
+  kBE3 = 29,     // [2]    A4 rows of tile m written                            (16 warps)
+  kBD4 = 31,     // [4]    P4: output rows of quarter q are complete            (commit)
+  kBS1 = 35,     // [2]    the K blocks of A2 tile m that the neighbour needs are written   (4 warps)
+  kBS2 = 37,     // [2]    the K blocks of A3 tile m that the neighbour needs are written   (8 warps)
+  kBA1 = 39,     // [2]    the neighbour has received this CTA's A2 halo of tile m (source blocks may be rewritten)
+  kBA2 = 41,     // [2]    ... A3 halo of tile m                                        (1 remote thread each)
+  kBCount = 43
 };
 
-// three UMMAs per k-step: D (+)= Ah Bh + Al Bh + Ah Bl
-__device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo_off, uint32_t lbo_a,
-                                           uint64_t dBh, uint64_t dBl, uint32_t idesc, int ksteps) {
-  const uint64_t dAh = smem_desc(a_hi, lbo_a, 128);
-  const uint64_t dAl = dAh + (uint64_t)(a_lo_off >> 4);
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint64_t aa = (uint64_t)((2u * lbo_a * ks) >> 4), ab = (uint64_t)((2u * 2048u * ks) >> 4);
-    umma_f16(d_tmem, dAh + aa, dBh + ab, idesc, ks > 0);
-    umma_f16(d_tmem, dAl + aa, dBh + ab, idesc, 1);
-    umma_f16(d_tmem, dAh + aa, dBl + ab, idesc, 1);
+// One K-step of a banded pass on NOUT outputs: the window of the 16 inputs 16 S .. 16 S + 15, three split terms.
+// Everything but the operand base is a compile-time constant (the issuing thread shares its scheduler with four
+// epilogue warps: every instruction it does not execute is tensor-pipe time won).  `a_lo32` / `b_lo32` are the low
+// words of the descriptors of the operand base / the Toeplitz block, `hi32` their common high word.
+template <int NOUT, int S, int A_MN>
+__device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t hi32) {
+  constexpr int w0 = 16 * S - 48;
+  constexpr int n_lo = w0 > 0 ? w0 : 0;
+  constexpr int n_hi = w0 + 64 < NOUT ? w0 + 64 : NOUT;
+  constexpr uint32_t id = idesc_f16(128, n_hi - n_lo, A_MN, 0);
+  const uint64_t up = (uint64_t)hi32 << 32;
+  const uint64_t dAh = up | (a_lo32 + (uint32_t)((2 * S * kKc) >> 4)), dAl = up | (a_lo32 + (uint32_t)((2 * S * kKc + kLo) >> 4));
+  const uint64_t dBh = up | (b_lo32 + (uint32_t)((((n_lo - w0) >> 3) * 128) >> 4));
+  const uint64_t dBl = up | (b_lo32 + (uint32_t)((((n_lo - w0) >> 3) * 128 + 1024) >> 4));
+  umma_f16_acc(d_tmem + n_lo, dAh, dBh, id);
+  umma_f16_acc(d_tmem + n_lo, dAl, dBh, id);
+  umma_f16_acc(d_tmem + n_lo, dAh, dBl, id);
+}
+template <int S0, int S1, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (S0 < S1) {
+    f(std::integral_constant<int, S0>{});
+    static_for<S0 + 1, S1>(f);
   }
 }
-
-// 32 fp32 accumulator values (times `sc`) -> four hi and four lo 16-byte operand pieces
-__device__ __forceinline__ void split32(const uint32_t (&v)[32], float sc, uint4 (&hi)[4], uint4 (&lo)[4]) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    split2(__uint_as_float(v[8 * g + 0]) * sc, __uint_as_float(v[8 * g + 1]) * sc, hi[g].x, lo[g].x);
-    split2(__uint_as_float(v[8 * g + 2]) * sc, __uint_as_float(v[8 * g + 3]) * sc, hi[g].y, lo[g].y);
-    split2(__uint_as_float(v[8 * g + 4]) * sc, __uint_as_float(v[8 * g + 5]) * sc, hi[g].z, lo[g].z);
-    split2(__uint_as_float(v[8 * g + 6]) * sc, __uint_as_float(v[8 * g + 7]) * sc, hi[g].w, lo[g].w);
-  }
+// D[:, 0 .. n) = 0
+__device__ __forceinline__ void issue_clear(uint32_t d_tmem, int n, uint32_t z_addr) {
+  umma_f16(d_tmem, smem_desc(z_addr, 2048, 128), smem_desc(z_addr, 4096, 128), idesc_f16(128, n, 0, 0), 0);
 }
 
-template <int PAD>
+// 8 fp32 values (times `sc`) -> one hi and one lo 16-byte operand piece
+__device__ __forceinline__ void split8(const uint32_t* v, float sc, uint4& hi, uint4& lo) {
+  split2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc, hi.x, lo.x);
+  split2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc, hi.y, lo.y);
+  split2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc, hi.z, lo.z);
+  split2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc, hi.w, lo.w);
+}
+__device__ __forceinline__ void st_piece(uint8_t* d, const uint4& hi, const uint4& lo) {
+  *reinterpret_cast<uint4*>(d) = hi;
+  *reinterpret_cast<uint4*>(d + kLo) = lo;
+}
+__device__ __forceinline__ void zero_fill(uint8_t* base, int bytes, int tid) {
+  for (int i = tid; i < bytes / 16; i += kTcEpi) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+}
+// all lanes have fenced their shared-memory writes; one arrival per warp
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     blur_k1_tc(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
-               float* __restrict__ cot, float* __restrict__ err_part, const uint8_t* __restrict__ bimg, float4 bsc,
+               float* __restrict__ cot, float* __restrict__ err_part, const uint8_t* __restrict__ bimg, float inv_scale,
                int C, int64_t obs_repeat, int pp, float sa, float s1, float coef, const float* __restrict__ dsc) {
-  using G = TcGeo<PAD>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* op = smem;
-  uint8_t* bsm = smem + G::OP_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(bsm + G::B_BYTES);  // [4] operand of pass p is in shared memory
-  uint64_t* done = full + 4;                                        // [4] UMMAs of pass p have completed
-  uint64_t* bfull = full + 8;                                       // Toeplitz block has landed
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 9);
-  float* red = reinterpret_cast<float*>(full + 10);                 // [kTcWarps]
+  uint8_t* bsm = smem + kOpBytes;
+  uint8_t* zsm = bsm + kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(zsm + kZBytes);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + kBCount);
+  float* red = reinterpret_cast<float*>(bars + kBCount + 1);  // [kTcWarps]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
   const int64_t plane = blockIdx.x >> 1;
   const int j0 = (int)rank * 128;
-  const uint32_t colbase = rank ? G::HALO_BYTES : 0;  // A2 / A3 live beside the halo slot the neighbour writes
   step_scalars_k1(dsc, sa, s1, coef);
   PSX_TCTICK(0, 0)
   PSX_TCTICK(1, 0)
+  PSX_TCCLOCK(30)
 
   if (warp == kTcWarps) {
     if (lane == 0) {
-      for (int i = 0; i < 4; ++i) {
-        mbar_init(full + i, kTcEpi);
-        mbar_init(done + i, 1);
-      }
-      mbar_init(bfull, 1);
+      mbar_init(bars + kBImg, 1);
       fence_mbar_init();
+      mbar_expect_tx(bars + kBImg, kBBytes);
+      bulk_g2s(bsm, bimg, kBBytes, bars + kBImg);
     }
     __syncwarp();
     tmem_alloc<512>(tslot);
-    if (lane == 0) {
-      mbar_expect_tx(bfull, G::B_BYTES);
-      bulk_g2s(bsm, bimg, G::B_BYTES, bfull);
+  } else if (warp == kTcWarps + 1) {
+    // one barrier per lane (two rounds); arrival counts by barrier index
+    for (int i = lane; i < kBCount; i += 32) {
+      if (i == kBImg) continue;
+      int cnt = 1;  // commits, bulk copies, single remote threads
+      if (i < kBLd + 8 || (i >= kBE1 && i < kBE1 + 2) || (i >= kBE3 && i < kBE3 + 2)) cnt = kTcWarps;
+      if (i >= kBE2 && i < kBE2 + 2) cnt = 2 * kTcWarps;
+      if (i >= kBS1 && i < kBS1 + 2) cnt = 4;
+      if (i >= kBS2 && i < kBS2 + 2) cnt = 8;
+      mbar_init(bars + i, cnt);
     }
+    fence_mbar_init();
+    __syncwarp();
+    if (lane < 4)  // armed here: the neighbour's bulk copies only add the bytes
+      mbar_expect_tx(bars + (lane < 2 ? kBH1 + lane : kBH2 + lane - 2), kHaloBytes);
+  } else if (warp < kTcWarps) {
+    reinterpret_cast<uint4*>(zsm)[tid] = make_uint4(0, 0, 0, 0);  // 512 x 16 B
+    fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  cluster_arrive_release();  // #0: this CTA's barriers are initialised
   const uint32_t tb = *tslot;
   PSX_TCTICK(0, 1)
   PSX_TCTICK(1, 1)
 
   if (warp == kTcWarps) {
-    // ------------------------------------------------------------------------------------ UMMA issue
-    const uint32_t op_s = smem_u32(op), b_s = smem_u32(bsm);
-    const uint64_t dBh = smem_desc(b_s, 2048, 128), dBl = dBh + (uint64_t)(1024 >> 4);
-    mbar_wait(bfull, 0);
-    PSX_TCTICK(1, 2)
-    mbar_wait(full + 0, 0);
-    tc_fence_after();
-    PSX_TCTICK(1, 3)
-    if (lane == 0) {
-      const uint32_t id = idesc_f16(128, kTcNT, 0, 0);
-      for (int mt = 0; mt < 2; ++mt)
-        for (int t = 0; t < 2; ++t)
-          issue_tile(tb + (mt * 2 + t) * 64, op_s + t * 8 * G::LBO_ROW + mt * 16 * 128, G::LO_ROW, G::LBO_ROW, dBh, dBl, id,
-                     G::KS);
-      umma_commit(done + 0);
+    // ================================================================================== UMMA issue (one lane)
+    cluster_wait_acquire();  // #0
+    if (elect_one()) {
+      const uint32_t op_s = smem_u32(op), z_s = smem_u32(zsm);
+      const uint64_t da = smem_desc(op_s, kKc, 128), db = smem_desc(smem_u32(bsm), 2048, 128);
+      const uint32_t hi32 = (uint32_t)(da >> 32), a0 = (uint32_t)da, b0 = (uint32_t)db;  // same SBO / version word
+      const uint32_t cbar = mapa(smem_u32(bars), peer);
+      mbar_spin(bars + kBImg, 0);
+      // ---- P1: V on the own columns, K = rows, streamed in behind the load
+      issue_clear(tb, 256, z_s);
+      static_for<1, kCpSteps - 1>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        constexpr int last = 16 * s - 9 < kTcN - 1 ? 16 * s - 9 : kTcN - 1;  // last image row of this K-step
+        constexpr int prev = s == 1 ? -1 : (16 * (s - 1) - 9 < kTcN - 1 ? 16 * (s - 1) - 9 : kTcN - 1);
+        if constexpr ((last >> 5) != (prev >> 5) || s == 1) {
+          mbar_spin(bars + kBLd + (last >> 5), 0);
+          tc_fence_after();
+        }
+        issue_kstep<256, s, 1>(tb, a0, b0, hi32);
+        if constexpr (s == 10) umma_commit(bars + kBD1 + 0);  // outputs n <= 132 are final
+      });
+      umma_commit(bars + kBD1 + 1);
+      PSX_TCTICK(1, 2)
+      // ---- P2: H per row tile, K = columns.  The K-steps that need only own columns go first, the two that touch
+      // the neighbour's halo last (rank 0: K blocks 19..21 = steps 9, 10, step 0 is border padding; rank 1: K blocks
+      // 0..2 = steps 0, 1, step 10 is border padding).  The half of the outputs that is complete first ("th 0") is
+      // columns 0..63 on rank 0 (after step 6) and columns 64..127 on rank 1 (after its own steps 2..9).
+#pragma unroll 1
+      for (int m = 0; m < 2; ++m) {
+        mbar_spin(bars + kBE1 + m, 0);
+        tc_fence_after();
+        PSX_TCTICK(1, 15 + m)
+        const uint32_t d = tb + 256 + 128 * m, am = a0 + (uint32_t)((m * kRpTile) >> 4);
+        issue_clear(d, 128, z_s);
+        if (rank == 0) {
+          static_for<1, 9>([&](auto S) {
+            constexpr int s = decltype(S)::value;
+            issue_kstep<128, s, 1>(d, am, b0, hi32);
+            if constexpr (s == 6) umma_commit(bars + kBD2 + 2 * m);  // outputs n <= 68 are final
+          });
+        } else {
+          static_for<2, 10>([&](auto S) { issue_kstep<128, decltype(S)::value, 1>(d, am, b0, hi32); });
+          umma_commit(bars + kBD2 + 2 * m);  // outputs n >= 59 are final
+        }
+        mbar_spin(bars + kBH1 + m, 0);
+        mbar_arrive_remote_relaxed(cbar + 8 * (kBA1 + m));  // the neighbour's copy has been read out of its operand
+        tc_fence_after();
+        PSX_TCTICK(1, 3 + 2 * m)
+        if (rank == 0) {
+          issue_kstep<128, 9, 1>(d, am, b0, hi32);
+          issue_kstep<128, 10, 1>(d, am, b0, hi32);
+        } else {
+          issue_kstep<128, 0, 1>(d, am, b0, hi32);
+          issue_kstep<128, 1, 1>(d, am, b0, hi32);
+        }
+        umma_commit(bars + kBD2 + 2 * m + 1);
+        PSX_TCTICK(1, 4 + 2 * m)
+      }
+      // ---- P3: H^T per row tile, the same order
+#pragma unroll 1
+      for (int m = 0; m < 2; ++m) {
+        mbar_spin(bars + kBE2 + m, 0);
+        tc_fence_after();
+        PSX_TCTICK(1, 17 + m)
+        const uint32_t d = tb + 128 * m, am = a0 + (uint32_t)((m * kRpTile) >> 4);
+        issue_clear(d, 128, z_s);
+        if (rank == 0) {
+          static_for<1, 9>([&](auto S) { issue_kstep<128, decltype(S)::value, 0>(d, am, b0, hi32); });
+        } else {
+          static_for<2, 10>([&](auto S) { issue_kstep<128, decltype(S)::value, 0>(d, am, b0, hi32); });
+        }
+        mbar_spin(bars + kBH2 + m, 0);
+        mbar_arrive_remote_relaxed(cbar + 8 * (kBA2 + m));
+        tc_fence_after();
+        PSX_TCTICK(1, 7 + 2 * m)
+        if (rank == 0) {
+          issue_kstep<128, 9, 0>(d, am, b0, hi32);
+          issue_kstep<128, 10, 0>(d, am, b0, hi32);
+        } else {
+          issue_kstep<128, 0, 0>(d, am, b0, hi32);
+          issue_kstep<128, 1, 0>(d, am, b0, hi32);
+        }
+        umma_commit(bars + kBD3 + m);
+        PSX_TCTICK(1, 8 + 2 * m)
+      }
+      // ---- P4: V^T, K = rows; K-steps 1..7 read rows < 104 (tile 0) and write output rows < 128
+      mbar_spin(bars + kBE3 + 0, 0);
+      tc_fence_after();
+      PSX_TCTICK(1, 11)
+      issue_clear(tb + 256, 128, z_s);
+      static_for<1, 8>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        issue_kstep<256, s, 1>(tb + 256, a0, b0, hi32);
+        if constexpr (s == 6) umma_commit(bars + kBD4 + 0);
+      });
+      PSX_TCTICK(1, 12)
+      mbar_spin(bars + kBE3 + 1, 0);
+      tc_fence_after();
+      PSX_TCTICK(1, 13)
+      issue_clear(tb + 384, 128, z_s);
+      static_for<8, kCpSteps - 1>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        issue_kstep<256, s, 1>(tb + 256, a0, b0, hi32);
+        if constexpr (s == 10) umma_commit(bars + kBD4 + 1);
+        if constexpr (s == 14) umma_commit(bars + kBD4 + 2);
+      });
+      umma_commit(bars + kBD4 + 3);
+      PSX_TCTICK(1, 14)
     }
     __syncwarp();
-    PSX_TCTICK(1, 4)
-    mbar_wait(done + 0, 0);
-    PSX_TCTICK(1, 5)
-    cluster_arrive_release();  // #1: this CTA has finished reading A1, its halo slot may be written
-    mbar_wait(full + 1, 0);
-    tc_fence_after();
-    PSX_TCTICK(1, 6)
-    if (lane == 0) {
-      const uint32_t id = idesc_f16(128, kTcNT, 1, 0);
-      for (int t = 0; t < 4; ++t)
-        issue_tile(tb + 256 + t * 64, op_s + colbase + t * 8 * G::LBO_COL, G::LO_COL, G::LBO_COL, dBh, dBl, id, G::KS);
-      umma_commit(done + 1);
+  } else if (warp == kTcWarps + 1) {
+    // ================================================================================== halo copies to the neighbour
+    // The 24 own columns next to the neighbour are 3 contiguous K blocks of a row tile, here and there: one bulk copy
+    // through distributed shared memory per tile and exchange, completing on the neighbour's H barrier.
+    cluster_wait_acquire();  // #0: the neighbour's barriers exist
+    if (elect_one()) {
+      const uint32_t src = (rank == 0 ? 16 : 3) * kKc, dst = (rank == 0 ? 0 : kRpKc - 3) * kKc;
+      const uint32_t cop = mapa(smem_u32(op), peer), cbar = mapa(smem_u32(bars), peer);
+      for (int m = 0; m < 2; ++m) {
+        mbar_spin(bars + kBS1 + m, 0);
+        PSX_TCTICK(2, 5 + m)
+        mbar_spin(bars + kBF1 + m, 0);
+        PSX_TCTICK(2, 1 + m)
+        bulk_s2peer(cop + m * kRpTile + dst, op + m * kRpTile + src, kHaloBytes, cbar + 8 * (kBH1 + m));
+      }
+      for (int m = 0; m < 2; ++m) {
+        mbar_spin(bars + kBS2 + m, 0);
+        PSX_TCTICK(2, 7 + m)
+        mbar_spin(bars + kBF2 + m, 0);
+        PSX_TCTICK(2, 3 + m)
+        bulk_s2peer(cop + m * kRpTile + dst, op + m * kRpTile + src, kHaloBytes, cbar + 8 * (kBH2 + m));
+      }
     }
     __syncwarp();
-    PSX_TCTICK(1, 7)
-    mbar_wait(full + 2, 0);
-    tc_fence_after();
-    PSX_TCTICK(1, 8)
-    if (lane == 0) {
-      const uint32_t id = idesc_f16(128, kTcNT, 0, 0);
-      for (int t = 0; t < 4; ++t)
-        issue_tile(tb + t * 64, op_s + colbase + t * 8 * G::LBO_COL, G::LO_COL, G::LBO_COL, dBh, dBl, id, G::KS);
-      umma_commit(done + 2);
+  } else if (warp == kTcWarps + 2) {
+    // ================================================================================== "slot is free" signals
+    cluster_wait_acquire();  // #0
+    if (elect_one()) {
+      const uint32_t f1 = mapa(smem_u32(bars + kBF1), peer), f2 = mapa(smem_u32(bars + kBF2), peer);
+      // this CTA's halo slot of tile m overlaps A1 rows that P1 reads up to the commit of tile m
+      mbar_spin(bars + kBD1 + 0, 0);
+      mbar_arrive_remote_relaxed(f1);
+      PSX_TCTICK(3, 1)
+      mbar_spin(bars + kBD1 + 1, 0);
+      mbar_arrive_remote_relaxed(f1 + 8);
+      PSX_TCTICK(3, 2)
+      // ... and holds the A2 halo until P2 of tile m is done
+      mbar_spin(bars + kBD2 + 1, 0);
+      mbar_arrive_remote_relaxed(f2);
+      PSX_TCTICK(3, 3)
+      mbar_spin(bars + kBD2 + 3, 0);
+      mbar_arrive_remote_relaxed(f2 + 8);
+      PSX_TCTICK(3, 4)
     }
     __syncwarp();
-    PSX_TCTICK(1, 9)
-    cluster_wait_acquire();    // #1
-    cluster_arrive_release();  // #2 (this warp writes nothing)
-    mbar_wait(full + 3, 0);
-    cluster_wait_acquire();    // #2: the neighbour's halo columns of H2 are in this CTA's A4
-    fence_async_all();
-    tc_fence_after();
-    PSX_TCTICK(1, 10)
-    if (lane == 0) {
-      const uint32_t id = idesc_f16(128, kTcNT, 1, 0);
-      for (int mt = 0; mt < 2; ++mt)
-        for (int t = 0; t < 2; ++t)
-          issue_tile(tb + 256 + (mt * 2 + t) * 64, op_s + t * 8 * G::LBO_ROW + mt * 16 * 128, G::LO_ROW, G::LBO_ROW, dBh,
-                     dBl, id, G::KS);
-      umma_commit(done + 3);
-    }
-    __syncwarp();
-    PSX_TCTICK(1, 11)
   } else {
-    // warp (q, cq): TMEM lanes 32 q .. 32 q + 31, accumulator columns 64 cq .. 64 cq + 63 (= one N-tile)
+    // ================================================================================== load / epilogues
+    // warp (q, cq): TMEM lanes 32 q .. 32 q + 31, a cq-th share of the accumulator columns of every task
     const int q = warp & 3, cq = warp >> 2;
+    const uint32_t tlane = tb + ((uint32_t)(32 * q) << 16);
+    const int ml = 32 * q + lane;  // this thread's TMEM lane
+    const int64_t l = plane / C, ch = plane % C;
+    const float* yplane = y + ((l / obs_repeat) * C + ch) * (int64_t)(kTcN * kTcN) + j0;
+    // the observation is read much later: pull this CTA's half plane towards L2 now
+    for (int i = tid; i < 256 * 4; i += kTcEpi)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(yplane + (i >> 2) * kTcN + (i & 3) * 32));
+
     // ------------------------------------------------------------------------------------ load: A1 = x_t - s1 eps
     {
-      const float* xp = x + plane * (int64_t)(kTcN * kTcN);
-      const float* ep = eps + plane * (int64_t)(kTcN * kTcN);
-      const int r = lane & 7, c = lane >> 3;
-      // item = (8-row group rg, four K core columns 4 qd .. 4 qd + 3); lane (r, c) converts 8 columns of one row
-      constexpr int kItems = 32 * 6, kPer = kItems / kTcWarps, kBatch = 4;
-      static_assert(kItems % kTcWarps == 0 && kPer % kBatch == 0, "load schedule");
-#pragma unroll 1
-      for (int b0 = 0; b0 < kPer; b0 += kBatch) {
-        float4 xa[kBatch], xb[kBatch], ea[kBatch], eb[kBatch];
+      // chunk c = rows 32 c .. 32 c + 31 = K blocks 3 + 4 c ..; warp = (K block kb, column-group quad), lane = (row r,
+      // column group cl): 32 bytes of one row per lane, 8 rows x 128 B per warp instruction
+      const int r = lane & 7, cg = 4 * (warp & 3) + (lane >> 3), kb = warp >> 2;
+      const float* xp = x + plane * (int64_t)(kTcN * kTcN) + (8 * kb + r) * kTcN + j0 + 8 * cg;
+      const float* ep = eps + plane * (int64_t)(kTcN * kTcN) + (8 * kb + r) * kTcN + j0 + 8 * cg;
+      uint8_t* d0 = op + (3 + kb) * kKc + cg * 128 + r * 16;
+      float4 xa[4], xb[4], ea[4], eb[4];
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          const int it = warp + (b0 + u) * kTcWarps, rg = it / 6, kc = (it % 6) * 4 + c;
-          const int j = j0 - PAD + 8 * kc;
-          const bool in = kc < G::KC_ROW && j >= 0 && j < kTcN;
-          const int off = (8 * rg + r) * kTcN + (in ? j : j0);
-          ld_nc8(xp + off, xa[u], xb[u]);  // one full 32-byte sector per lane and instruction
-          ld_nc8(ep + off, ea[u], eb[u]);
-        }
+      for (int u = 0; u < 4; ++u) {
+        ld_nc8(xp + u * 32 * kTcN, xa[u], xb[u]);
+        ld_nc8(ep + u * 32 * kTcN, ea[u], eb[u]);
+      }
+      // rows above / below the image: K blocks 0..2 and 35..37 of A1 (covered by the arrival on chunk 0)
+      zero_fill(op, 3 * kKc, tid);
+      zero_fill(op + 35 * kKc, 3 * kKc, tid);
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          const int it = warp + (b0 + u) * kTcWarps, rg = it / 6, kc = (it % 6) * 4 + c;
-          const int j = j0 - PAD + 8 * kc;
-          const bool in = j >= 0 && j < kTcN;
-          uint4 hi, lo;
-          split2(fmaf(-s1, ea[u].x, xa[u].x), fmaf(-s1, ea[u].y, xa[u].y), hi.x, lo.x);
-          split2(fmaf(-s1, ea[u].z, xa[u].z), fmaf(-s1, ea[u].w, xa[u].w), hi.y, lo.y);
-          split2(fmaf(-s1, eb[u].x, xb[u].x), fmaf(-s1, eb[u].y, xb[u].y), hi.z, lo.z);
-          split2(fmaf(-s1, eb[u].z, xb[u].z), fmaf(-s1, eb[u].w, xb[u].w), hi.w, lo.w);
-          if (!in) hi = lo = make_uint4(0, 0, 0, 0);
-          if (kc < G::KC_ROW) {
-            uint8_t* d = op + kc * G::LBO_ROW + rg * 128 + r * 16;
-            *reinterpret_cast<uint4*>(d) = hi;
-            *reinterpret_cast<uint4*>(d + G::LO_ROW) = lo;
-          }
+      for (int c = 0; c < 8; ++c) {
+        const int u = c & 3;
+        uint4 hi, lo;
+        split2(fmaf(-s1, ea[u].x, xa[u].x), fmaf(-s1, ea[u].y, xa[u].y), hi.x, lo.x);
+        split2(fmaf(-s1, ea[u].z, xa[u].z), fmaf(-s1, ea[u].w, xa[u].w), hi.y, lo.y);
+        split2(fmaf(-s1, eb[u].x, xb[u].x), fmaf(-s1, eb[u].y, xb[u].y), hi.z, lo.z);
+        split2(fmaf(-s1, eb[u].z, xb[u].z), fmaf(-s1, eb[u].w, xb[u].w), hi.w, lo.w);
+        if (c + 4 < 8) {
+          ld_nc8(xp + (c + 4) * 32 * kTcN, xa[u], xb[u]);
+          ld_nc8(ep + (c + 4) * 32 * kTcN, ea[u], eb[u]);
         }
+        st_piece(d0 + c * 4 * kKc, hi, lo);
+        fence_async_smem();
+        warp_arrive(bars + kBLd + c, lane);
       }
     }
-    fence_async_smem();
-    mbar_arrive(full + 0);
     PSX_TCTICK(0, 2)
+    cluster_wait_acquire();  // #0
 
-    // ------------------------------------------------------------------------------------ E1: H1 -> A2 (MN-major)
-    mbar_wait(done + 0, 0);
-    tc_fence_after();
-    PSX_TCTICK(0, 3)
-    cluster_arrive_release();  // #1
+    // ------------------------------------------------------------------------------------ E1: V x0 -> A2 (MN-major)
+    // lane = own column jl, accumulator columns = image rows; tile m = rows 128 m .. 128 m + 127
     {
-      const int qi = 128 * (cq >> 1) + 32 * q + lane + PAD;  // K index of this thread's image row
-      uint8_t* d = op + colbase + (qi >> 3) * G::LBO_COL + (qi & 7) * 16 + (cq & 1) * 8 * 128;
-      const uint32_t ta = tb + ((uint32_t)(32 * q) << 16) + 64 * cq;
-      uint32_t v0[32], v1[32];
-      tmem_ld32(ta, v0);
-      tmem_ld_wait();
-      tmem_ld32(ta + 32, v1);
-      uint4 hi[4], lo[4];
-      split32(v0, bsc.x, hi, lo);
+      const int jl = ml;
+      const bool halo_warp = rank == 0 ? q == 3 : q == 0;  // owns the columns the neighbour needs
+#pragma unroll 1
+      for (int m = 0; m < 2; ++m) {
+        mbar_wait(bars + kBD1 + m, 0);
+        tc_fence_after();
+        PSX_TCTICK(0, 3 + 2 * m)
+        uint32_t v[32];
+        tmem_ld32(tlane + 128 * m + 32 * cq, v);
+        // border side of the row-pass operand: K blocks 0..2 (rank 0) / 19..21 (rank 1) of tile m
+        zero_fill(op + m * kRpTile + (rank == 0 ? 0 : kRpKc - 3) * kKc, 3 * kKc, tid);
+        tmem_ld_wait();
+        uint4 hi[4], lo[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        *reinterpret_cast<uint4*>(d + g * 128) = hi[g];
-        *reinterpret_cast<uint4*>(d + G::LO_COL + g * 128) = lo[g];
-      }
-      tmem_ld_wait();
-      split32(v1, bsc.x, hi, lo);
+        for (int g = 0; g < 4; ++g) split8(v + 8 * g, inv_scale, hi[g], lo[g]);
+        uint8_t* d = op + m * kRpTile + (3 + (jl >> 3)) * kKc + (4 * cq) * 128 + (jl & 7) * 16;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        *reinterpret_cast<uint4*>(d + (4 + g) * 128) = hi[g];
-        *reinterpret_cast<uint4*>(d + G::LO_COL + (4 + g) * 128) = lo[g];
-      }
-      // zero rows above / below the image (K core columns [0, PAD/8) and [32 + PAD/8, KC_COL)); A3 reuses them
-      for (int idx = tid; idx < 2 * (PAD / 8) * 256; idx += kTcEpi) {
-        const int kz = idx >> 8, kc = kz < PAD / 8 ? kz : 32 + kz;
-        reinterpret_cast<uint4*>(op + colbase + kc * G::LBO_COL)[idx & 255] = make_uint4(0, 0, 0, 0);
+        for (int g = 0; g < 4; ++g) st_piece(d + g * 128, hi[g], lo[g]);
+        tc_fence_before();
+        fence_async_smem();
+        warp_arrive(bars + kBE1 + m, lane);
+        if (halo_warp && lane == 0) mbar_arrive(bars + kBS1 + m);
+        PSX_TCTICK(0, 4 + 2 * m)
       }
     }
-    tc_fence_before();
-    fence_async_smem();
-    mbar_arrive(full + 1);
-    PSX_TCTICK(0, 4)
 
-    // ------------------------------------------------------------------------------------ E2: r = y - AX -> A3 (K-major)
+    // ------------------------------------------------------------------------------------ E2: r = y - H V x0 -> A3 (K-major)
+    // lane = image row il of tile m, accumulator columns = own columns; task (m, h): columns 64 h + 16 cq .. + 15
     float acc = 0.f;
     {
-      const int jl = 32 * q + lane;
-      const int64_t l = plane / C, ch = plane % C;
-      const float* yp = y + ((l / obs_repeat) * C + ch) * (int64_t)(kTcN * kTcN) + (int64_t)(64 * cq) * kTcN + j0 + jl;
-      uint8_t* d = op + colbase + (jl >> 3) * 128 + (jl & 7) * 16 + ((64 * cq + PAD) >> 3) * G::LBO_COL;
-      const uint32_t ta = tb + ((uint32_t)(32 * q) << 16) + 256 + 64 * cq;
-      const float sc = bsc.y / sa;
-      float y0[32], y1[32];
+      // task t = (tile m, th): th 0 = the half of the columns whose outputs are complete first (see P2)
+      const float sc = inv_scale / sa;
+      const int hfirst = rank == 0 ? 0 : 1;
+      const float* yrow = yplane + (int64_t)ml * kTcN + 16 * cq;
+      float4 ya, yb, yc, yd;
+      ld_nc8(yrow + 64 * hfirst, ya, yb);  // in flight while P2 runs; later tasks are fetched one task ahead
+      ld_nc8(yrow + 64 * hfirst + 8, yc, yd);
+#pragma unroll 1
+      for (int t = 0; t < 4; ++t) {
+        const int m = t >> 1, th = t & 1, h = th ^ hfirst, n0 = 64 * h + 16 * cq;
+        const float yy[16] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w, yc.x, yc.y, yc.z, yc.w, yd.x, yd.y, yd.z, yd.w};
+        if (t < 3) {
+          const int t1 = t + 1;
+          const float* yn = yrow + (int64_t)(128 * (t1 >> 1)) * kTcN + 64 * ((t1 & 1) ^ hfirst);
+          ld_nc8(yn, ya, yb);
+          ld_nc8(yn + 8, yc, yd);
+        }
+        mbar_wait(bars + kBD2 + t, 0);
+        tc_fence_after();
+        PSX_TCTICK(0, 7 + 2 * t)
+        uint32_t v[16];
+        tmem_ld16(tlane + 256 + 128 * m + n0, v);
+        tmem_ld_wait();
+        uint32_t rr[16];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) y0[e] = __ldg(yp + e * kTcN);  // in flight while P2 runs
-      mbar_wait(done + 1, 0);
-      tc_fence_after();
-      PSX_TCTICK(0, 5)
-#pragma unroll
-      for (int e = 0; e < 32; ++e) y1[e] = __ldg(yp + (32 + e) * kTcN);
-      uint32_t v[32];
-      uint4 hi[4], lo[4];
-      tmem_ld32(ta, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float rr = y0[e] - __uint_as_float(v[e]) * sc;
-        acc = fmaf(rr, rr, acc);
-        y0[e] = rr;
-      }
-      tmem_ld32(ta + 32, v);
-      split32(reinterpret_cast<const uint32_t(&)[32]>(y0), kTcRScale, hi, lo);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        *reinterpret_cast<uint4*>(d + g * G::LBO_COL) = hi[g];
-        *reinterpret_cast<uint4*>(d + g * G::LBO_COL + G::LO_COL) = lo[g];
-      }
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float rr = y1[e] - __uint_as_float(v[e]) * sc;
-        acc = fmaf(rr, rr, acc);
-        y1[e] = rr;
-      }
-      split32(reinterpret_cast<const uint32_t(&)[32]>(y1), kTcRScale, hi, lo);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        *reinterpret_cast<uint4*>(d + (4 + g) * G::LBO_COL) = hi[g];
-        *reinterpret_cast<uint4*>(d + (4 + g) * G::LBO_COL + G::LO_COL) = lo[g];
+        for (int e = 0; e < 16; ++e) {
+          const float rv = yy[e] - __uint_as_float(v[e]) * sc;
+          acc = fmaf(rv, rv, acc);
+          rr[e] = __float_as_uint(rv);
+        }
+        uint4 hi[2], lo[2];
+        split8(rr, kTcRScale, hi[0], lo[0]);
+        split8(rr + 8, kTcRScale, hi[1], lo[1]);
+        uint8_t* d = op + m * kRpTile + (3 + (n0 >> 3)) * kKc + (ml >> 3) * 128 + (ml & 7) * 16;
+        // the columns next to the neighbour are in the late half on both ranks
+        const bool halo_warp = th == 1 && (rank == 0 ? cq >= 2 : cq <= 1);
+        if (halo_warp) mbar_wait_cluster(bars + kBA1 + m, 0);  // (the copy left long ago; this only makes it formal)
+        st_piece(d, hi[0], lo[0]);
+        st_piece(d + kKc, hi[1], lo[1]);
+        tc_fence_before();
+        fence_async_smem();
+        warp_arrive(bars + kBE2 + m, lane);
+        if (halo_warp && lane == 0) mbar_arrive(bars + kBS2 + m);
+        PSX_TCTICK(0, 8 + 2 * t)
       }
     }
-    tc_fence_before();
-    fence_async_smem();
-    mbar_arrive(full + 2);
-    PSX_TCTICK(0, 6)
     acc = warp_sum(acc);
     if (lane == 0) red[warp] = acc;
 
-    // ------------------------------------------------------------------------------------ E3: H2 -> A4 (MN-major) + halo
-    mbar_wait(done + 2, 0);
-    tc_fence_after();
-    PSX_TCTICK(0, 7)
-    cluster_wait_acquire();  // #1: the neighbour has finished reading its A1
-    PSX_TCTICK(0, 8)
-    {
-      const int jl = 32 * q + lane, pk = jl + PAD;
-      uint8_t* d = op + (pk >> 3) * G::LBO_ROW + (pk & 7) * 16 + 8 * cq * 128;
-      const bool rem = rank == 0 ? jl >= 128 - PAD : jl < PAD;
-      const int pkr = rank == 0 ? jl - 128 + PAD : jl + 128 + PAD;
-      const uint32_t rd =
-          mapa(smem_u32(op) + (uint32_t)((pkr >> 3) * G::LBO_ROW + (pkr & 7) * 16 + 8 * cq * 128), rank ^ 1u);
-      const uint32_t ta = tb + ((uint32_t)(32 * q) << 16) + 64 * cq;
-      uint32_t v0[32], v1[32];
-      tmem_ld32(ta, v0);
+    // ------------------------------------------------------------------------------------ E3: H^T r -> A4 (MN-major)
+    // lane = image row il of tile m, accumulator columns = own columns 32 cq .. 32 cq + 31 (= M of the next pass)
+#pragma unroll 1
+    for (int m = 0; m < 2; ++m) {
+      mbar_wait(bars + kBD3 + m, 0);
+      tc_fence_after();
+      PSX_TCTICK(0, 15 + 2 * m)
+      uint32_t v[32];
+      tmem_ld32(tlane + 128 * m + 32 * cq, v);
+      // rows above (tile 0) / below (tile 1) the image: K blocks 0..2 / 35..37 of A4
+      zero_fill(op + (m == 0 ? 0 : 35) * kKc, 3 * kKc, tid);
       tmem_ld_wait();
-      tmem_ld32(ta + 32, v1);
-      uint4 hi[4], lo[4];
-      split32(v0, bsc.z, hi, lo);
+      mbar_wait_cluster(bars + kBA2 + m, 0);  // this CTA's A3 halo copy of tile m has left its source blocks
+      const int kp = 128 * m + ml + kTcPad;
+      uint8_t* d = op + (kp >> 3) * kKc + (4 * cq) * 128 + (kp & 7) * 16;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        *reinterpret_cast<uint4*>(d + g * 128) = hi[g];
-        *reinterpret_cast<uint4*>(d + G::LO_ROW + g * 128) = lo[g];
+        uint4 hi, lo;
+        split8(v + 8 * g, inv_scale, hi, lo);
+        st_piece(d + g * 128, hi, lo);
       }
-      if (rem) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          st_cluster_v4(rd + g * 128, hi[g]);
-          st_cluster_v4(rd + G::LO_ROW + g * 128, lo[g]);
-        }
-      }
-      tmem_ld_wait();
-      split32(v1, bsc.z, hi, lo);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        *reinterpret_cast<uint4*>(d + (4 + g) * 128) = hi[g];
-        *reinterpret_cast<uint4*>(d + G::LO_ROW + (4 + g) * 128) = lo[g];
-      }
-      if (rem) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          st_cluster_v4(rd + (4 + g) * 128, hi[g]);
-          st_cluster_v4(rd + G::LO_ROW + (4 + g) * 128, lo[g]);
-        }
-      }
-      // columns beyond the image border: zero K core columns on the outer side
-      uint4* z = reinterpret_cast<uint4*>(op + (rank == 0 ? 0 : G::COL_BYTES));
-      for (int idx = tid; idx < G::HALO_BYTES / 16; idx += kTcEpi) z[idx] = make_uint4(0, 0, 0, 0);
+      tc_fence_before();
+      fence_async_smem();
+      warp_arrive(bars + kBE3 + m, lane);
+      PSX_TCTICK(0, 16 + 2 * m)
     }
-    tc_fence_before();
-    fence_async_all();
-    cluster_arrive_release();  // #2: halo written
-    mbar_arrive(full + 3);
-    PSX_TCTICK(0, 9)
 
     // |r|^2 of this CTA's half plane -> its partial-sum slots (the epilogue warps only)
     asm volatile("bar.sync 1, %0;" ::"n"(kTcEpi) : "memory");
@@ -422,57 +545,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         for (int i = 0; i < kTcWarps; ++i) tot += red[i];
       err_part[plane * pp + rank * (pp / 2) + tid] = tot;
     }
-    cluster_wait_acquire();  // #2
-    PSX_TCTICK(0, 10)
 
     // ------------------------------------------------------------------------------------ E4: cot
-    mbar_wait(done + 3, 0);
-    tc_fence_after();
-    PSX_TCTICK(0, 11)
+    // lane = own column, accumulator columns = image rows: every store instruction writes one 128-byte line
     {
-      const uint32_t ta = tb + ((uint32_t)(32 * q) << 16) + 256 + 64 * cq;
-      uint8_t* stage = op + warp * 8192;  // 32 rows x 64 columns fp32 per warp, 16-byte chunks XOR-swizzled by row
-      const float sc = bsc.w * coef * (1.f / kTcRScale);
-      uint32_t v0[32], v1[32];
-      tmem_ld32(ta, v0);
-      tmem_ld_wait();
-      tmem_ld32(ta + 32, v1);
+      const float sc = inv_scale * coef * (1.f / kTcRScale);
+      float* cp = cot + plane * (int64_t)(kTcN * kTcN) + j0 + ml;
+#pragma unroll 1
+      for (int qq = 0; qq < 4; ++qq) {
+        mbar_wait(bars + kBD4 + qq, 0);
+        tc_fence_after();
+        PSX_TCTICK(0, 19 + 2 * qq)
+        const int i0 = 64 * qq + 16 * cq;
+        uint32_t v[16];
+        tmem_ld16(tlane + 256 + i0, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 o = make_float4(__uint_as_float(v0[4 * g]) * sc, __uint_as_float(v0[4 * g + 1]) * sc,
-                                     __uint_as_float(v0[4 * g + 2]) * sc, __uint_as_float(v0[4 * g + 3]) * sc);
-        *reinterpret_cast<float4*>(stage + lane * 256 + ((g ^ (lane & 7)) * 16)) = o;
-      }
-      tmem_ld_wait();
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 o = make_float4(__uint_as_float(v1[4 * g]) * sc, __uint_as_float(v1[4 * g + 1]) * sc,
-                                     __uint_as_float(v1[4 * g + 2]) * sc, __uint_as_float(v1[4 * g + 3]) * sc);
-        *reinterpret_cast<float4*>(stage + lane * 256 + (((8 + g) ^ (lane & 7)) * 16)) = o;
-      }
-      __syncwarp();
-      // two rows (2 x 256 B) per warp instruction
-      const int hr = lane >> 4, cc = lane & 15;
-      float* cp = cot + plane * (int64_t)(kTcN * kTcN) + (int64_t)(128 * (cq >> 1) + 32 * q + hr) * kTcN + j0 +
-                  64 * (cq & 1) + 4 * cc;
-#pragma unroll 4
-      for (int r2 = 0; r2 < 16; ++r2) {
-        const int rr = 2 * r2 + hr;
-        const float4 o = *reinterpret_cast<const float4*>(stage + rr * 256 + ((cc ^ (rr & 7)) * 16));
-        st_stream4(cp + (2 * r2) * kTcN, o);
+        for (int e = 0; e < 16; ++e) __stcs(cp + (i0 + e) * kTcN, __uint_as_float(v[e]) * sc);
+        PSX_TCTICK(0, 20 + 2 * qq)
       }
     }
-    PSX_TCTICK(0, 12)
   }
+  // Every bulk copy into this CTA and every remote arrival on its barriers is awaited by one of its own waits above
+  // (H1 / H2 before P2 / P3, F1 / F2 before the copies, A1 / A2 before the copied blocks are rewritten), and the A
+  // acknowledgements also say that this CTA's own outgoing copies have been read out of its shared memory: nothing
+  // of or for the neighbour can still be in flight here.
   tc_fence_before();
   __syncthreads();
-  PSX_TCTICK(0, 13)
+  PSX_TCTICK(0, 27)
+  PSX_TCCLOCK(31)
   if (warp == kTcWarps) tmem_dealloc<512>(tb);
 }
 
 // ------------------------------------------------------------------------------------------ host: Toeplitz block image
-// B[n][k] = scale * tap[(k - PAD) - n - lo] for the pass whose 1-D operation is out[p] = sum_i w[i] in[p + lo + i]
-// (psx::Taps), as fp16 hi / lo in the shared-memory image [K core column][16 N groups: hi 0-7, lo 8-15][8 x 8 core].
+// Bw[n'][k'] = scale * tap[k' - n' + PAD - lo] for the pass whose 1-D operation is out[p] = sum_i w[i] in[p + lo + i]
+// (psx::Taps), as fp16 hi / lo in the shared-memory image [K core column (2)][hi: 8 N groups | lo: 8 N groups][8 x 8].
 bool taps_extent(const Taps& t, int& lo_off, int& hi_off) {
   int a = -1, b = -1;
   for (int i = 0; i < t.k; ++i)
@@ -486,12 +593,11 @@ bool taps_extent(const Taps& t, int& lo_off, int& hi_off) {
   return true;
 }
 
-void build_image(const Taps& t, int pad, float scale, std::vector<uint8_t>& img) {
-  const int KW = kTcNT + 2 * pad;
-  img.assign((size_t)(KW / 8) * 2048, 0);
-  for (int n = 0; n < kTcNT; ++n)
-    for (int k = 0; k < KW; ++k) {
-      const int ti = (k - pad) - n - t.lo;
+void build_image(const Taps& t, float scale, std::vector<uint8_t>& img) {
+  img.assign(kBBytes, 0);
+  for (int n = 0; n < 64; ++n)
+    for (int k = 0; k < 16; ++k) {
+      const int ti = k - n + kTcPad - t.lo;
       const float w = (ti >= 0 && ti < t.k) ? t.ww[ti].x * scale : 0.f;
       const __half h = __float2half_rn(w);
       const __half l = __float2half_rn(w - __half2float(h));
@@ -517,14 +623,13 @@ void tcblur_plan(psx_op* op) {
     need = std::max(need, std::max(-a, b));
     for (int i = 0; i < t->k; ++i) mx = std::fmax(mx, std::fabs(t->ww[i].x));
   }
-  const int pad = (need + 7) & ~7;
-  if (pad != 24) return;  // instantiated window: radius 17 .. 24 (the 61-tap sigma = 3 Gaussian prunes to 19)
+  if (need > kTcPad) return;  // the 64-wide window of a K-step covers tap offsets up to +-24 (61-tap sigma = 3: 19)
   if (!(mx > 0.f) || !std::isfinite(mx)) return;
   int e = 0;
-  std::frexp(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
+  std::frexp(mx, &e);                           // mx = f * 2^e, f in [0.5, 1)
   const float scale = std::ldexp(1.f, 10 - e);  // largest tap -> [512, 1024)
   std::vector<uint8_t> img[4];
-  for (int p = 0; p < 4; ++p) build_image(*ts[p], pad, scale, img[p]);
+  for (int p = 0; p < 4; ++p) build_image(*ts[p], scale, img[p]);
   for (int p = 1; p < 4; ++p)
     if (img[p] != img[0]) return;  // one resident block: symmetric taps, the same for rows and columns
   void* d = nullptr;
@@ -535,7 +640,7 @@ void tcblur_plan(psx_op* op) {
     return;
   }
   op->d_tc_img = (uint8_t*)d;
-  op->tc_pad = pad;
+  op->tc_pad = kTcPad;
   op->tc_inv_scale = 1.f / scale;
 }
 
@@ -550,20 +655,18 @@ bool tcblur_available(const psx_op* op) { return op->tc_pad != 0 && op->err_part
 int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                           int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot,
                           float* err_part, cudaStream_t st) {
-  using G = TcGeo<24>;
   static bool attr = false;
   if (!attr) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(blur_k1_tc<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM),
+    if (int rc = check_cuda(cudaFuncSetAttribute(blur_k1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem),
                             "blur_k1_tc attribute"))
       return rc;
     attr = true;
   }
   const int64_t planes = L * op->C;
   const float coef = (float)((double)w / (double)sa);
-  const float s = op->tc_inv_scale;
-  blur_k1_tc<24><<<(unsigned)(planes * 2), kTcThreads, G::SMEM, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
-                                                                       make_float4(s, s, s, s), op->C, obs_repeat,
-                                                                       op->err_parts / op->C, sa, s1, coef, dsc);
+  blur_k1_tc<<<(unsigned)(planes * 2), kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
+                                                                   op->tc_inv_scale, op->C, obs_repeat,
+                                                                   op->err_parts / op->C, sa, s1, coef, dsc);
   return check_cuda(cudaGetLastError(), "blur_k1_tc launch");
 }
 

@@ -24,3 +24,22 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def psx_env(monkeypatch):
+    """psx_env(NAME=value, OTHER=None) sets / clears libpsx's PSX_* kernel-selection switches and has the library read
+    them again (it caches them at the first launch, include/psx.h: psx_reload_env); undone after the test."""
+    from samplers_b200 import _native
+
+    def apply(**kv):
+        for k, v in kv.items():
+            if v is None:
+                monkeypatch.delenv(k, raising=False)
+            else:
+                monkeypatch.setenv(k, str(v))
+        _native.reload_env()
+
+    yield apply
+    monkeypatch.undo()
+    _native.reload_env()

@@ -90,13 +90,12 @@ def test_k1_box_bf16_is_the_rounded_fp32_kernel(shape):
 
 @pytest.mark.parametrize("shape,ksize,split", [((3, 256, 256), 61, None), ((3, 256, 256), 61, "2"), ((1, 512, 512), 61, None),
                                                ((2, 64, 96), 9, None)])
-def test_k1_blur_bf16_is_the_rounded_fp32_kernel(monkeypatch, shape, ksize, split):
-    """Separable blur on a bf16 state: bf16 x_t / eps in, fp32 intermediates, bf16 cotangent out."""
+def test_k1_blur_bf16_is_the_rounded_fp32_kernel(psx_env, shape, ksize, split):
+    """Separable blur on a bf16 state: bf16 x_t / eps in, fp32 intermediates, bf16 cotangent out.  The identity is
+    between the bf16 strip kernels and the fp32 strip kernels (PSX_NO_TC: the fp32 default for 256 x 256 planes is the
+    tensor-core kernel, a different summation order)."""
     from samplers_b200 import _native, operators as P
-    if split:
-        monkeypatch.setenv("PSX_SPLIT", split)
-    else:
-        monkeypatch.delenv("PSX_SPLIT", raising=False)
+    psx_env(PSX_SPLIT=split, PSX_NO_TC="1")
     op = P.GaussianBlurOperator(shape, ksize, 3.0 if ksize == 61 else 1.5).to(DEV)
     nat = op._native_cached(torch.device(DEV))
     L, n = 4, nat.n

@@ -104,13 +104,14 @@ def test_blur_heights_between_128_and_256_regression():
 @pytest.mark.parametrize("kind,env", [("identity", None), ("mask", None), ("box", None), ("blur", None),
                                       ("blur", "PSX_NO_FAST16"), ("blur", "PSX_NO_PIPE"), ("blur", "PSX_SPLIT"),
                                       ("sep", None), ("sep", "PSX_NO_FAST16"), ("motion", None)])
-def test_random_geometries(monkeypatch, kind, env):
+def test_random_geometries(psx_env, kind, env):
     from samplers_b200 import _native
     torch.backends.cudnn.allow_tf32 = False
-    for k in ("PSX_NO_FAST16", "PSX_NO_PIPE", "PSX_SPLIT", "PSX_FUSED", "PSX_PSF_FORM"):
-        monkeypatch.delenv(k, raising=False)
+    psx_env(PSX_NO_FAST16=None, PSX_NO_PIPE=None, PSX_SPLIT=None, PSX_FUSED=None, PSX_PSF_FORM=None, PSX_NO_TC=None)
     if env:
-        monkeypatch.setenv(env, "2")     # any value switches the NO_* paths; PSX_SPLIT=2 forces two sample groups
+        # any value switches the NO_* paths; PSX_SPLIT=2 forces two sample groups.  These are switches of the CUDA-core
+        # strip kernels: keep the tensor-core kernel (which 256 x 256 planes would take first) out of the way.
+        psx_env(**{env: "2", "PSX_NO_TC": "1"})
     gen = torch.Generator(device=DEV).manual_seed(sum(map(ord, kind)))
     for c, h, w, L, extra in _cases(kind, 40 if kind != "sep" else 30, seed=len(kind)):
         shape = (c, h, w)
@@ -357,8 +358,10 @@ def test_random_geometries_bf16_state_is_the_rounded_fp32_path():
         n = nat.n
         tag = f"case {case}: {kind} {(c, h, w)} L={L}"
         os.environ.pop("PSX_SPLIT", None)
+        os.environ["PSX_NO_TC"] = "1"   # the rounding identity is between the bf16 and the fp32 strip kernels
         if kind == "blur" and L % 2 == 0 and L >= 4 and rng.random() < 0.5:
             os.environ["PSX_SPLIT"] = "2"
+        _native.reload_env()
         try:
             x, e, v, z = (torch.randn(L, n, device=DEV, generator=gen).to(BF) for _ in range(4))
             y = torch.randn(1, nat.n_y, device=DEV, generator=gen)
@@ -380,6 +383,8 @@ def test_random_geometries_bf16_state_is_the_rounded_fp32_path():
             assert torch.equal(o16, o32.to(BF)), tag
         finally:
             os.environ.pop("PSX_SPLIT", None)
+            os.environ.pop("PSX_NO_TC", None)
+            _native.reload_env()
 
 
 def test_random_pgdm_runs():

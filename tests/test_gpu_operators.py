@@ -147,8 +147,8 @@ def test_full_size_k1_consistent_with_standalone_kernels():
         assert rel_err(part.sum(1).cpu(), r.double().square().sum(1).float().cpu()) < 1e-5, type(op).__name__
 
 
-def test_cluster_fused_blur_k1_matches_three_launch_path(monkeypatch):
-    """The opt-in single-launch cluster/DSMEM kernel (PSX_FUSED=1) against the default three-launch K1."""
+def test_cluster_fused_blur_k1_matches_three_launch_path(psx_env):
+    """The opt-in single-launch cluster/DSMEM CUDA-core kernel (PSX_FUSED=1) against the three-launch strip kernels."""
     from samplers_b200 import _native, operators as pops
     op = pops.GaussianBlurOperator(FULL).to(DEV)
     nat = op._native_cached(torch.device(DEV))
@@ -160,10 +160,7 @@ def test_cluster_fused_blur_k1_matches_three_launch_path(monkeypatch):
     ws = torch.empty(nat.workspace_bytes(L) // 4, device=DEV)
     outs = []
     for fused in (False, True):
-        if fused:
-            monkeypatch.setenv("PSX_FUSED", "1")
-        else:
-            monkeypatch.delenv("PSX_FUSED", raising=False)
+        psx_env(PSX_FUSED="1" if fused else None, PSX_NO_TC="1")
         cot, part = torch.empty_like(x), torch.empty(L, nat.err_parts, device=DEV)
         _native.dps_pre(nat, x, eps, y, L, 0.8, 0.6, 400.0, cot, part, ws)
         outs.append((cot.clone(), part.sum(1).clone()))
@@ -201,13 +198,13 @@ def test_blur_k1_on_planes_up_to_512_matches_oracle(shape, taps, L):
 
 
 @pytest.mark.parametrize("env", [{}, {"PSX_SPLIT": "2"}, {"PSX_SPLIT": "4"}, {"PSX_NO_FAST16": "1"}, {"PSX_NO_PIPE": "1"},
-                                 {"PSX_FUSED": "1"}])
-def test_every_blur_k1_code_path_gives_the_same_answer(monkeypatch, env):
-    """The default strip kernels, the multi-group schedule, the 8-output pipelined kernels, the one-tile-per-CTA
-    kernels and the cluster kernel are five implementations of one function."""
+                                 {"PSX_FUSED": "1"}, {"PSX_NO_TC": None}])
+def test_every_blur_k1_code_path_gives_the_same_answer(psx_env, env):
+    """The tensor-core kernel (the default for 256 x 256 planes; the last case), the strip kernels, the multi-group
+    schedule, the 8-output pipelined kernels, the one-tile-per-CTA kernels and the cluster kernel are six
+    implementations of one function.  The base is the strip-kernel path (PSX_NO_TC)."""
     from samplers_b200 import _native, operators as pops
-    for k in ("PSX_SPLIT", "PSX_NO_FAST16", "PSX_NO_PIPE", "PSX_FUSED"):
-        monkeypatch.delenv(k, raising=False)
+    psx_env(PSX_SPLIT=None, PSX_NO_FAST16=None, PSX_NO_PIPE=None, PSX_FUSED=None, PSX_NO_TC="1")
     op = pops.GaussianBlurOperator(FULL).to(DEV)
     nat = op._native_cached(torch.device(DEV))
     L = 8
@@ -224,8 +221,7 @@ def test_every_blur_k1_code_path_gives_the_same_answer(monkeypatch, env):
         return cot, part.sum(1)
 
     base = run()
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+    psx_env(**env)
     got = run()
     if "PSX_SPLIT" in env:                  # same kernels, same tiles per sample: bit-identical
         assert torch.equal(got[0], base[0]) and torch.equal(got[1], base[1])

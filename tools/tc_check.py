@@ -68,6 +68,7 @@ def main():
                 os.environ["PSX_NO_TC"] = env
             else:
                 os.environ.pop("PSX_NO_TC", None)
+            _native.reload_env()
             cot, err = run(nat, x, eps, y, L, sa, s1, w, obs_repeat)
             e_cot = ((cot.double() - rc).norm() / rc.norm()).item()
             e_max = ((cot.double() - rc).abs().max() / rc.abs().max()).item()
@@ -90,6 +91,7 @@ def main():
                 os.environ["PSX_NO_TC"] = env
             else:
                 os.environ.pop("PSX_NO_TC", None)
+            _native.reload_env()
 
             def k1(i):
                 d = S[i]
