@@ -47,6 +47,9 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.relaxed.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
                "r"(bytes)
@@ -103,6 +106,28 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
 // the sender is not held up (profiles/r02_dsmem_probe.txt)
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t caddr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+// non-blocking tests of phase 0.  The cluster-scope acquire is for barriers that a peer CTA's bulk copy completes
+// (the data it guards was written from outside this CTA); it is several times more expensive than the CTA-scope
+// one, which matters in a polling loop.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar))
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_cluster(uint64_t* bar) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], 0;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar))
+      : "memory");
+  return ok != 0;
 }
 // arrive (release at cluster scope) on a barrier in a peer CTA; `caddr` is a shared::cluster address (mapa)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t caddr) {
@@ -216,6 +241,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void st_cluster_v4(uint32_t caddr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+// for threads that have written nothing the other CTA will read (also: a release would wait for their loads in flight)
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void cluster_arrive_release() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");

@@ -55,12 +55,24 @@ def main():
     op = pops.GaussianBlurOperator((3, 256, 256), 61, 3.0).to(dev)
     nat = op._native_cached(dev)
     worst = 0.0
+    # yscale None: the observation of a late timestep, y = A x0 + N(0, 0.05^2) (residual at the noise level);
+    # sa = 0.00633: the first timestep of the 1000-step schedule (x0 and the residual are O(1 / sa))
     for (L, obs_repeat, sa, s1, w, yscale) in [(1, 1, 0.8, 0.6, 400.0, 1.0), (2, 2, 0.05, 0.998, 400.0, 1.0),
-                                              (16, 16, 0.9, 0.43, 25.0, 1.0), (5, 1, 0.999, 0.03, 400.0, 1.0)]:
+                                              (16, 16, 0.9, 0.43, 25.0, 1.0), (5, 1, 0.999, 0.03, 400.0, 1.0),
+                                              (4, 4, 0.00633, 0.99998, 400.0, 1.0), (3, 1, 0.9995, 0.0316, 400.0, None),
+                                              (2, 1, 1.0, 0.0, 1.0, None)]:
         n = nat.n
         x = torch.randn(L, n, device=dev, generator=gen)
         eps = torch.randn(L, n, device=dev, generator=gen)
-        y = torch.randn(L // obs_repeat, nat.n_y, device=dev, generator=gen) * yscale
+        if yscale is None:
+            C, H, W = op.x_shape
+            k = op.taps_h.double().to(dev)
+            R = k.numel() // 2
+            x0 = ((x.double() - s1 * eps.double()) / sa).view(L * C, 1, H, W)
+            ax = F.conv2d(F.conv2d(x0, k.view(1, 1, 1, -1), padding=(0, R)), k.view(1, 1, -1, 1), padding=(R, 0))
+            y = (ax.view(L, n) + 0.05 * torch.randn(L, n, device=dev, generator=gen, dtype=torch.float64)).float()
+        else:
+            y = torch.randn(L // obs_repeat, nat.n_y, device=dev, generator=gen) * yscale
         rc, re = ref64(op, x, eps, y, sa, s1, w, obs_repeat)
         out = {"L": L, "obs_repeat": obs_repeat, "sa": sa}
         for name, env in (("cuda_core", "1"), ("tc", None)):
