@@ -252,6 +252,12 @@ PSX_API int psx_bridge_update(const float* d_x, const float* d_eps, const float*
  * block around psx_dps_pre: x_eff = x0 + A^T(y - A x0) (psld.py:132-136) and its cotangent. */
 PSX_API int psx_lincomb3(const float* d_a, float ca, const float* d_b, float cb, const float* d_c, float cc,
                          float* d_out, int64_t numel, void* stream);
+/* psx_lincomb3_dev -- the same with the third coefficient completed ON THE DEVICE: cc * (*d_num) / (*d_den)
+ * (d_den may be NULL = 1; a zero denominator switches the term off).  The cotangent of a batch-global norm,
+ * -(c / ||r||) * A^T r (autograd mirror of torch.norm, psld.py:130,138, resample_kernels.py:27), has both factors
+ * in device memory: the sampling loop stays free of host synchronisation. */
+PSX_API int psx_lincomb3_dev(const float* d_a, float ca, const float* d_b, float cb, const float* d_c, float cc,
+                             const float* d_num, const float* d_den, float* d_out, int64_t numel, void* stream);
 
 /* ------------------------------------------------------------- ReSample
  * psx_ddim_eps_step -- DDIM update in the eps parameterisation (bridge_kernels.py:82-115), three outputs:

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "psx_tweedie": (C.c_int, [_f32p, _f32p, _i64, _i64, _f, _f, _f32p, _f32p, _f32p, _vp]),
     "psx_bridge_update": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, _f, _f32p, _vp]),
     "psx_lincomb3": (C.c_int, [_f32p, _f, _f32p, _f, _f32p, _f, _f32p, _i64, _vp]),
+    "psx_lincomb3_dev": (C.c_int, [_f32p, _f, _f32p, _f, _f32p, _f, _f32p, _f32p, _f32p, _i64, _vp]),
     "psx_ddim_eps_step": (C.c_int, [_f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, _f, _f32p, _f32p, _f32p, _vp]),
     "psx_stochastic_resample": (C.c_int, [_f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f32p, _vp]),
     "psx_adamw_step": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f, _f, _f, _f, _f, C.c_int, _vp, C.c_int,
@@ -371,6 +372,15 @@ def lincomb3(a, ca: float, b, cb: float, c, cc: float, out) -> None:
     with torch.cuda.device(a.device):
         check(load().psx_lincomb3(a.data_ptr(), ca, b.data_ptr(), cb, ptr(c), cc, out.data_ptr(), a.numel(),
                                   stream_ptr(a.device)))
+    launch_count += 1
+
+
+def lincomb3_dev(a, ca: float, b, cb: float, c, cc: float, num, den, out) -> None:
+    """out = ca*a + cb*b + (cc * num / den) * c with `num`, `den` 0-dim CUDA tensors (den may be None)."""
+    global launch_count
+    with torch.cuda.device(a.device):
+        check(load().psx_lincomb3_dev(a.data_ptr(), ca, b.data_ptr(), cb, c.data_ptr(), cc, num.data_ptr(), ptr(den),
+                                      out.data_ptr(), a.numel(), stream_ptr(a.device)))
     launch_count += 1
 
 

@@ -46,7 +46,8 @@ int launch_image_from_u8(const uint8_t*, float*, int64_t, int, int64_t, cudaStre
 int launch_gather(bool, const float*, const int64_t*, float*, int64_t, int64_t, int64_t, cudaStream_t);
 int launch_bridge_update(const float*, const float*, const float*, const float*, int64_t, float, float, float,
                          float, float, float, float*, cudaStream_t);
-int launch_lincomb3(const float*, float, const float*, float, const float*, float, float*, int64_t, cudaStream_t);
+int launch_lincomb3(const float*, float, const float*, float, const float*, float, float*, int64_t, cudaStream_t,
+                    const float* d_num = nullptr, const float* d_den = nullptr);
 int launch_ddim_eps(const float*, const float*, const float*, int64_t, float, float, float, float, float, float,
                     float*, float*, float*, cudaStream_t);
 int launch_stoch_resample(const float*, const float*, const float*, int64_t, float, float, float, float, float*,
@@ -558,6 +559,12 @@ PSX_API int psx_lincomb3(const float* d_a, float ca, const float* d_b, float cb,
                          float* d_out, int64_t numel, void* stream) {
   PSX_REQUIRE(d_a && d_b && d_out && numel > 0, "psx_lincomb3: null pointer or empty tensor");
   return launch_lincomb3(d_a, ca, d_b, cb, d_c, cc, d_out, numel, (cudaStream_t)stream);
+}
+
+PSX_API int psx_lincomb3_dev(const float* d_a, float ca, const float* d_b, float cb, const float* d_c, float cc,
+                             const float* d_num, const float* d_den, float* d_out, int64_t numel, void* stream) {
+  PSX_REQUIRE(d_a && d_b && d_c && d_num && d_out && numel > 0, "psx_lincomb3_dev: null pointer or empty tensor");
+  return launch_lincomb3(d_a, ca, d_b, cb, d_c, cc, d_out, numel, (cudaStream_t)stream, d_num, d_den);
 }
 
 PSX_API int psx_ddim_eps_step(const float* d_x, const float* d_eps, const float* d_z, int64_t numel,

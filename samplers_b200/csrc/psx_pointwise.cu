@@ -614,7 +614,14 @@ int launch_bridge_update(const float* x, const float* eps, const float* z, const
 template <bool HAS_C>
 __global__ void __launch_bounds__(kThreads)
 k_lincomb3(const float* __restrict__ a, float ca, const float* __restrict__ b, float cb,
-           const float* __restrict__ c, float cc, float* __restrict__ out, int64_t total) {
+           const float* __restrict__ c, float cc, float* __restrict__ out, int64_t total,
+           const float* __restrict__ d_num, const float* __restrict__ d_den) {
+  // device-side factor of cc (psx_lincomb3_dev): cc * num / den with torch's roundings (one multiply, one division);
+  // a zero denominator (a residual norm of exactly 0) switches the term off instead of producing inf / nan
+  if (d_num != nullptr) {
+    const float den = d_den != nullptr ? __ldg(d_den) : 1.f;
+    cc = den != 0.f ? __fdiv_rn(__fmul_rn(cc, __ldg(d_num)), den) : 0.f;
+  }
   const int64_t t4 = total >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 av = ld_stream4(a + 4 * i), bv = ld_stream4(b + 4 * i);
@@ -637,11 +644,11 @@ k_lincomb3(const float* __restrict__ a, float ca, const float* __restrict__ b, f
 }
 
 int launch_lincomb3(const float* a, float ca, const float* b, float cb, const float* c, float cc, float* out,
-                    int64_t total, cudaStream_t st) {
+                    int64_t total, cudaStream_t st, const float* d_num, const float* d_den) {
   int blocks = ceil_div(total / 4 + 1, kThreads);
   blocks = blocks > sm_count() * 8 ? sm_count() * 8 : blocks;
-  if (c) k_lincomb3<true><<<blocks, kThreads, 0, st>>>(a, ca, b, cb, c, cc, out, total);
-  else k_lincomb3<false><<<blocks, kThreads, 0, st>>>(a, ca, b, cb, c, cc, out, total);
+  if (c) k_lincomb3<true><<<blocks, kThreads, 0, st>>>(a, ca, b, cb, c, cc, out, total, d_num, d_den);
+  else k_lincomb3<false><<<blocks, kThreads, 0, st>>>(a, ca, b, cb, c, cc, out, total, d_num, d_den);
   return check_cuda(cudaGetLastError(), "lincomb3 launch");
 }
 

@@ -80,22 +80,25 @@ class PosteriorSummary:
 def combine_posterior(local_slot: Tensor, gathered: Tensor, total: Tensor, total_sq: Tensor, counts: list[int],
                       group=None) -> PosteriorSummary:
     """Terminal exchange.  ``gathered`` is (world * max_count, n); this rank already wrote its samples into
-    rows [rank * max_count, rank * max_count + counts[rank]) (``local_slot`` is that view).  ``total`` /
-    ``total_sq`` are this rank's per-pixel sum and sum of squares and are reduced in place."""
+    rows [rank * max_count, rank * max_count + counts[rank]) (``local_slot`` is that view).  ``total`` is this rank's
+    per-pixel sum (from the final-estimate kernel) and is all-reduced to the posterior mean.  The variance is the
+    two-pass form about that mean, sum((x - mean)^2) / (R - 1) over the gathered samples: the one-pass
+    (sum x^2 - R mean^2) cancels catastrophically for a converged posterior (spread << mean), so ``total_sq`` is
+    accepted for compatibility but not used."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     max_count = max(counts)
     if world > 1:
         dist.all_gather_into_tensor(gathered, gathered.view(world, max_count, -1)[dist.get_rank(group)].contiguous(),
                                     group=group)
-        moments = torch.stack([total, total_sq])
-        dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
-        total, total_sq = moments[0], moments[1]
+        total = total.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     rows = [gathered.view(world, max_count, -1)[r, : counts[r]] for r in range(world)]
     samples = torch.cat(rows, dim=0)
     n_tot = float(sum(counts))
     mean = total / n_tot
-    var = (total_sq - n_tot * mean * mean) / max(n_tot - 1.0, 1.0)
-    return PosteriorSummary(samples=samples, mean=mean, variance=var.clamp_min_(0))
+    # every rank holds all samples after the gather: the second pass needs no further exchange
+    var = (samples - mean).square_().sum(0) / max(n_tot - 1.0, 1.0)
+    return PosteriorSummary(samples=samples, mean=mean, variance=var)
 
 
 def sample_posterior(sampler, inverse_problem, *, num_reconstructions: int, num_sampling_steps: int = 50,

@@ -288,10 +288,12 @@ class OfflineSDPipeline:
 
 @dataclasses.dataclass(slots=True)
 class StableDiffusionCondition:
-    """The fields of the reference's condition object that can be honoured without a text encoder."""
+    """The fields of the reference's condition object that can be honoured without a text encoder.  Defaults as in the
+    reference (networks/diffusers/stable_diffusion.py:16-28): classifier-free guidance is ON (7.5) unless the caller
+    passes guidance_scale <= 1."""
     prompt: str | list[str] = ""
     negative_prompt: str | list[str] | None = None
-    guidance_scale: float = 1.0
+    guidance_scale: float = 7.5
     guidance_rescale: float = 0.0
     prompt_embeds: Tensor | None = None            # (B or 1, context_len, context_dim)
     negative_prompt_embeds: Tensor | None = None

@@ -62,9 +62,9 @@ class _PsldDataTerm(torch.autograd.Function):
         neg_ata_c = torch.empty_like(c)
         part = torch.empty((L, ctx.op.err_parts), device=c.device, dtype=torch.float32)
         _native.dps_pre(ctx.op, c, c, zeros_y, L, 1.0, 0.0, 1.0, neg_ata_c, part, ctx.ws)  # A^T(0 - A c)
-        kappa = -(c_lik / lik)
         out = torch.empty_like(c)
-        _native.lincomb3(c, 1.0, neg_ata_c, 1.0, atr, float(kappa), out)
+        # -(c_lik / lik) * A^T r with both factors read on the device (no host synchronisation in the loop)
+        _native.lincomb3_dev(c, 1.0, neg_ata_c, 1.0, atr, -1.0, c_lik.float().contiguous(), lik, out)
         return out, None, None, None, None, None, None
 
 

@@ -61,13 +61,15 @@ class _ResidualTerm(torch.autograd.Function):
     forward (partials + A^T r), one scaling backward."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, op, y: Tensor, obs_repeat: int, ws, mode: str, group=None):
+    def forward(ctx, x: Tensor, op, y: Tensor, obs_repeat: int, ws, mode: str, group=None, n_obs=None):
+        # n_obs: observed values per sample as the reference's nn.MSELoss counts them (prod(operator.y_shape): the m
+        # kept pixels of a flattened inpainting operator, not the n entries of the dense-mask form the kernels use)
         L = x.shape[0]
         atr = torch.empty_like(x)
         part = torch.empty((L, op.err_parts), device=x.device, dtype=torch.float32)
         _native.dps_pre(op, x, x, y, obs_repeat, 1.0, 0.0, 1.0, atr, part, ws)
         e2 = reduce_sum_(part.sum(), group)             # batch-global over all ranks of `group`
-        count = float(L * op.n_y) * group_size(group)   # equal shards
+        count = float(L * (op.n_y if n_obs is None else n_obs)) * group_size(group)   # equal shards
         val = e2.sqrt() if mode == "norm" else e2 / count
         ctx.mode, ctx.count = mode, count
         ctx.save_for_backward(atr, val)
@@ -76,10 +78,14 @@ class _ResidualTerm(torch.autograd.Function):
     @staticmethod
     def backward(ctx, c: Tensor):
         atr, val = ctx.saved_tensors
-        kappa = -(c / val) if ctx.mode == "norm" else -(2.0 / ctx.count) * c
         out = torch.empty_like(atr)
-        _native.lincomb3(atr, float(kappa), atr, 0.0, None, 0.0, out)
-        return out, None, None, None, None, None, None
+        c = c.float().contiguous()
+        # kappa * A^T r, kappa = -(c / val) or -(2 / count) * c, completed on the device (no host synchronisation)
+        if ctx.mode == "norm":
+            _native.lincomb3_dev(atr, 0.0, atr, 0.0, atr, -1.0, c, val, out)
+        else:
+            _native.lincomb3_dev(atr, 0.0, atr, 0.0, atr, -2.0 / ctx.count, c, None, out)
+        return out, None, None, None, None, None, None, None
 
 
 class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
@@ -93,14 +99,15 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
                 f"({type(self._epsilon_network).__name__}).")
 
     # ------------------------------------------------------------------ hard data consistency
-    def _pixel_optimization(self, nat, y, obs_repeat, ws, x_init: Tensor, eps: float, max_iters: int) -> Tensor:
+    def _pixel_optimization(self, nat, y, obs_repeat, ws, x_init: Tensor, eps: float, max_iters: int,
+                            n_obs=None) -> Tensor:
         L, n = x_init.shape
         x = x_init.detach().clone()
         m, v, grad = torch.zeros_like(x), torch.zeros_like(x), torch.empty_like(x)
         part = torch.empty((L, nat.err_parts), device=x.device, dtype=torch.float32)
         flags = torch.zeros(2, device=x.device, dtype=torch.int32)
         group = getattr(self, "process_group", None)
-        count = float(L * nat.n_y) * group_size(group)
+        count = float(L * (nat.n_y if n_obs is None else n_obs)) * group_size(group)   # resample_kernels.py:48 (MSELoss)
         for i in range(max_iters):
             # grad of mean((y - A x)^2) = -(2/N) A^T (y - A x); partials of |r|^2 in the same launch
             _native.dps_pre(nat, x, x, y, obs_repeat, 1.0, 0.0, -2.0 / count, grad, part, ws)
@@ -114,7 +121,7 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
         return x
 
     def _latent_optimization(self, net, nat, y, obs_repeat, ws, z_init: Tensor, x_shape, eps: float,
-                             max_iters: int) -> Tensor:
+                             max_iters: int, n_obs=None) -> Tensor:
         z = z_init.detach().clone()
         m, v = torch.zeros_like(z), torch.zeros_like(z)
         L = z.shape[0]
@@ -124,7 +131,7 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
             nd = getattr(self, "_net_dtype", torch.float32)
             x = net.decode(leaf if nd == torch.float32 else leaf.to(nd), differentiable=True).float()
             loss = _ResidualTerm.apply(x.reshape(L, nat.n).contiguous(), nat, y, obs_repeat, ws, "mse",
-                                       self.process_group)
+                                       self.process_group, n_obs)
             (g,) = torch.autograd.grad(loss, leaf)
             _native.adamw_step(z, g.contiguous(), m, v, 5e-3, itr + 1)
             cur = float(loss.detach())
@@ -169,6 +176,9 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
             def to_net(t: Tensor) -> Tensor:
                 return t if net_dtype == torch.float32 else t.to(net_dtype)
             nat = op._native_cached(device)
+            n_obs = 1
+            for d in op.y_shape:
+                n_obs *= int(d)
             y = op._dense_observation(inverse_problem.observation.to(device=device, dtype=torch.float32))
             obs_repeat = num_reconstructions if x_view.batch_size > 1 else L
             wsb = nat.workspace_bytes(L)
@@ -213,16 +223,16 @@ class ReSampleSampler(PosteriorSampler, Generic[Condition_co]):
                     c_p, c_x, den, k_n = resample_scalars(acp, t, tp, sigma_scale)
                     if idx >= index_split:
                         x_pix = net.decode(to_net(pseudo), differentiable=False).float().reshape(L, nat.n).contiguous()
-                        x_opt = self._pixel_optimization(nat, y, obs_repeat, ws, x_pix, eps, max_optimization_iters)
+                        x_opt = self._pixel_optimization(nat, y, obs_repeat, ws, x_pix, eps, max_optimization_iters, n_obs)
                         z_opt = net.encode(to_net(x_opt.view(L, *x_shape)), differentiable=False).float().contiguous()
                     else:
                         z_opt = self._latent_optimization(net, nat, y, obs_repeat, ws, pseudo, x_shape, eps,
-                                                          max_optimization_iters)
+                                                          max_optimization_iters, n_obs)
                     noise = self.draw(tuple(z.shape), device, dtype)
                     z = torch.empty_like(snapshot)
                     _native.stochastic_resample(z_opt, snapshot, noise, c_p, c_x, den, k_n, z)
 
-            z0 = self._latent_optimization(net, nat, y, obs_repeat, ws, z, x_shape, eps, max_optimization_iters)
+            z0 = self._latent_optimization(net, nat, y, obs_repeat, ws, z, x_shape, eps, max_optimization_iters, n_obs)
             if decode_output:
                 return x_view.unflatten(net.decode(to_net(z0), differentiable=False).float())
             return z_view.unflatten(z0)

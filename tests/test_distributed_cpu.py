@@ -27,12 +27,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, counts, n, q):
+def _draw(rank, count, n, offset, scale):
+    return offset + scale * torch.randn(count, n, generator=torch.Generator().manual_seed(100 + rank))
+
+
+def _worker(rank, world, port, counts, n, q, offset=0.0, scale=1.0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        g = torch.Generator().manual_seed(100 + rank)
-        local = torch.randn(counts[rank], n, generator=g)
+        local = _draw(rank, counts[rank], n, offset, scale)
         mx = max(counts)
         gathered = torch.zeros(world * mx, n)
         slot = gathered[rank * mx: rank * mx + counts[rank]]
@@ -56,12 +59,34 @@ def test_terminal_gather_and_moments_world2(counts):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    expected = torch.cat([torch.randn(counts[r], n, generator=torch.Generator().manual_seed(100 + r))
-                          for r in range(world)])
+    expected = torch.cat([_draw(r, counts[r], n, 0.0, 1.0) for r in range(world)])
     for _, samples, mean, var in results:  # every rank ends with the same, complete answer
         assert torch.equal(samples, expected)
         assert torch.allclose(mean, expected.mean(0), atol=1e-6)
         assert torch.allclose(var, expected.var(0, unbiased=True), atol=1e-5)
+
+
+def test_posterior_variance_of_a_converged_posterior_world2():
+    """256 samples with mean 0.9 and standard deviation 1e-3: sum(x^2) - R mean^2 has no correct digit left in fp32
+    (0.81 * 256 against a spread of 2.6e-4); the two-pass form keeps 4+ digits."""
+    world, n, counts = 2, 32, [128, 128]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, counts, n, q, 0.9, 1e-3)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expected = torch.cat([_draw(r, counts[r], n, 0.9, 1e-3) for r in range(world)]).double()
+    ref = expected.var(0, unbiased=True)
+    for _, samples, mean, var in results:
+        assert torch.allclose(mean.double(), expected.mean(0), atol=1e-6)
+        assert ((var.double() - ref).abs() / ref).max() < 1e-3
+    one_pass = (expected.float().square().sum(0) - 256 * expected.float().mean(0) ** 2) / 255
+    assert ((one_pass.double() - ref).abs() / ref).max() > 0.05   # what the previous formula delivered
 
 
 def test_combine_posterior_single_process():

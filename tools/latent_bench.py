@@ -52,13 +52,19 @@ def main():
                 return r
             return w
         setattr(_native, name, make(fn))
+    # classifier-free guidance is explicitly OFF here (no text conditioning in the synthetic workload): the API default,
+    # as in the reference, is 7.5, which doubles the UNet batch
+    from samplers_b200.networks.sd15 import StableDiffusionCondition
+    cond = StableDiffusionCondition(guidance_scale=1.0)
     if a.sampler == "psld":
         sampler = PSLDSampler(net)
-        call = lambda: sampler(prob, num_sampling_steps=a.steps + 2, num_reconstructions=a.batch, decode_output=False)
+        call = lambda: sampler(prob, num_sampling_steps=a.steps + 2, num_reconstructions=a.batch, decode_output=False,
+                               condition=cond)
     else:
         sampler = ReSampleSampler(net)
         call = lambda: sampler(prob, num_sampling_steps=a.steps + 2, num_reconstructions=a.batch, decode_output=False,
-                               max_optimization_iters=a.opt_iters, time_travel_interval=2, inter_timesteps=2)
+                               max_optimization_iters=a.opt_iters, time_travel_interval=2, inter_timesteps=2,
+                               condition=cond)
     for rep in range(2):    # first call warms cuDNN up
         spans.clear()
         torch.cuda.synchronize()
