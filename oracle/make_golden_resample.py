@@ -26,6 +26,11 @@ CASES = {
     "blur9_poisson": dict(shape=(3, 16, 16), steps=10, batch=(2,), R=1, op=("gblur", 9, 1.5), noise=("poisson", 4.0),
                           kw=dict(sigma_scale=10.0, max_optimization_iters=4, eta=0.5, inter_timesteps=3,
                                   time_travel_interval=3, stage_splits=2)),
+    # the reference's own InpaintingOperator (flatten=True): nn.MSELoss averages over the m KEPT pixels, which scales
+    # the optimisers' gradients and the `< eps^2` stop rule (resample_kernels.py:43-51,71-91)
+    "inpaint": dict(shape=(3, 16, 16), steps=10, batch=(), R=1, op=("mask", 0.7, 7), noise=("gaussian", 0.05),
+                    kw=dict(sigma_scale=40.0, max_optimization_iters=8, eta=1.0, inter_timesteps=2,
+                            time_travel_interval=2, stage_splits=3)),
 }
 
 
@@ -45,7 +50,12 @@ def run_case(name, cfg):
             out = oracle_op.apply(x.reshape(-1, *shape))
             return out.reshape(*lead, *out.shape[1:])
 
-    ref_op = ref.operators.IdentityOperator(x_shape=shape) if cfg["op"][0] == "identity" else _Wrapped(x_shape=shape)
+    if cfg["op"][0] == "identity":
+        ref_op = ref.operators.IdentityOperator(x_shape=shape)
+    elif cfg["op"][0] == "mask":
+        ref_op = ref.operators.InpaintingOperator(x_shape=shape, mask=torch.from_numpy(extra["mask"]))
+    else:
+        ref_op = _Wrapped(x_shape=shape)
     nk, nparam = cfg["noise"]
     noise = ref.noise.GaussianNoise(sigma=nparam) if nk == "gaussian" else ref.noise.PoissonNoise(rate=nparam)
     x_true = torch.rand((*cfg["batch"], *shape), generator=torch.Generator().manual_seed(0)) * 2 - 1

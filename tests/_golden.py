@@ -165,6 +165,8 @@ class PsldGolden:
             return oops.OracleSeparableBlur(self.shape, self.a["taps"])
         if spec[0] == "box":
             return oops.OracleBoxDownsample(self.shape, spec[1])
+        if spec[0] == "mask":
+            return oops.OracleMaskGather(self.shape, self.a["mask"])
         raise ValueError(spec)
 
     def y_flat(self, op):
@@ -220,6 +222,8 @@ def make_psld_problem(g: "PsldGolden", device):
         op = pops.IdentityOperator(shape)
     elif spec[0] == "gblur":
         op = pops.SeparableBlurOperator(shape, g["taps"])
+    elif spec[0] == "mask":
+        op = pops.InpaintingOperator(shape, g["mask"])
     else:
         op = pops.BoxDownsampleOperator(shape, spec[1])
     return InverseProblem(operator=op.to(device), observation=g["y"].to(device), noise=GaussianNoise(sigma=g.meta["sigma"]))
