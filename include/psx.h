@@ -59,6 +59,9 @@ PSX_API const char* psx_last_error(void);
  * (the tests and measurement tools do) calls this to have them read again.  No reference counterpart: the
  * reference has one code path per operator. */
 PSX_API void psx_reload_env(void);
+/* Number of CUDA kernels this library has launched in this process so far (a launch recorded into a CUDA graph
+ * counts once, when it is captured).  Measurement aid: bench.py's "gpu_launches" is a difference of two readings. */
+PSX_API long long psx_kernel_launches(void);
 
 /* ---------------------------------------------------------------- operators
  * Degradation operators A (forward) / A^T (adjoint).  Replaces

@@ -24,6 +24,7 @@ PROTOTYPES = {
     "psx_abi_version": (C.c_int, []),
     "psx_last_error": (C.c_char_p, []),
     "psx_reload_env": (None, []),
+    "psx_kernel_launches": (C.c_longlong, []),
     "psx_op_create_identity": (C.c_int, [_i64, C.POINTER(_opp)]),
     "psx_op_create_mask": (C.c_int, [_i64, _vp, C.POINTER(_opp)]),
     "psx_op_create_box": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_opp)]),
@@ -106,6 +107,11 @@ def load() -> C.CDLL:
                 raise RuntimeError("libpsx.so ABI version mismatch; rebuild with `python -m samplers_b200.build --force`")
             _lib = lib
     return _lib
+
+
+def kernel_launches() -> int:
+    """CUDA kernels launched by libpsx so far (graph captures count once)."""
+    return int(load().psx_kernel_launches())
 
 
 def reload_env() -> None:

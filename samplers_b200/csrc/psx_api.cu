@@ -19,8 +19,16 @@ int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
 }
+// Every kernel launch of the library is followed by exactly one check_cuda(cudaGetLastError(), "<kernel> launch"):
+// that is where the library counts its own launches (psx_kernel_launches; a launch recorded into a CUDA graph is
+// counted once, at capture).
+std::atomic<long long> g_kernel_launches{0};
 int check_cuda(cudaError_t e, const char* what) {
-  if (e == cudaSuccess) return PSX_OK;
+  if (e == cudaSuccess) {
+    const size_t n = std::strlen(what);
+    if (n >= 6 && std::strcmp(what + n - 6, "launch") == 0) g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    return PSX_OK;
+  }
   g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
   return PSX_ERR_CUDA;
 }
@@ -112,6 +120,7 @@ using namespace psx;
 extern "C" {
 
 PSX_API int psx_abi_version(void) { return PSX_ABI_VERSION; }
+PSX_API long long psx_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 PSX_API void psx_reload_env(void) {
   std::lock_guard<std::mutex> lock(g_env_mu);
   read_env();

@@ -200,8 +200,10 @@ class DPSRun:
         torch.cuda.synchronize(dev)
         torch.cuda.empty_cache()   # hand the warm-up's activation memory back before the graph's private pool grows
         graph = torch.cuda.CUDAGraph()
+        launches = _native.kernel_launches()
         with torch.cuda.graph(graph):
             self._timestep_body()
+        self.graph_kernel_launches = _native.kernel_launches() - launches   # libpsx kernels per replay
         self.x.copy_(keep)                               # capture does not execute, but keep this explicit
         self.k_dev.zero_()
         self._graph = graph
