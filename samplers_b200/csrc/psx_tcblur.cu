@@ -66,10 +66,17 @@ __device__ long long psx_trace_tc[1024 * 4 * 32];
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
     psx_trace_tc[(blockIdx.x * 4 + (role)) * 32 + (slot)] = t_;                            \
   }
+#define PSX_TCTICK_W0(slot)  /* epilogue warp 0 writing into role 3's slots 8.. */                         \
+  if (warp == 0 && lane == 0 && blockIdx.x < 1024) {                                          \
+    long long t_;                                                                          \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
+    psx_trace_tc[(blockIdx.x * 4 + 3) * 32 + (slot)] = t_;                                 \
+  }
 #define PSX_TCCLOCK(slot)                                                      \
   if (tid == 0 && blockIdx.x < 1024) psx_trace_tc[(blockIdx.x * 4) * 32 + (slot)] = clock64();
 #else
 #define PSX_TCTICK(role, slot)
+#define PSX_TCTICK_W0(slot)
 #define PSX_TCCLOCK(slot)
 #endif
 
@@ -255,6 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
         mbar_spin(bars + kBE1 + m, 0);
+        fence_async_smem();
         tc_fence_after();
         PSX_TCTICK(1, 15 + m)
         const uint32_t d = tb + 256 + 128 * m, am = a0 + (uint32_t)((m * kRpTile) >> 4);
@@ -287,6 +295,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
         mbar_spin(bars + kBE2 + m, 0);
+        fence_async_smem();
         tc_fence_after();
         PSX_TCTICK(1, 17 + m)
         const uint32_t d = tb + 128 * m, am = a0 + (uint32_t)((m * kRpTile) >> 4);
@@ -312,6 +321,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       }
       // ---- P4: V^T, K = rows; K-steps 1..7 read rows < 104 (tile 0) and write output rows < 128
       mbar_spin(bars + kBE3 + 0, 0);
+      fence_async_smem();
       tc_fence_after();
       PSX_TCTICK(1, 11)
       issue_clear(tb + 256, 128, z_s);
@@ -322,6 +332,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       });
       PSX_TCTICK(1, 12)
       mbar_spin(bars + kBE3 + 1, 0);
+      fence_async_smem();
       tc_fence_after();
       PSX_TCTICK(1, 13)
       issue_clear(tb + 384, 128, z_s);
@@ -345,6 +356,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       const uint32_t cop = mapa(smem_u32(op), peer), cbar = mapa(smem_u32(bars), peer);
       for (int m = 0; m < 2; ++m) {
         mbar_spin(bars + kBS1 + m, 0);
+        fence_async_smem();  // the source blocks were written through the generic proxy, the bulk copy reads through the async one
         PSX_TCTICK(2, 5 + m)
         mbar_spin(bars + kBF1 + m, 0);
         PSX_TCTICK(2, 1 + m)
@@ -352,6 +364,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       }
       for (int m = 0; m < 2; ++m) {
         mbar_spin(bars + kBS2 + m, 0);
+        fence_async_smem();
         PSX_TCTICK(2, 7 + m)
         mbar_spin(bars + kBF2 + m, 0);
         PSX_TCTICK(2, 3 + m)
@@ -433,6 +446,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     const float rscale = __int_as_float((__float_as_int(sa) & 0x7f800000) + (5 << 23));
     cluster_wait_acquire();  // #0
 
+    // the observation values of the first E2 task: requested now, needed ~2 us from here (nothing in between waits
+    // for this thread's loads: the proxy fences are on the consumers' side)
+    const int hfirst = rank == 0 ? 0 : 1;
+    const float* yrow = yplane + (int64_t)ml * kTcN + 16 * cq;
+    float4 ya, yb, yc, yd;
+    ld_nc8(yrow + 64 * hfirst, ya, yb);
+    ld_nc8(yrow + 64 * hfirst + 8, yc, yd);
+
     // ------------------------------------------------------------------------------------ E1: V x0 -> A2 (MN-major)
     // lane = own column jl, accumulator columns = image rows; tile m = rows 128 m .. 128 m + 127
     {
@@ -443,20 +464,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         mbar_wait(bars + kBD1 + m, 0);
         tc_fence_after();
         PSX_TCTICK(0, 3 + 2 * m)
-        uint32_t v[32];
-        tmem_ld32(tlane + 128 * m + 32 * cq, v);
+        // TMEM is read 8 columns at a time, the next chunk in flight while this one is split and stored (TMEM read,
+        // ALU and shared-memory stores are three different pipes: a task costs the longest, not the sum)
+        uint32_t va[8], vb[8];
+        const uint32_t tsrc = tlane + 128 * m + 32 * cq;
+        tmem_ld8(tsrc, va);
         // border side of the row-pass operand: K blocks 0..2 (rank 0) / 19..21 (rank 1) of tile m
         zero_fill(op + m * kRpTile + (rank == 0 ? 0 : kRpKc - 3) * kKc, 3 * kKc, tid);
-        tmem_ld_wait();
-        uint4 hi[4], lo[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) split8(v + 8 * g, inv_scale, hi[g], lo[g]);
         uint8_t* d = op + m * kRpTile + (3 + (jl >> 3)) * kKc + (4 * cq) * 128 + (jl & 7) * 16;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) st_piece(d + g * 128, hi[g], lo[g]);
+        for (int g = 0; g < 4; ++g) {
+          tmem_ld_wait();
+          if (g < 3) tmem_ld8(tsrc + 8 * (g + 1), (g & 1) ? va : vb);
+          uint4 hi, lo;
+          split8((g & 1) ? vb : va, inv_scale, hi, lo);
+          st_piece(d + g * 128, hi, lo);
+        }
         tc_fence_before();
-        fence_async_smem();
-        warp_arrive(bars + kBE1 + m, lane);
+        warp_arrive(bars + kBE1 + m, lane);  // (proxy fence: on the consumers' side, see the chunk loop)
         if (halo_warp && lane == 0) mbar_arrive(bars + kBS1 + m);
         PSX_TCTICK(0, 4 + 2 * m)
       }
@@ -468,46 +493,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     {
       // task t = (tile m, th): th 0 = the half of the columns whose outputs are complete first (see P2)
       const float sc = inv_scale / sa;
-      const int hfirst = rank == 0 ? 0 : 1;
-      const float* yrow = yplane + (int64_t)ml * kTcN + 16 * cq;
-      float4 ya, yb, yc, yd;
-      ld_nc8(yrow + 64 * hfirst, ya, yb);  // in flight while P2 runs; later tasks: requested at the end of the task before
-      ld_nc8(yrow + 64 * hfirst + 8, yc, yd);
 #pragma unroll 1
       for (int t = 0; t < 4; ++t) {
         const int m = t >> 1, th = t & 1, h = th ^ hfirst, n0 = 64 * h + 16 * cq;
-        mbar_wait(bars + kBD2 + t, 0);
-        tc_fence_after();
-        PSX_TCTICK(0, 7 + 2 * t)
-        uint32_t v[16];
-        tmem_ld16(tlane + 256 + 128 * m + n0, v);
-        tmem_ld_wait();
         const float yy[16] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w, yc.x, yc.y, yc.z, yc.w, yd.x, yd.y, yd.z, yd.w};
-        uint32_t rr[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float rv = yy[e] - __uint_as_float(v[e]) * sc;
-          acc = fmaf(rv, rv, acc);
-          rr[e] = __float_as_uint(rv);
-        }
-        uint4 hi[2], lo[2];
-        split8(rr, rscale, hi[0], lo[0]);
-        split8(rr + 8, rscale, hi[1], lo[1]);
-        uint8_t* d = op + m * kRpTile + (3 + (n0 >> 3)) * kKc + (ml >> 3) * 128 + (ml & 7) * 16;
-        // the columns next to the neighbour are in the late half on both ranks
-        const bool halo_warp = th == 1 && (rank == 0 ? cq >= 2 : cq <= 1);
-        if (halo_warp) mbar_wait_cluster(bars + kBA1 + m, 0);  // (the copy left long ago; this only makes it formal)
-        st_piece(d, hi[0], lo[0]);
-        st_piece(d + kKc, hi[1], lo[1]);
-        tc_fence_before();
-        fence_async_smem();
-        warp_arrive(bars + kBE2 + m, lane);
-        if (halo_warp && lane == 0) mbar_arrive(bars + kBS2 + m);
-        if (t < 3) {  // (a fence or a release arrival waits for the loads in flight: the next request goes out after them)
+        if (t < 3) {  // the next task's observation values: in flight across this task (no fence in it waits for them)
           const float* yn = yrow + (int64_t)(128 * ((t + 1) >> 1)) * kTcN + 64 * (((t + 1) & 1) ^ hfirst);
           ld_nc8(yn, ya, yb);
           ld_nc8(yn + 8, yc, yd);
         }
+        mbar_wait(bars + kBD2 + t, 0);
+        tc_fence_after();
+        PSX_TCTICK(0, 7 + 2 * t)
+        uint32_t va[8], vb[8];
+        const uint32_t tsrc = tlane + 256 + 128 * m + n0;
+        tmem_ld8(tsrc, va);
+        uint8_t* d = op + m * kRpTile + (3 + (n0 >> 3)) * kKc + (ml >> 3) * 128 + (ml & 7) * 16;
+        // the columns next to the neighbour are in the late half on both ranks
+        const bool halo_warp = th == 1 && (rank == 0 ? cq >= 2 : cq <= 1);
+        if (halo_warp) mbar_wait_cluster(bars + kBA1 + m, 0);  // (the copy left long ago; this only makes it formal)
+        tmem_ld_wait();
+        tmem_ld8(tsrc + 8, vb);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g == 1) tmem_ld_wait();
+          uint32_t rr[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float rv = yy[8 * g + e] - __uint_as_float(g ? vb[e] : va[e]) * sc;
+            acc = fmaf(rv, rv, acc);
+            rr[e] = __float_as_uint(rv);
+          }
+          uint4 hi, lo;
+          split8(rr, rscale, hi, lo);
+          st_piece(d + g * kKc, hi, lo);
+        }
+        tc_fence_before();
+        warp_arrive(bars + kBE2 + m, lane);
+        if (halo_warp && lane == 0) mbar_arrive(bars + kBS2 + m);
         PSX_TCTICK(0, 8 + 2 * t)
       }
     }
@@ -521,22 +544,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       mbar_wait(bars + kBD3 + m, 0);
       tc_fence_after();
       PSX_TCTICK(0, 15 + 2 * m)
-      uint32_t v[32];
-      tmem_ld32(tlane + 128 * m + 32 * cq, v);
+      uint32_t va[8], vb[8];
+      const uint32_t tsrc = tlane + 128 * m + 32 * cq;
+      tmem_ld8(tsrc, va);
       // rows above (tile 0) / below (tile 1) the image: K blocks 0..2 / 35..37 of A4
       zero_fill(op + (m == 0 ? 0 : 35) * kKc, 3 * kKc, tid);
-      tmem_ld_wait();
       mbar_wait_cluster(bars + kBA2 + m, 0);  // this CTA's A3 halo copy of tile m has left its source blocks
       const int kp = 128 * m + ml + kTcPad;
       uint8_t* d = op + (kp >> 3) * kKc + (4 * cq) * 128 + (kp & 7) * 16;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
+        tmem_ld_wait();
+        if (g < 3) tmem_ld8(tsrc + 8 * (g + 1), (g & 1) ? va : vb);
         uint4 hi, lo;
-        split8(v + 8 * g, inv_scale, hi, lo);
+        split8((g & 1) ? vb : va, inv_scale, hi, lo);
         st_piece(d + g * 128, hi, lo);
       }
       tc_fence_before();
-      fence_async_smem();
       warp_arrive(bars + kBE3 + m, lane);
       PSX_TCTICK(0, 16 + 2 * m)
     }
@@ -561,11 +585,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         tc_fence_after();
         PSX_TCTICK(0, 19 + 2 * qq)
         const int i0 = 64 * qq + 16 * cq;
-        uint32_t v[16];
-        tmem_ld16(tlane + 256 + i0, v);
+        uint32_t va[8], vb[8];
+        tmem_ld8(tlane + 256 + i0, va);
+        tmem_ld_wait();
+        tmem_ld8(tlane + 256 + i0 + 8, vb);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) __stcs(cp + (i0 + e) * kTcN, __uint_as_float(va[e]) * sc);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) __stcs(cp + (i0 + e) * kTcN, __uint_as_float(v[e]) * sc);
+        for (int e = 0; e < 8; ++e) __stcs(cp + (i0 + 8 + e) * kTcN, __uint_as_float(vb[e]) * sc);
         PSX_TCTICK(0, 20 + 2 * qq)
       }
     }

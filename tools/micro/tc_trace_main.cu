@@ -43,16 +43,17 @@ int main(int argc, char** argv) {
   printf("SM clock during CTA 0: %.0f MHz\n", (double)(h[31] - h[30]) / ((double)(h[27] - h[0]) / 1e3));
   const char* cn[9] = {"start", "A2(0) halo copy issued", "A2(1) halo copy issued", "A3(0) halo copy issued", "A3(1) halo copy issued",
                        "A2(0) source ready", "A2(1) source ready", "A3(0) source ready", "A3(1) source ready"};
-  const char* sn[5] = {"start", "slot free: A2(0)", "slot free: A2(1)", "slot free: A3(0)", "slot free: A3(1)"};
+  const char* sn[11] = {"start", "slot free: A2(0)", "slot free: A2(1)", "slot free: A3(0)", "slot free: A3(1)", "", "", "",
+                        "E2(1,0) warp 0: TMEM read", "E2(1,0) warp 0: residual + split done", "E2(1,0) warp 0: stored"};
   const char* rn[4] = {"epilogue warp 0", "UMMA thread", "halo-copy thread", "slot-free signal thread"};
   for (int role = 0; role < 4; ++role) {
-    const int ns = role == 0 ? 28 : role == 1 ? 19 : role == 2 ? 9 : 5;
+    const int ns = role == 0 ? 28 : role == 1 ? 19 : role == 2 ? 9 : 11;
     printf("%s: us since CTA start, avg over the rank-0 CTAs | rank-1 CTAs (max over all)\n", rn[role]);
     for (int sl = 0; sl < ns; ++sl) {
       double avg[2] = {0, 0}, mx = 0;
       for (int b = 0; b < nb; ++b) { double d = (double)(h[(b * 4 + role) * 32 + sl] - h[(b * 4) * 32]); avg[b & 1] += d; mx = std::max(mx, d); }
       const char* nm = role == 0 ? en[sl] : role == 1 ? mn[sl] : role == 2 ? cn[sl] : sn[sl];
-      if (role >= 2 && sl == 0) continue;
+      if (role >= 2 && (sl == 0 || (sl > 4 && sl < 8))) continue;
       printf("   %-24s %7.2f | %7.2f (%7.2f)\n", nm, avg[0] / (nb / 2) / 1e3, avg[1] / (nb / 2) / 1e3, mx / 1e3);
     }
   }
