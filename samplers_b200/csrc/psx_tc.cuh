@@ -107,6 +107,16 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t caddr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
+// Suspends the thread (no issue slots used, unlike a polling loop) until phase 0 completes or ~`ns` have passed.
+__device__ __forceinline__ bool mbar_try_wait_for(uint64_t* bar, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0, %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // non-blocking tests of phase 0.  The cluster-scope acquire is for barriers that a peer CTA's bulk copy completes
 // (the data it guards was written from outside this CTA); it is several times more expensive than the CTA-scope
 // one, which matters in a polling loop.
