@@ -96,6 +96,7 @@ void read_env() {
   e.no_pipe = getenv("PSX_NO_PIPE") != nullptr;
   e.no_fast16 = getenv("PSX_NO_FAST16") != nullptr;
   e.no_tc = getenv("PSX_NO_TC") != nullptr;
+  e.tc_one_plane = getenv("PSX_TC_ONE_PLANE") != nullptr;
   e.fused = getenv("PSX_FUSED") != nullptr;
   const char* sp = getenv("PSX_SPLIT");
   e.split = sp ? atoi(sp) : 0;
@@ -334,7 +335,11 @@ PSX_API int psx_op_err_parts(const psx_op* op) { return op ? op->err_parts : 0; 
 
 PSX_API size_t psx_op_workspace_bytes(const psx_op* op, int64_t L) {
   if (!op || L <= 0) return 0;
-  if (op->kind == PSX_OP_SEPBLUR || op->kind == PSX_OP_CONV2D) return (size_t)L * op->n * sizeof(float);
+  // separable blur: h1 and h2 of the CUDA-core K1 live in two regions -- the row-pair-interleaved h2 of a strip
+  // covers cells of OTHER strips' h1 (offset 2 * column inside the double row), so writing it in place raced with
+  // strips that had not been fetched yet once persistent CTAs drifted apart (L >= 32)
+  if (op->kind == PSX_OP_SEPBLUR) return 2 * (size_t)L * op->n * sizeof(float);
+  if (op->kind == PSX_OP_CONV2D) return (size_t)L * op->n * sizeof(float);
   return 0;
 }
 

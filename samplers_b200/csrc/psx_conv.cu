@@ -1374,7 +1374,7 @@ static int run_cols(const psx_op* op, const Taps& tf, const Taps& ta, const floa
 
 // cols16 + rows_il tail of K1 (h1 in ws, row-major)  ->  cot.  Returns -1 when the geometry does not qualify.
 template <int K, int TC>
-static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot, float* err_part, int64_t planes,
+static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* ws2, float* cot, float* err_part, int64_t planes,
                          int64_t sample0, int64_t obs_repeat, float w, float sa, const float* dsc, cudaStream_t st,
                          bool half = false) {
   const int W = op->W, H = op->H;
@@ -1398,10 +1398,9 @@ static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot
   const int64_t tiles_c = planes * strips;
   int64_t grid_c = (int64_t)occ_c * sm_count();
   if (grid_c > tiles_c) grid_c = tiles_c;
-  // in place: the strip of h1 is fully in shared memory before the interleaved h2 of the same rows/columns is
-  // written; other CTAs never touch this strip's (row pair, column) cells -- but the IL layout moves data
-  // ACROSS rows of a pair, so in-place is only safe because both rows of a pair belong to the same strip tile.
-  conv_cols16<K, TC><<<(unsigned)grid_c, kThreads, smem_c, st>>>(map, y, ws, err_part, op->C, H, W, strips, tiles_c,
+  // NOT in place: the interleaved h2 of (row pair, column c) sits at offset 2 c of the double row, i.e. on cells of
+  // two OTHER strips' h1 -- which their (persistent, unsynchronised) CTAs may not have fetched yet.  h2 -> ws2.
+  conv_cols16<K, TC><<<(unsigned)grid_c, kThreads, smem_c, st>>>(map, y, ws2, err_part, op->C, H, W, strips, tiles_c,
                                                              obs_repeat, sample0, box_h, op->fv, op->av);
   int rc = check_cuda(cudaGetLastError(), "conv_cols16 launch");
   if (rc) return rc;
@@ -1416,10 +1415,10 @@ static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* cot
       cudaFuncSetAttribute(conv_rows_il<K, ROUNDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr_h = true;
     }
-    conv_rows_il<K, ROUNDS, true><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r,
+    conv_rows_il<K, ROUNDS, true><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws2, cot, total_rows, W, pitch2, tiles_r,
                                                                                 op->ah, coef, dsc);
   } else {
-    conv_rows_il<K, ROUNDS><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws, cot, total_rows, W, pitch2, tiles_r, op->ah, coef, dsc);
+    conv_rows_il<K, ROUNDS><<<(unsigned)grid_r, kIlThreads, smem_r, st>>>(ws2, cot, total_rows, W, pitch2, tiles_r, op->ah, coef, dsc);
   }
   return check_cuda(cudaGetLastError(), "conv_rows_il launch");
 }
@@ -1481,23 +1480,26 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
     }
     for (int p = 0; p < parts; ++p) {
       cudaStream_t s = p == 0 ? st : op->aux_stream[p - 1];
-      if (p > 0)
-        if (int rc = check_cuda(cudaStreamWaitEvent(s, op->ev_fork, 0), "K1 fork wait")) return rc;
+      int rc = p > 0 ? check_cuda(cudaStreamWaitEvent(s, op->ev_fork, 0), "K1 fork wait") : PSX_OK;
       const int64_t l0 = p * Lp, off = l0 * op->n;
       const int64_t off_io = half ? off / 2 : off;  // x / eps / cot offsets in float units (n is even for these shapes)
-      int rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x + off_io, eps + off_io, ws + off, planes_p, sa, s1, w, dsc, s, half);
-      if (rc) return rc;
+      if (!rc) rc = run_rows<ROWS_TWEEDIE>(op, op->fh, x + off_io, eps + off_io, ws + off, planes_p, sa, s1, w, dsc, s, half);
       float* part = err_part + l0 * op->err_parts;
 #define PSX_TAIL(KK, TCC) \
-  run_fast_tail<KK, TCC>(op, y, ws + off, cot + off_io, part, planes_p, l0, obs_repeat, w, sa, dsc, s, half)
-      rc = small ? (kk == 40 ? PSX_TAIL(40, 32) : PSX_TAIL(16, 32)) : (kk == 40 ? PSX_TAIL(40, 16) : PSX_TAIL(16, 16));
-#undef PSX_TAIL
-      if (rc < 0) return fail(PSX_ERR_CUDA, "blur K1: could not encode the strip tensor map");
-      if (rc) return rc;
-      if (p > 0) {
-        if (int e = check_cuda(cudaEventRecord(op->ev_join[p - 1], s), "K1 join event")) return e;
-        if (int e = check_cuda(cudaStreamWaitEvent(st, op->ev_join[p - 1], 0), "K1 join wait")) return e;
+  run_fast_tail<KK, TCC>(op, y, ws + off, ws + L * op->n + off, cot + off_io, part, planes_p, l0, obs_repeat, w, sa, dsc, s, half)
+      if (!rc) {
+        rc = small ? (kk == 40 ? PSX_TAIL(40, 32) : PSX_TAIL(16, 32)) : (kk == 40 ? PSX_TAIL(40, 16) : PSX_TAIL(16, 16));
+        if (rc < 0) rc = fail(PSX_ERR_CUDA, "blur K1: could not encode the strip tensor map");
       }
+#undef PSX_TAIL
+      if (p > 0) {
+        // joined even after a failure: whatever reached the side stream must not be left unordered against the
+        // caller's stream (under capture an unjoined fork invalidates the whole graph with an opaque error)
+        const int e1 = check_cuda(cudaEventRecord(op->ev_join[p - 1], s), "K1 join event");
+        const int e2 = e1 ? e1 : check_cuda(cudaStreamWaitEvent(st, op->ev_join[p - 1], 0), "K1 join wait");
+        if (!rc) rc = e2;
+      }
+      if (rc) return rc;  // the groups after this one have not been forked
     }
     return PSX_OK;
   }

@@ -43,6 +43,8 @@
 // halo copies, warp 18 sends the "slot is free" signals.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -87,6 +89,10 @@ constexpr int kTcPad = 24;                 // zero padding / halo width = larges
 constexpr int kTcWarps = 16;               // loader / epilogue warps
 constexpr int kTcEpi = 32 * kTcWarps;      // loader / epilogue threads
 constexpr int kTcThreads = kTcEpi + 96;    // + the UMMA warp, the halo-copy warp, the slot-free signal warp
+#ifndef PSX_TC_AHEAD
+#define PSX_TC_AHEAD 2
+#endif
+constexpr int kTcAhead = PSX_TC_AHEAD;     // chunks of the next plane requested ahead of E4 (16 registers each)
 constexpr int kHaloBytes = (kTcPad / 8) * 4096;  // 24 halo columns of one row tile: 3 K blocks
 
 constexpr int kKc = 4096;                  // one K block: 8 K values x 128 M values, [hi 2 KB | lo 2 KB]
@@ -168,6 +174,12 @@ __device__ __forceinline__ void st_piece(uint8_t* d, const uint4& hi, const uint
 __device__ __forceinline__ void zero_fill(uint8_t* base, int bytes, int tid) {
   for (int i = tid; i < bytes / 16; i += kTcEpi) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
 }
+// ld_nc8 that stays where it is written (the requests for the next plane must leave BEFORE the waits of E4)
+__device__ __forceinline__ void ld_nc8_v(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
 // all lanes have fenced their shared-memory writes; one arrival per warp
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
   __syncwarp();
@@ -177,7 +189,8 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     blur_k1_tc(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
                float* __restrict__ cot, float* __restrict__ err_part, const uint8_t* __restrict__ bimg, float inv_scale,
-               int C, int64_t obs_repeat, int pp, float sa, float s1, float coef, const float* __restrict__ dsc) {
+               int C, int64_t obs_repeat, int pp, float sa, float s1, float coef, const float* __restrict__ dsc,
+               int planes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* op = smem;
   uint8_t* bsm = smem + kOpBytes;
@@ -188,7 +201,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
-  const int64_t plane = blockIdx.x >> 1;
+  // persistent: cluster c works on planes c, c + (clusters in the grid), ...; every mbarrier completes exactly one
+  // phase per plane, so the parity every wait uses is the low bit of the plane iteration `it`
+  const int plane0 = blockIdx.x >> 1, pstride = gridDim.x >> 1;
   const int j0 = (int)rank * 128;
   PSX_TCTICK(0, 0)
   PSX_TCTICK(1, 0)
@@ -239,17 +254,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       const uint32_t hi32 = (uint32_t)(da >> 32), a0 = (uint32_t)da, b0 = (uint32_t)db;  // same SBO / version word
       const uint32_t cbar = mapa(smem_u32(bars), peer);
       mbar_spin(bars + kBImg, 0);
-      // ---- P1: V on the own columns, K = rows, streamed in behind the load
-      issue_clear(tb, 256, z_s);
+      uint32_t ph = 0;
+#pragma unroll 1
+      for (int plane = plane0; plane < planes; plane += pstride, ph ^= 1u) {
+      // ---- P1: V on the own columns, K = rows, streamed in behind the load.  (The accumulator is cleared after the
+      // first chunk has been seen: from the second plane on that also says that E3 / E4 of the previous plane have
+      // read their accumulators.)
       static_for<1, kCpSteps - 1>([&](auto S) {
         constexpr int s = decltype(S)::value;
         constexpr int last = 16 * s - 9 < kTcN - 1 ? 16 * s - 9 : kTcN - 1;  // last image row of this K-step
         constexpr int prev = s == 1 ? -1 : (16 * (s - 1) - 9 < kTcN - 1 ? 16 * (s - 1) - 9 : kTcN - 1);
         if constexpr ((last >> 5) != (prev >> 5) || s == 1) {
-          mbar_spin(bars + kBLd + (last >> 5), 0);
+          mbar_spin(bars + kBLd + (last >> 5), ph);
           fence_async_smem();  // the loaders' generic-proxy stores, acquired above -> visible to the UMMA's async proxy
           tc_fence_after();
         }
+        if constexpr (s == 1) issue_clear(tb, 256, z_s);
         issue_kstep<256, s, 1>(tb, a0, b0, hi32);
         if constexpr (s == 10) umma_commit(bars + kBD1 + 0);  // outputs n <= 132 are final
       });
@@ -261,7 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       // columns 0..63 on rank 0 (after step 6) and columns 64..127 on rank 1 (after its own steps 2..9).
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
-        mbar_spin(bars + kBE1 + m, 0);
+        mbar_spin(bars + kBE1 + m, ph);
         fence_async_smem();
         tc_fence_after();
         PSX_TCTICK(1, 15 + m)
@@ -277,7 +297,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
           static_for<2, 10>([&](auto S) { issue_kstep<128, decltype(S)::value, 1>(d, am, b0, hi32); });
           umma_commit(bars + kBD2 + 2 * m);  // outputs n >= 59 are final
         }
-        mbar_spin(bars + kBH1 + m, 0);
+        mbar_spin(bars + kBH1 + m, ph);
+        if (plane + pstride < planes) mbar_expect_tx(bars + kBH1 + m, kHaloBytes);  // armed for the next plane
         mbar_arrive_remote_relaxed(cbar + 8 * (kBA1 + m));  // the neighbour's copy has been read out of its operand
         tc_fence_after();
         PSX_TCTICK(1, 3 + 2 * m)
@@ -294,7 +315,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       // ---- P3: H^T per row tile, the same order
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
-        mbar_spin(bars + kBE2 + m, 0);
+        mbar_spin(bars + kBE2 + m, ph);
         fence_async_smem();
         tc_fence_after();
         PSX_TCTICK(1, 17 + m)
@@ -305,7 +326,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         } else {
           static_for<2, 10>([&](auto S) { issue_kstep<128, decltype(S)::value, 0>(d, am, b0, hi32); });
         }
-        mbar_spin(bars + kBH2 + m, 0);
+        mbar_spin(bars + kBH2 + m, ph);
+        if (plane + pstride < planes) mbar_expect_tx(bars + kBH2 + m, kHaloBytes);
         mbar_arrive_remote_relaxed(cbar + 8 * (kBA2 + m));
         tc_fence_after();
         PSX_TCTICK(1, 7 + 2 * m)
@@ -320,7 +342,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         PSX_TCTICK(1, 8 + 2 * m)
       }
       // ---- P4: V^T, K = rows; K-steps 1..7 read rows < 104 (tile 0) and write output rows < 128
-      mbar_spin(bars + kBE3 + 0, 0);
+      mbar_spin(bars + kBE3 + 0, ph);
       fence_async_smem();
       tc_fence_after();
       PSX_TCTICK(1, 11)
@@ -331,7 +353,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         if constexpr (s == 6) umma_commit(bars + kBD4 + 0);
       });
       PSX_TCTICK(1, 12)
-      mbar_spin(bars + kBE3 + 1, 0);
+      mbar_spin(bars + kBE3 + 1, ph);
       fence_async_smem();
       tc_fence_after();
       PSX_TCTICK(1, 13)
@@ -344,6 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       });
       umma_commit(bars + kBD4 + 3);
       PSX_TCTICK(1, 14)
+      }  // planes
     }
     __syncwarp();
   } else if (warp == kTcWarps + 1) {
@@ -354,21 +377,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     if (elect_one()) {
       const uint32_t src = (rank == 0 ? 16 : 3) * kKc, dst = (rank == 0 ? 0 : kRpKc - 3) * kKc;
       const uint32_t cop = mapa(smem_u32(op), peer), cbar = mapa(smem_u32(bars), peer);
-      for (int m = 0; m < 2; ++m) {
-        mbar_spin(bars + kBS1 + m, 0);
-        fence_async_smem();  // the source blocks were written through the generic proxy, the bulk copy reads through the async one
-        PSX_TCTICK(2, 5 + m)
-        mbar_spin(bars + kBF1 + m, 0);
-        PSX_TCTICK(2, 1 + m)
-        bulk_s2peer(cop + m * kRpTile + dst, op + m * kRpTile + src, kHaloBytes, cbar + 8 * (kBH1 + m));
-      }
-      for (int m = 0; m < 2; ++m) {
-        mbar_spin(bars + kBS2 + m, 0);
-        fence_async_smem();
-        PSX_TCTICK(2, 7 + m)
-        mbar_spin(bars + kBF2 + m, 0);
-        PSX_TCTICK(2, 3 + m)
-        bulk_s2peer(cop + m * kRpTile + dst, op + m * kRpTile + src, kHaloBytes, cbar + 8 * (kBH2 + m));
+      uint32_t ph = 0;
+#pragma unroll 1
+      for (int plane = plane0; plane < planes; plane += pstride, ph ^= 1u) {
+        for (int m = 0; m < 2; ++m) {
+          mbar_spin(bars + kBS1 + m, ph);
+          fence_async_smem();  // the source blocks were written through the generic proxy, the bulk copy reads through the async one
+          PSX_TCTICK(2, 5 + m)
+          mbar_spin(bars + kBF1 + m, ph);
+          PSX_TCTICK(2, 1 + m)
+          bulk_s2peer(cop + m * kRpTile + dst, op + m * kRpTile + src, kHaloBytes, cbar + 8 * (kBH1 + m));
+        }
+        for (int m = 0; m < 2; ++m) {
+          mbar_spin(bars + kBS2 + m, ph);
+          fence_async_smem();
+          PSX_TCTICK(2, 7 + m)
+          mbar_spin(bars + kBF2 + m, ph);
+          PSX_TCTICK(2, 3 + m)
+          bulk_s2peer(cop + m * kRpTile + dst, op + m * kRpTile + src, kHaloBytes, cbar + 8 * (kBH2 + m));
+        }
       }
     }
     __syncwarp();
@@ -377,20 +404,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     cluster_wait_acquire();  // #0
     if (elect_one()) {
       const uint32_t f1 = mapa(smem_u32(bars + kBF1), peer), f2 = mapa(smem_u32(bars + kBF2), peer);
-      // this CTA's halo slot of tile m overlaps A1 rows that P1 reads up to the commit of tile m
-      mbar_spin(bars + kBD1 + 0, 0);
-      mbar_arrive_remote_relaxed(f1);
-      PSX_TCTICK(3, 1)
-      mbar_spin(bars + kBD1 + 1, 0);
-      mbar_arrive_remote_relaxed(f1 + 8);
-      PSX_TCTICK(3, 2)
-      // ... and holds the A2 halo until P2 of tile m is done
-      mbar_spin(bars + kBD2 + 1, 0);
-      mbar_arrive_remote_relaxed(f2);
-      PSX_TCTICK(3, 3)
-      mbar_spin(bars + kBD2 + 3, 0);
-      mbar_arrive_remote_relaxed(f2 + 8);
-      PSX_TCTICK(3, 4)
+      uint32_t ph = 0;
+#pragma unroll 1
+      for (int plane = plane0; plane < planes; plane += pstride, ph ^= 1u) {
+        // this CTA's halo slot of tile m overlaps A1 rows that P1 reads up to the commit of tile m
+        mbar_spin(bars + kBD1 + 0, ph);
+        mbar_arrive_remote_relaxed(f1);
+        PSX_TCTICK(3, 1)
+        mbar_spin(bars + kBD1 + 1, ph);
+        mbar_arrive_remote_relaxed(f1 + 8);
+        PSX_TCTICK(3, 2)
+        // ... and holds the A2 halo until P2 of tile m is done
+        mbar_spin(bars + kBD2 + 1, ph);
+        mbar_arrive_remote_relaxed(f2);
+        PSX_TCTICK(3, 3)
+        mbar_spin(bars + kBD2 + 3, ph);
+        mbar_arrive_remote_relaxed(f2 + 8);
+        PSX_TCTICK(3, 4)
+      }
     }
     __syncwarp();
   } else {
@@ -399,6 +430,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     const int q = warp & 3, cq = warp >> 2;
     const uint32_t tlane = tb + ((uint32_t)(32 * q) << 16);
     const int ml = 32 * q + lane;  // this thread's TMEM lane
+    // chunk c = rows 32 c .. 32 c + 31 = K blocks 3 + 4 c ..; warp = (K block kb, column-group quad), lane = (row r,
+    // column group cl): 32 bytes of one row per lane, 8 rows x 128 B per warp instruction
+    const int ld_r = lane & 7, ld_cg = 4 * (warp & 3) + (lane >> 3), ld_kb = warp >> 2;
+    const int64_t ld_off = (int64_t)(8 * ld_kb + ld_r) * kTcN + j0 + 8 * ld_cg;
+    float4 xa[4], xb[4], ea[4], eb[4];
+    // the first chunks of the first plane (those of every further plane are requested ahead of E4 of the plane before)
+#pragma unroll
+    for (int u = 0; u < kTcAhead; ++u) {
+      ld_nc8_v(x + plane0 * (int64_t)(kTcN * kTcN) + ld_off + u * 32 * kTcN, xa[u], xb[u]);
+      ld_nc8_v(eps + plane0 * (int64_t)(kTcN * kTcN) + ld_off + u * 32 * kTcN, ea[u], eb[u]);
+    }
+    step_scalars_k1(dsc, sa, s1, coef);  // graph replay: a device row, in flight together with the first chunks
+    // residual scale 32 * 2^floor(log2 sa) (sa is a positive normal number: sqrt of a clipped alpha-bar)
+    const float rscale = __int_as_float((__float_as_int(sa) & 0x7f800000) + (5 << 23));
+    uint32_t ph = 0;
+#pragma unroll 1
+    for (int plane = plane0; plane < planes; plane += pstride, ph ^= 1u) {
     const int64_t l = plane / C, ch = plane % C;
     const float* yplane = y + ((l / obs_repeat) * C + ch) * (int64_t)(kTcN * kTcN) + j0;
     // the observation is read much later: pull this CTA's half plane towards L2 now
@@ -407,19 +455,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 
     // ------------------------------------------------------------------------------------ load: A1 = x_t - s1 eps
     {
-      // chunk c = rows 32 c .. 32 c + 31 = K blocks 3 + 4 c ..; warp = (K block kb, column-group quad), lane = (row r,
-      // column group cl): 32 bytes of one row per lane, 8 rows x 128 B per warp instruction
-      const int r = lane & 7, cg = 4 * (warp & 3) + (lane >> 3), kb = warp >> 2;
-      const float* xp = x + plane * (int64_t)(kTcN * kTcN) + (8 * kb + r) * kTcN + j0 + 8 * cg;
-      const float* ep = eps + plane * (int64_t)(kTcN * kTcN) + (8 * kb + r) * kTcN + j0 + 8 * cg;
-      uint8_t* d0 = op + (3 + kb) * kKc + cg * 128 + r * 16;
-      float4 xa[4], xb[4], ea[4], eb[4];
+      const float* xp = x + plane * (int64_t)(kTcN * kTcN) + ld_off;
+      const float* ep = eps + plane * (int64_t)(kTcN * kTcN) + ld_off;
+      uint8_t* d0 = op + (3 + ld_kb) * kKc + ld_cg * 128 + ld_r * 16;
+      // chunks 0 .. kTcAhead - 1 were requested ahead of E4 of the plane before (register budget); the rest now
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        ld_nc8(xp + u * 32 * kTcN, xa[u], xb[u]);
-        ld_nc8(ep + u * 32 * kTcN, ea[u], eb[u]);
+      for (int u = kTcAhead; u < 4; ++u) {
+        ld_nc8_v(xp + u * 32 * kTcN, xa[u], xb[u]);
+        ld_nc8_v(ep + u * 32 * kTcN, ea[u], eb[u]);
       }
-      step_scalars_k1(dsc, sa, s1, coef);  // graph replay: a device row, in flight together with the first chunks
       // rows above / below the image: K blocks 0..2 and 35..37 of A1 (covered by the arrival on chunk 0)
       zero_fill(op, 3 * kKc, tid);
       zero_fill(op + 35 * kKc, 3 * kKc, tid);
@@ -442,9 +486,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       }
     }
     PSX_TCTICK(0, 2)
-    // residual scale 32 * 2^floor(log2 sa) (sa is a positive normal number: sqrt of a clipped alpha-bar)
-    const float rscale = __int_as_float((__float_as_int(sa) & 0x7f800000) + (5 << 23));
-    cluster_wait_acquire();  // #0
+    if (plane == plane0) cluster_wait_acquire();  // #0
 
     // the observation values of the first E2 task: requested now, needed ~2 us from here (nothing in between waits
     // for this thread's loads: the proxy fences are on the consumers' side)
@@ -461,7 +503,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       const bool halo_warp = rank == 0 ? q == 3 : q == 0;  // owns the columns the neighbour needs
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
-        mbar_wait(bars + kBD1 + m, 0);
+        mbar_wait(bars + kBD1 + m, ph);
         tc_fence_after();
         PSX_TCTICK(0, 3 + 2 * m)
         // TMEM is read 8 columns at a time, the next chunk in flight while this one is split and stored (TMEM read,
@@ -502,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
           ld_nc8(yn, ya, yb);
           ld_nc8(yn + 8, yc, yd);
         }
-        mbar_wait(bars + kBD2 + t, 0);
+        mbar_wait(bars + kBD2 + t, ph);
         tc_fence_after();
         PSX_TCTICK(0, 7 + 2 * t)
         uint32_t va[8], vb[8];
@@ -511,7 +553,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         uint8_t* d = op + m * kRpTile + (3 + (n0 >> 3)) * kKc + (ml >> 3) * 128 + (ml & 7) * 16;
         // the columns next to the neighbour are in the late half on both ranks
         const bool halo_warp = th == 1 && (rank == 0 ? cq >= 2 : cq <= 1);
-        if (halo_warp) mbar_wait_cluster(bars + kBA1 + m, 0);  // (the copy left long ago; this only makes it formal)
+        if (halo_warp) mbar_wait_cluster(bars + kBA1 + m, ph);  // (the copy left long ago; this only makes it formal)
         tmem_ld_wait();
         tmem_ld8(tsrc + 8, vb);
 #pragma unroll
@@ -541,7 +583,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     // lane = image row il of tile m, accumulator columns = own columns 32 cq .. 32 cq + 31 (= M of the next pass)
 #pragma unroll 1
     for (int m = 0; m < 2; ++m) {
-      mbar_wait(bars + kBD3 + m, 0);
+      mbar_wait(bars + kBD3 + m, ph);
       tc_fence_after();
       PSX_TCTICK(0, 15 + 2 * m)
       uint32_t va[8], vb[8];
@@ -549,7 +591,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       tmem_ld8(tsrc, va);
       // rows above (tile 0) / below (tile 1) the image: K blocks 0..2 / 35..37 of A4
       zero_fill(op + (m == 0 ? 0 : 35) * kKc, 3 * kKc, tid);
-      mbar_wait_cluster(bars + kBA2 + m, 0);  // this CTA's A3 halo copy of tile m has left its source blocks
+      mbar_wait_cluster(bars + kBA2 + m, ph);  // this CTA's A3 halo copy of tile m has left its source blocks
       const int kp = 128 * m + ml + kTcPad;
       uint8_t* d = op + (kp >> 3) * kKc + (4 * cq) * 128 + (kp & 7) * 16;
 #pragma unroll
@@ -574,6 +616,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       err_part[plane * pp + rank * (pp / 2) + tid] = tot;
     }
 
+    // the next plane's first four chunks: requested here, in flight across E4 (registers only; A1 itself is written
+    // after E4 has seen P4's last commit, i.e. after the tensor cores have read A4 out of the operand buffer)
+    if (plane + pstride < planes) {
+      const float* xn = x + (plane + pstride) * (int64_t)(kTcN * kTcN) + ld_off;
+      const float* en = eps + (plane + pstride) * (int64_t)(kTcN * kTcN) + ld_off;
+#pragma unroll
+      for (int u = 0; u < kTcAhead; ++u) {
+        ld_nc8_v(xn + u * 32 * kTcN, xa[u], xb[u]);
+        ld_nc8_v(en + u * 32 * kTcN, ea[u], eb[u]);
+      }
+    }
+
     // ------------------------------------------------------------------------------------ E4: cot
     // lane = own column, accumulator columns = image rows: every store instruction writes one 128-byte line
     {
@@ -581,7 +635,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       float* cp = cot + plane * (int64_t)(kTcN * kTcN) + j0 + ml;
 #pragma unroll 1
       for (int qq = 0; qq < 4; ++qq) {
-        mbar_wait(bars + kBD4 + qq, 0);
+        mbar_wait(bars + kBD4 + qq, ph);
         tc_fence_after();
         PSX_TCTICK(0, 19 + 2 * qq)
         const int i0 = 64 * qq + 16 * cq;
@@ -597,6 +651,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         PSX_TCTICK(0, 20 + 2 * qq)
       }
     }
+    }  // planes
   }
   // Every bulk copy into this CTA and every remote arrival on its barriers is awaited by one of its own waits above
   // (H1 / H2 before P2 / P3, F1 / F2 before the copies, A1 / A2 before the copied blocks are rewritten), and the A
@@ -684,21 +739,49 @@ void tcblur_release(psx_op* op) {
 
 bool tcblur_available(const psx_op* op) { return op->tc_pad != 0 && op->err_parts % (2 * op->C) == 0; }
 
+// Cluster pairs of blur_k1_tc that are resident at once on the current device (74 on a 148-SM B200), per device.
+static int tc_resident_clusters() {
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * 148);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = kTcSmem;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, blur_k1_tc, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = sm_count() / 2;
+    }
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                           int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot,
                           float* err_part, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};  // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr[dev]) {
     if (int rc = check_cuda(cudaFuncSetAttribute(blur_k1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem),
                             "blur_k1_tc attribute"))
       return rc;
-    attr = true;
+    attr[dev] = true;
   }
   const int64_t planes = L * op->C;
+  PSX_REQUIRE(planes <= INT32_MAX / 2, "blur_k1_tc: too many planes");
   const float coef = (float)((double)w / (double)sa);
-  blur_k1_tc<<<(unsigned)(planes * 2), kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
-                                                                   op->tc_inv_scale, op->C, obs_repeat,
-                                                                   op->err_parts / op->C, sa, s1, coef, dsc);
+  // persistent cluster pairs: one resident wave (74 pairs on a 148-SM part), each pair loops over its planes
+  const int64_t clusters = env_opts().tc_one_plane ? planes : std::min<int64_t>(planes, tc_resident_clusters());
+  blur_k1_tc<<<(unsigned)(clusters * 2), kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
+                                                                     op->tc_inv_scale, op->C, obs_repeat,
+                                                                     op->err_parts / op->C, sa, s1, coef, dsc,
+                                                                     (int)planes);
   return check_cuda(cudaGetLastError(), "blur_k1_tc launch");
 }
 

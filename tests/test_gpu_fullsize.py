@@ -172,3 +172,52 @@ def test_posterior_moments_of_many_samples_match_torch():
     assert torch.equal(out, ref)
     assert rel_err(tot.cpu(), ref.double().sum(0).float().cpu()) < 1e-6
     assert rel_err(tsq.cpu(), ref.double().square().sum(0).float().cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("L,obs_repeat", [(64, 64), (64, 1), (30, 1), (50, 5)])
+@pytest.mark.parametrize("path", ["tc", "tc_one_plane", "cuda_core_1", "cuda_core_2"])
+def test_blur_k1_large_batches_every_path(L, obs_repeat, path, monkeypatch):
+    """K1 of config 2's blur at batches with MORE planes than resident CTA groups -- the persistent loop of the
+    tensor-core kernel (74 cluster pairs; 90 / 150 / 192 planes) and the persistent strip kernels of the CUDA-core
+    path (whose in-place interleaved h2 once raced with unfetched strips from L = 32 on) -- against the oracle's
+    operator evaluated in fp64 on the device, per sample, twice (repeatability)."""
+    from samplers_b200 import _native, operators as pops
+    env = {"tc": {}, "tc_one_plane": {"PSX_TC_ONE_PLANE": "1"}, "cuda_core_1": {"PSX_NO_TC": "1", "PSX_SPLIT": "1"},
+           "cuda_core_2": {"PSX_NO_TC": "1", "PSX_SPLIT": "2"}}[path]
+    for k in ("PSX_TC_ONE_PLANE", "PSX_NO_TC", "PSX_SPLIT"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _native.reload_env()
+    try:
+        op = pops.GaussianBlurOperator(FULL).to(DEV)
+        nat = op._native_cached(torch.device(DEV))
+        ora = _dev_op(oops.OracleGaussianBlur(FULL, 61, 3.0))
+        ora.taps_h, ora.taps_v = ora.taps_h.double(), ora.taps_v.double()
+        gen = torch.Generator(device=DEV).manual_seed(L + obs_repeat)
+        n = nat.n
+        x = torch.randn(L, n, device=DEV, generator=gen)
+        eps = torch.randn(L, n, device=DEV, generator=gen)
+        y = torch.randn(L // obs_repeat, n, device=DEV, generator=gen)
+        sa, s1, w = 0.9, 0.43, 25.0
+        x0 = ((x.double() - s1 * eps.double()) / sa).view(L, *FULL).requires_grad_()
+        r = y.double().repeat_interleave(obs_repeat, 0).view(L, *FULL) - ora.apply(x0)
+        err_ref = (r.detach() ** 2).flatten(1).sum(1)
+        (g,) = torch.autograd.grad(-0.5 * (r ** 2).sum(), x0)          # = A^T r
+        cot_ref = (g * (w / sa)).flatten(1)
+        ws = torch.empty(nat.workspace_bytes(L) // 4, device=DEV)
+        outs = []
+        for _ in range(2):
+            cot = torch.full_like(x, float("nan"))
+            part = torch.full((L, nat.err_parts), float("nan"), device=DEV)
+            _native.dps_pre(nat, x, eps, y, obs_repeat, sa, s1, w, cot, part, ws)
+            torch.cuda.synchronize()
+            per = ((cot.double() - cot_ref).norm(dim=1) / cot_ref.norm(dim=1))
+            assert float(per.max()) < 1e-5, [int(i) for i in torch.nonzero(per > 1e-5).flatten()]
+            assert float(((part.double().sum(1) - err_ref).abs() / err_ref).max()) < 1e-5
+            outs.append(cot)
+        assert torch.equal(outs[0], outs[1])
+    finally:
+        for k in env:
+            monkeypatch.delenv(k, raising=False)
+        _native.reload_env()

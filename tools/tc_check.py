@@ -60,7 +60,11 @@ def main():
     for (L, obs_repeat, sa, s1, w, yscale) in [(1, 1, 0.8, 0.6, 400.0, 1.0), (2, 2, 0.05, 0.998, 400.0, 1.0),
                                               (16, 16, 0.9, 0.43, 25.0, 1.0), (5, 1, 0.999, 0.03, 400.0, 1.0),
                                               (4, 4, 0.00633, 0.99998, 400.0, 1.0), (3, 1, 0.9995, 0.0316, 400.0, None),
-                                              (2, 1, 1.0, 0.0, 1.0, None)]:
+                                              (2, 1, 1.0, 0.0, 1.0, None),
+                                              # more planes than resident cluster pairs (74): the persistent loop --
+                                              # 90 planes (some pairs run two planes, some one), 150 (two or three), 192
+                                              (30, 1, 0.7, 0.71, 100.0, 1.0), (50, 5, 0.3, 0.95, 400.0, 1.0),
+                                              (64, 64, 0.9, 0.43, 25.0, 1.0), (25, 1, 0.9995, 0.0316, 400.0, None)]:
         n = nat.n
         x = torch.randn(L, n, device=dev, generator=gen)
         eps = torch.randn(L, n, device=dev, generator=gen)
@@ -90,7 +94,7 @@ def main():
                 worst = max(worst, e_cot, e_max, e_err)
         print(json.dumps(out), flush=True)
     # timing, rotate mode over cold buffers
-    for L in (16, 64):
+    for L in (16, 32, 64):
         n = nat.n
         nsets = max(2, -(-4 * 126 * 2**20 // (4 * L * n * 4)))
         S = [dict(x=torch.randn(L, n, device=dev), eps=torch.randn(L, n, device=dev), cot=torch.empty(L, n, device=dev),
@@ -98,11 +102,13 @@ def main():
              for _ in range(nsets)]
         y = torch.randn(1, nat.n_y, device=dev)
         res = {"L": L, "nsets": nsets}
-        for name, env in (("cuda_core", "1"), ("tc", None)):
-            if env:
+        for name, env in (("cuda_core", "1"), ("tc", None), ("tc_one_plane", "one"), ("tc", None)):
+            os.environ.pop("PSX_NO_TC", None)
+            os.environ.pop("PSX_TC_ONE_PLANE", None)
+            if env == "1":
                 os.environ["PSX_NO_TC"] = env
-            else:
-                os.environ.pop("PSX_NO_TC", None)
+            elif env == "one":
+                os.environ["PSX_TC_ONE_PLANE"] = "1"
             _native.reload_env()
 
             def k1(i):
@@ -122,7 +128,7 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(s.elapsed_time(e) / nsets * 1e3)
             ts.sort()
-            res[name + "_k1_us"] = ts[len(ts) // 2]
+            res.setdefault(name + "_k1_us", []).append(round(ts[len(ts) // 2], 2))
         print(json.dumps(res), flush=True)
     print("worst tc error", worst)
     return 0 if worst < 1e-5 else 1
