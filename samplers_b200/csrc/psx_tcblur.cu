@@ -186,6 +186,9 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
+// LOOP = false: one cluster pair per plane (grid = 2 x planes; all of them resident: up to 74 planes), straight-line
+// code.  LOOP = true: one resident wave of cluster pairs, each looping over its planes.
+template <bool LOOP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     blur_k1_tc(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
                float* __restrict__ cot, float* __restrict__ err_part, const uint8_t* __restrict__ bimg, float inv_scale,
@@ -256,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       mbar_spin(bars + kBImg, 0);
       uint32_t ph = 0;
 #pragma unroll 1
-      for (int plane = plane0; plane < planes; plane += pstride, ph ^= 1u) {
+      for (int plane = plane0, it_ = 0; LOOP ? plane < planes : it_ < 1; plane += pstride, ++it_, ph ^= 1u) {
       // ---- P1: V on the own columns, K = rows, streamed in behind the load.  (The accumulator is cleared after the
       // first chunk has been seen: from the second plane on that also says that E3 / E4 of the previous plane have
       // read their accumulators.)
@@ -298,7 +301,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
           umma_commit(bars + kBD2 + 2 * m);  // outputs n >= 59 are final
         }
         mbar_spin(bars + kBH1 + m, ph);
-        if (plane + pstride < planes) mbar_expect_tx(bars + kBH1 + m, kHaloBytes);  // armed for the next plane
+        if (LOOP && plane + pstride < planes) mbar_expect_tx(bars + kBH1 + m, kHaloBytes);  // armed for the next plane
         mbar_arrive_remote_relaxed(cbar + 8 * (kBA1 + m));  // the neighbour's copy has been read out of its operand
         tc_fence_after();
         PSX_TCTICK(1, 3 + 2 * m)
@@ -327,7 +330,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
           static_for<2, 10>([&](auto S) { issue_kstep<128, decltype(S)::value, 0>(d, am, b0, hi32); });
         }
         mbar_spin(bars + kBH2 + m, ph);
-        if (plane + pstride < planes) mbar_expect_tx(bars + kBH2 + m, kHaloBytes);
+        if (LOOP && plane + pstride < planes) mbar_expect_tx(bars + kBH2 + m, kHaloBytes);
         mbar_arrive_remote_relaxed(cbar + 8 * (kBA2 + m));
         tc_fence_after();
         PSX_TCTICK(1, 7 + 2 * m)
@@ -379,7 +382,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       const uint32_t cop = mapa(smem_u32(op), peer), cbar = mapa(smem_u32(bars), peer);
       uint32_t ph = 0;
 #pragma unroll 1
-      for (int plane = plane0; plane < planes; plane += pstride, ph ^= 1u) {
+      for (int plane = plane0, it_ = 0; LOOP ? plane < planes : it_ < 1; plane += pstride, ++it_, ph ^= 1u) {
         for (int m = 0; m < 2; ++m) {
           mbar_spin(bars + kBS1 + m, ph);
           fence_async_smem();  // the source blocks were written through the generic proxy, the bulk copy reads through the async one
@@ -406,7 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       const uint32_t f1 = mapa(smem_u32(bars + kBF1), peer), f2 = mapa(smem_u32(bars + kBF2), peer);
       uint32_t ph = 0;
 #pragma unroll 1
-      for (int plane = plane0; plane < planes; plane += pstride, ph ^= 1u) {
+      for (int plane = plane0, it_ = 0; LOOP ? plane < planes : it_ < 1; plane += pstride, ++it_, ph ^= 1u) {
         // this CTA's halo slot of tile m overlaps A1 rows that P1 reads up to the commit of tile m
         mbar_spin(bars + kBD1 + 0, ph);
         mbar_arrive_remote_relaxed(f1);
@@ -434,19 +437,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     // column group cl): 32 bytes of one row per lane, 8 rows x 128 B per warp instruction
     const int ld_r = lane & 7, ld_cg = 4 * (warp & 3) + (lane >> 3), ld_kb = warp >> 2;
     const int64_t ld_off = (int64_t)(8 * ld_kb + ld_r) * kTcN + j0 + 8 * ld_cg;
+    constexpr int kAhead = LOOP ? kTcAhead : 4;
     float4 xa[4], xb[4], ea[4], eb[4];
     // the first chunks of the first plane (those of every further plane are requested ahead of E4 of the plane before)
 #pragma unroll
-    for (int u = 0; u < kTcAhead; ++u) {
+    for (int u = 0; u < kAhead; ++u) {
       ld_nc8_v(x + plane0 * (int64_t)(kTcN * kTcN) + ld_off + u * 32 * kTcN, xa[u], xb[u]);
       ld_nc8_v(eps + plane0 * (int64_t)(kTcN * kTcN) + ld_off + u * 32 * kTcN, ea[u], eb[u]);
     }
-    step_scalars_k1(dsc, sa, s1, coef);  // graph replay: a device row, in flight together with the first chunks
-    // residual scale 32 * 2^floor(log2 sa) (sa is a positive normal number: sqrt of a clipped alpha-bar)
-    const float rscale = __int_as_float((__float_as_int(sa) & 0x7f800000) + (5 << 23));
     uint32_t ph = 0;
 #pragma unroll 1
-    for (int plane = plane0; plane < planes; plane += pstride, ph ^= 1u) {
+    for (int plane = plane0, it_ = 0; LOOP ? plane < planes : it_ < 1; plane += pstride, ++it_, ph ^= 1u) {
+    const float* xp = x + plane * (int64_t)(kTcN * kTcN) + ld_off;
+    const float* ep = eps + plane * (int64_t)(kTcN * kTcN) + ld_off;
+    // chunks 0 .. kTcAhead - 1 were requested ahead of E4 of the plane before (register budget); the rest now, before
+    // anything that waits (the step scalars are first used by the conversions below)
+#pragma unroll
+    for (int u = kAhead; u < 4; ++u) {
+      ld_nc8_v(xp + u * 32 * kTcN, xa[u], xb[u]);
+      ld_nc8_v(ep + u * 32 * kTcN, ea[u], eb[u]);
+    }
+    // graph replay: the step scalars are a device row, requested behind the chunks (re-read per plane: three words
+    // that hit L1 / L2, instead of three registers -- or stack slots, whose store would wait for the load -- kept
+    // alive across the whole loop)
+    if (dsc != nullptr) {
+      sa = __ldg(dsc);
+      s1 = __ldg(dsc + 1);
+    }
     const int64_t l = plane / C, ch = plane % C;
     const float* yplane = y + ((l / obs_repeat) * C + ch) * (int64_t)(kTcN * kTcN) + j0;
     // the observation is read much later: pull this CTA's half plane towards L2 now
@@ -455,15 +472,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 
     // ------------------------------------------------------------------------------------ load: A1 = x_t - s1 eps
     {
-      const float* xp = x + plane * (int64_t)(kTcN * kTcN) + ld_off;
-      const float* ep = eps + plane * (int64_t)(kTcN * kTcN) + ld_off;
       uint8_t* d0 = op + (3 + ld_kb) * kKc + ld_cg * 128 + ld_r * 16;
-      // chunks 0 .. kTcAhead - 1 were requested ahead of E4 of the plane before (register budget); the rest now
-#pragma unroll
-      for (int u = kTcAhead; u < 4; ++u) {
-        ld_nc8_v(xp + u * 32 * kTcN, xa[u], xb[u]);
-        ld_nc8_v(ep + u * 32 * kTcN, ea[u], eb[u]);
-      }
       // rows above / below the image: K blocks 0..2 and 35..37 of A1 (covered by the arrival on chunk 0)
       zero_fill(op, 3 * kKc, tid);
       zero_fill(op + 35 * kKc, 3 * kKc, tid);
@@ -486,6 +495,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       }
     }
     PSX_TCTICK(0, 2)
+    // residual scale 32 * 2^floor(log2 sa) (sa is a positive normal number: sqrt of a clipped alpha-bar)
+    const float rscale = __int_as_float((__float_as_int(sa) & 0x7f800000) + (5 << 23));
     if (plane == plane0) cluster_wait_acquire();  // #0
 
     // the observation values of the first E2 task: requested now, needed ~2 us from here (nothing in between waits
@@ -618,11 +629,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 
     // the next plane's first four chunks: requested here, in flight across E4 (registers only; A1 itself is written
     // after E4 has seen P4's last commit, i.e. after the tensor cores have read A4 out of the operand buffer)
-    if (plane + pstride < planes) {
+    if (LOOP && plane + pstride < planes) {
       const float* xn = x + (plane + pstride) * (int64_t)(kTcN * kTcN) + ld_off;
       const float* en = eps + (plane + pstride) * (int64_t)(kTcN * kTcN) + ld_off;
 #pragma unroll
-      for (int u = 0; u < kTcAhead; ++u) {
+      for (int u = 0; u < kAhead; ++u) {
         ld_nc8_v(xn + u * 32 * kTcN, xa[u], xb[u]);
         ld_nc8_v(en + u * 32 * kTcN, ea[u], eb[u]);
       }
@@ -631,6 +642,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     // ------------------------------------------------------------------------------------ E4: cot
     // lane = own column, accumulator columns = image rows: every store instruction writes one 128-byte line
     {
+      step_scalars_coef(dsc, coef);  // (first needed here: not kept alive across the plane)
       const float sc = inv_scale * coef / rscale;
       float* cp = cot + plane * (int64_t)(kTcN * kTcN) + j0 + ml;
 #pragma unroll 1
@@ -751,7 +763,7 @@ static int tc_resident_clusters() {
     cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = kTcSmem;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, blur_k1_tc, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, blur_k1_tc<true>, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       n = sm_count() / 2;
     }
@@ -768,7 +780,10 @@ int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, co
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!attr[dev]) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(blur_k1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem),
+    if (int rc = check_cuda(cudaFuncSetAttribute(blur_k1_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem),
+                            "blur_k1_tc attribute"))
+      return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(blur_k1_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem),
                             "blur_k1_tc attribute"))
       return rc;
     attr[dev] = true;
@@ -776,12 +791,19 @@ int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, co
   const int64_t planes = L * op->C;
   PSX_REQUIRE(planes <= INT32_MAX / 2, "blur_k1_tc: too many planes");
   const float coef = (float)((double)w / (double)sa);
-  // persistent cluster pairs: one resident wave (74 pairs on a 148-SM part), each pair loops over its planes
-  const int64_t clusters = env_opts().tc_one_plane ? planes : std::min<int64_t>(planes, tc_resident_clusters());
-  blur_k1_tc<<<(unsigned)(clusters * 2), kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
-                                                                     op->tc_inv_scale, op->C, obs_repeat,
-                                                                     op->err_parts / op->C, sa, s1, coef, dsc,
-                                                                     (int)planes);
+  // up to one resident wave of cluster pairs (74 on a 148-SM part): a pair per plane; beyond: one resident wave of
+  // persistent pairs, each looping over its planes (PSX_TC_ONE_PLANE=1 keeps a pair per plane: several waves)
+  const int64_t resident = tc_resident_clusters();
+  if (planes <= resident || env_opts().tc_one_plane)
+    blur_k1_tc<false><<<(unsigned)(planes * 2), kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
+                                                                            op->tc_inv_scale, op->C, obs_repeat,
+                                                                            op->err_parts / op->C, sa, s1, coef, dsc,
+                                                                            (int)planes);
+  else
+    blur_k1_tc<true><<<(unsigned)(resident * 2), kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
+                                                                             op->tc_inv_scale, op->C, obs_repeat,
+                                                                             op->err_parts / op->C, sa, s1, coef, dsc,
+                                                                             (int)planes);
   return check_cuda(cudaGetLastError(), "blur_k1_tc launch");
 }
 
