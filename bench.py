@@ -388,8 +388,10 @@ def roofline_by_config(device, peak: float) -> list:
     makers = {"identity": lambda: pops.IdentityOperator(SHAPE),
               "mask70": lambda: pops.RandomInpaintingOperator(SHAPE, 0.7, flatten=False),
               "box4": lambda: pops.BoxDownsampleOperator(SHAPE, 4),
+              "maskbox4": lambda: pops.MaskedBoxDownsampleOperator(SHAPE, 4, missing_fraction=0.7),
               "gblur61": lambda: pops.GaussianBlurOperator(SHAPE, 61, 3.0)}
-    for kind, L in (("gblur61", 16), ("gblur61", 64), ("identity", 16), ("identity", 64), ("mask70", 64), ("box4", 64)):
+    for kind, L in (("gblur61", 16), ("gblur61", 64), ("identity", 16), ("identity", 64), ("mask70", 64), ("box4", 64),
+                    ("maskbox4", 64)):
         op = makers[kind]().to(device)
         nat = op._native_cached(device)
         n = nat.n
@@ -420,7 +422,9 @@ def roofline_by_config(device, peak: float) -> list:
         out.append({"operator": kind, "L": L, "k1_us": m1 * 1e3, "k2_us": m2 * 1e3,
                     "k1_frac": b1 / m1 / 1e6 / peak, "k2_frac": b2 / m2 / 1e6 / peak,
                     "fused_gbs": (b1 + b2) / (m1 + m2) / 1e6, "fused_frac": (b1 + b2) / (m1 + m2) / 1e6 / peak,
-                    "timing": f"ring of {nsets} cold buffer sets, the ring pass replayed as one CUDA graph"})
+                    "timing": f"ring of {nsets} cold buffer sets, the ring pass replayed as one CUDA graph; the L "
+                              "reconstructions share ONE observation (as in configs 2-3), which stays in L2: of the 16 "
+                              "algorithmic B/elem of K1, 4 do not come from HBM -- fractions above 1 are that"})
         del S
         torch.cuda.empty_cache()
     return out

@@ -41,7 +41,7 @@ extern "C" {
 #define PSX_ERR_UNSUPPORTED 3 /* valid request this build has no kernel for  */
 
 #define PSX_MAX_TAPS 127  /* longest 1-D tap vector of a separable blur       */
-#define PSX_ABI_VERSION 3
+#define PSX_ABI_VERSION 4
 
 /* Operator kinds (psx_op_kind). */
 #define PSX_OP_IDENTITY 0
@@ -78,6 +78,11 @@ PSX_API int psx_op_create_identity(int64_t n, psx_op** out);
 PSX_API int psx_op_create_mask(int64_t n, const uint8_t* d_keep, psx_op** out);
 /* mean over non-overlapping factor x factor blocks; y is (C, H/f, W/f). */
 PSX_API int psx_op_create_box(int C, int H, int W, int factor, psx_op** out);
+/* BASELINE config 3 read as ONE composed operator, y = keep * box_f(x) (random-mask inpainting of the 4x
+ * box-downsampled image; no counterpart in the reference, defined by oracle/operators.py: OracleMaskedBox):
+ * d_keep has C * (H/f) * (W/f) bytes, 1 = coarse pixel observed.  Dense form: y is (C, H/f, W/f) with zeros at
+ * the dropped pixels.  Not served by the bf16-state entry points. */
+PSX_API int psx_op_create_box_masked(int C, int H, int W, int factor, const uint8_t* d_keep, psx_op** out);
 /* y = V(H(x)): zero-padded "same" cross-correlation of every row with
  * h_taps_h (length kh, odd) then of every column with h_taps_v (length kv, odd). */
 PSX_API int psx_op_create_sepblur(int C, int H, int W, const float* h_taps_h, int kh,

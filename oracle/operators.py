@@ -216,3 +216,23 @@ class OracleBoxDownsample(OracleOperator):
     def pinv(self, y):  # A A^T = I / f^2  =>  A^+ = f^2 A^T = replicate
         f = self.factor
         return y.repeat_interleave(f, dim=-2).repeat_interleave(f, dim=-1)
+
+
+class OracleMaskedBox(OracleBoxDownsample):
+    """BASELINE config 3 read as one composed operator: y = keep * box_f(x), ``keep`` a 0/1 array over the coarse
+    grid (dense form, zeros at the dropped pixels).  Neither factor exists in the reference; this
+    class is the definition the CUDA path is checked against.  A A^T = diag(keep) / f^2."""
+
+    def __init__(self, x_shape, factor: int, keep: Tensor):
+        super().__init__(x_shape, factor)
+        assert tuple(keep.shape) == self.y_shape
+        self.kept = keep.to(torch.float32)
+
+    def apply(self, x):
+        return super().apply(x) * self.kept.to(x)
+
+    def adjoint(self, y):
+        return super().adjoint(y * self.kept.to(y))
+
+    def pinv(self, y):
+        return super().pinv(y * self.kept.to(y))

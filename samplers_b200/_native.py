@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libpsx.so")
 
 PSX_OK, PSX_ERR_INVALID, PSX_ERR_CUDA, PSX_ERR_UNSUPPORTED = 0, 1, 2, 3
 OP_IDENTITY, OP_MASK, OP_BOX, OP_SEPBLUR, OP_CONV2D = range(5)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes); must list every prototype of include/psx.h
 _f32p, _i64, _vp, _f = C.c_void_p, C.c_int64, C.c_void_p, C.c_float
@@ -28,6 +28,7 @@ PROTOTYPES = {
     "psx_op_create_identity": (C.c_int, [_i64, C.POINTER(_opp)]),
     "psx_op_create_mask": (C.c_int, [_i64, _vp, C.POINTER(_opp)]),
     "psx_op_create_box": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_opp)]),
+    "psx_op_create_box_masked": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(_opp)]),
     "psx_op_create_sepblur": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
                                         C.POINTER(C.c_float), C.c_int, C.POINTER(_opp)]),
     "psx_op_create_conv2d": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int,
@@ -190,6 +191,14 @@ class NativeOp:
         h = _opp()
         check(load().psx_op_create_box(c, hh, w, factor, C.byref(h)))
         return NativeOp(h.value)
+
+    @staticmethod
+    def box_masked(c: int, hh: int, w: int, factor: int, keep_u8: torch.Tensor) -> "NativeOp":
+        assert keep_u8.is_cuda and keep_u8.dtype == torch.uint8 and keep_u8.is_contiguous()
+        assert keep_u8.numel() == c * (hh // factor) * (w // factor)
+        h = _opp()
+        check(load().psx_op_create_box_masked(c, hh, w, factor, keep_u8.data_ptr(), C.byref(h)))
+        return NativeOp(h.value, keepalive=(keep_u8,))
 
     @staticmethod
     def sepblur(c: int, hh: int, w: int, taps_h, taps_v) -> "NativeOp":

@@ -172,6 +172,13 @@ PSX_API int psx_op_create_box(int C, int H, int W, int factor, psx_op** out) {
   return PSX_OK;
 }
 
+PSX_API int psx_op_create_box_masked(int C, int H, int W, int factor, const uint8_t* d_keep, psx_op** out) {
+  PSX_REQUIRE(d_keep != nullptr, "psx_op_create_box_masked: need a device keep-mask over the coarse grid");
+  if (int rc = psx_op_create_box(C, H, W, factor, out)) return rc;
+  (*out)->d_keep = d_keep;  // C * (H / factor) * (W / factor) bytes, caller-owned
+  return PSX_OK;
+}
+
 PSX_API int psx_op_create_sepblur(int C, int H, int W, const float* h_taps_h, int kh, const float* h_taps_v,
                           int kv, psx_op** out) {
   PSX_REQUIRE(out && C > 0 && H > 0 && W > 0, "psx_op_create_sepblur: bad shape");
@@ -517,6 +524,8 @@ PSX_API int psx_dps_pre_bf16(const psx_op* op, const void* d_x_t, const void* d_
               "psx_dps_pre_bf16: non-finite or non-positive schedule scalar");
   const bool dev = d_step_row != nullptr;
   const float sa = dev ? 1.f : sqrt_acp, s1 = dev ? 0.f : sqrt_1m_acp, w = dev ? 1.f : lik_weight;
+  if (op->kind == PSX_OP_BOX && op->d_keep)
+    return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre_bf16: the masked box operator runs on an fp32 state only");
   if (op->kind == PSX_OP_BOX)
     return launch_pre_box_bf16(op, d_x_t, d_eps, d_y, L, obs_repeat, sa, s1, w, d_step_row, d_cot, d_err_part,
                                (cudaStream_t)stream);

@@ -191,8 +191,8 @@ template <> struct RowVec<4> { using T = float4; };
 template <int F>
 __global__ void __launch_bounds__(kThreads)
 k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
-       float* __restrict__ cot, float* __restrict__ err_part, int slots, float* __restrict__ x0_out,
-       int planes, int H, int W, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef, const float* __restrict__ dsc) {
+       const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part, int slots,
+       float* __restrict__ x0_out, int planes, int H, int W, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef, const float* __restrict__ dsc) {
   step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
@@ -235,9 +235,12 @@ k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* 
       }
     }
     const float avg = __fmul_rn(s, inv);  // F*F is a power of two for F = 2, 4, 8: exact scaling
-    const float r = __fsub_rn(__ldg(y + (l / obs_repeat) * ny + q), avg);
+    // composed operator mask o box (keep != nullptr): (A x0)[q] = 0 at a dropped coarse pixel -- the residual there is
+    // y itself (it counts in |r|^2 exactly as in the oracle; a pre-masked observation makes it 0) and A^T drops it
+    const bool kept = keep == nullptr || __ldg(keep + q) != 0;
+    const float r = __fsub_rn(__ldg(y + (l / obs_repeat) * ny + q), kept ? avg : 0.f);
     acc = fmaf(r, r, acc);
-    const float d = __fmul_rn(coef, __fmul_rn(r, inv));
+    const float d = kept ? __fmul_rn(coef, __fmul_rn(r, inv)) : 0.f;
 #pragma unroll
     for (int dy = 0; dy < F; ++dy) {
       if constexpr (F == 4) {
@@ -262,8 +265,8 @@ k1_box(const float* __restrict__ x, const float* __restrict__ eps, const float* 
 // generic factor (not a power of two): division by F*F as the oracle does
 __global__ void __launch_bounds__(kThreads)
 k1_box_any(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
-           float* __restrict__ cot, float* __restrict__ err_part, int slots, float* __restrict__ x0_out,
-           int planes, int H, int W, int F, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef, const float* __restrict__ dsc) {
+           const uint8_t* __restrict__ keep, float* __restrict__ cot, float* __restrict__ err_part, int slots,
+           float* __restrict__ x0_out, int planes, int H, int W, int F, int64_t chunk, int64_t obs_repeat, float sa, float s1, float coef, const float* __restrict__ dsc) {
   step_scalars_k1(dsc, sa, s1, coef);
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
@@ -286,9 +289,10 @@ k1_box_any(const float* __restrict__ x, const float* __restrict__ eps, const flo
         if (x0_out) x0_out[off + (int64_t)dy * W + dx] = v;
         s = __fadd_rn(s, v);
       }
-    const float r = __fsub_rn(y[(l / obs_repeat) * ny + q], __fdiv_rn(s, ff));
+    const bool kept = keep == nullptr || keep[q] != 0;
+    const float r = __fsub_rn(y[(l / obs_repeat) * ny + q], kept ? __fdiv_rn(s, ff) : 0.f);
     acc = fmaf(r, r, acc);
-    const float d = __fmul_rn(coef, __fdiv_rn(r, ff));
+    const float d = kept ? __fmul_rn(coef, __fdiv_rn(r, ff)) : 0.f;
     for (int dy = 0; dy < F; ++dy)
       for (int dx = 0; dx < F; ++dx) cot[off + (int64_t)dy * W + dx] = d;
   }
@@ -312,7 +316,7 @@ int launch_pre_box(const psx_op* op, const float* x, const float* eps, const flo
     if (!rs) rs = resident_slots(KERNEL);                                                             \
     const int parts = one_wave_parts(rs, L, op->n_y, slots);                                          \
     const int64_t chunk = (op->n_y + parts - 1) / parts;                                              \
-    KERNEL<<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(x, eps, y, cot, err_part, slots, x0_out,    \
+    KERNEL<<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(x, eps, y, op->d_keep, cot, err_part, slots, x0_out, \
                                                           op->C, op->H, op->W, __VA_ARGS__ chunk,     \
                                                           obs_repeat, sa, s1, coef, dsc);             \
   }
@@ -760,8 +764,8 @@ k_mask_apply(const float* __restrict__ in, const uint8_t* __restrict__ keep, flo
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_box_apply(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W, int F,
-            int64_t total_y) {
+k_box_apply(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ keep, int64_t n_y,
+            int planes, int H, int W, int F, int64_t total_y) {
   const int Hc = H / F, Wc = W / F;
   const bool pow2 = (F & (F - 1)) == 0;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_y;
@@ -774,13 +778,14 @@ k_box_apply(const float* __restrict__ x, float* __restrict__ y, int planes, int 
     float s = 0.f;
     for (int dy = 0; dy < F; ++dy)
       for (int dx = 0; dx < F; ++dx) s = __fadd_rn(s, x[off + (int64_t)dy * W + dx]);
-    y[q] = pow2 ? __fmul_rn(s, 1.0f / (float)(F * F)) : __fdiv_rn(s, (float)(F * F));
+    const float avg = pow2 ? __fmul_rn(s, 1.0f / (float)(F * F)) : __fdiv_rn(s, (float)(F * F));
+    y[q] = (keep == nullptr || keep[q % n_y]) ? avg : 0.f;
   }
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_box_adjoint(const float* __restrict__ y, float* __restrict__ x, int planes, int H, int W, int F,
-              int64_t total_x) {
+k_box_adjoint(const float* __restrict__ y, float* __restrict__ x, const uint8_t* __restrict__ keep, int64_t n_y,
+              int planes, int H, int W, int F, int64_t total_x) {
   const int Hc = H / F, Wc = W / F;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_x;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -788,7 +793,8 @@ k_box_adjoint(const float* __restrict__ y, float* __restrict__ x, int planes, in
     const int64_t t = i / W;
     const int py = (int)(t % H);
     const int64_t pl = t / H;
-    x[i] = __fdiv_rn(y[(pl * Hc + py / F) * Wc + px / F], (float)(F * F));
+    const int64_t q = (pl * Hc + py / F) * Wc + px / F;
+    x[i] = (keep == nullptr || keep[q % n_y]) ? __fdiv_rn(y[q], (float)(F * F)) : 0.f;
   }
 }
 
@@ -845,11 +851,11 @@ int launch_op_pointwise(const psx_op* op, bool adjoint, const float* in, float* 
       break;
     case PSX_OP_BOX:
       if (!adjoint)
-        k_box_apply<<<blocks_for(total_y), kThreads, 0, st>>>(in, out, op->C, op->H, op->W, op->factor,
-                                                              total_y);
+        k_box_apply<<<blocks_for(total_y), kThreads, 0, st>>>(in, out, op->d_keep, op->n_y, op->C, op->H, op->W,
+                                                              op->factor, total_y);
       else
-        k_box_adjoint<<<blocks_for(total_x), kThreads, 0, st>>>(in, out, op->C, op->H, op->W, op->factor,
-                                                                total_x);
+        k_box_adjoint<<<blocks_for(total_x), kThreads, 0, st>>>(in, out, op->d_keep, op->n_y, op->C, op->H, op->W,
+                                                                op->factor, total_x);
       break;
     default:
       return fail(PSX_ERR_INVALID, "launch_op_pointwise: wrong operator kind");

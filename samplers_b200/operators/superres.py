@@ -3,6 +3,7 @@ the reference).  A = mean over non-overlapping f x f blocks, A^T = replicate / f
 A^+ = replicate (A A^T = I / f^2).  Convention: oracle/operators.py."""
 from __future__ import annotations
 
+import torch
 from torch import Tensor
 
 from .. import _native
@@ -44,3 +45,29 @@ class BoxDownsampleOperator(LinearOperator):
 
 
 SuperResolutionOperator = BoxDownsampleOperator
+
+
+class MaskedBoxDownsampleOperator(BoxDownsampleOperator):
+    """BASELINE config 3 read as ONE operator: y = keep * box_f(x) -- the ``factor`` x ``factor`` box average followed
+    by a pixel mask on the coarse grid (dense form: zeros where ``mask`` is True = missing, the convention of
+    ``InpaintingOperator``).  The reference has neither factor; the arithmetic is defined by
+    ``oracle/operators.py: OracleMaskedBox``.  K1 is the box kernel with the residual zeroed at dropped pixels."""
+
+    def __init__(self, x_shape: Shape, factor: int = 4, mask: Tensor | None = None, missing_fraction: float = 0.7,
+                 seed: int = 0, device: Device = None):
+        super().__init__(x_shape, factor, device=device)
+        target = torch.device(device) if device is not None else (mask.device if mask is not None else torch.device("cpu"))
+        if mask is None:
+            g = torch.Generator().manual_seed(int(seed))
+            mask = torch.rand(self.y_shape, generator=g) < float(missing_fraction)
+        mask = mask.to(target)
+        if mask.dtype != torch.bool:
+            mask = mask.ne(0)
+        if tuple(mask.shape) != tuple(self.y_shape):
+            raise ValueError(f"Mask shape incompatible with the coarse grid: {tuple(mask.shape)} vs. {self.y_shape}.")
+        self.register_buffer("mask", mask)
+
+    def _native(self, device):
+        c, h, w = self.x_shape
+        keep = (~self.mask).to(device=device, dtype=torch.uint8).contiguous()
+        return _native.NativeOp.box_masked(c, h, w, self.factor, keep)

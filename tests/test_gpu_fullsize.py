@@ -58,12 +58,21 @@ def _dev_op(o):
     return o
 
 
+def _coarse_keep(shape, f, frac, seed):
+    """The keep array MaskedBoxDownsampleOperator(missing_fraction=frac, seed=seed) draws."""
+    g = torch.Generator().manual_seed(seed)
+    return (~(torch.rand((shape[0], shape[1] // f, shape[2] // f), generator=g) < frac)).float()
+
+
 CASES = {
     # config 2: Gaussian blur 61x61 sigma 3, batch 16
     "cfg2_blur_L16": (16, lambda p: p.GaussianBlurOperator(FULL), lambda: oops.OracleGaussianBlur(FULL, 61, 3.0)),
     # config 3: random mask 70 % (dense form) and 4x box super-resolution, batch 64
     "cfg3_mask_L64": (64, lambda p: p.RandomInpaintingOperator(FULL, 0.7, seed=0, flatten=False), None),
     "cfg3_box4_L64": (64, lambda p: p.BoxDownsampleOperator(FULL, 4), lambda: oops.OracleBoxDownsample(FULL, 4)),
+    # config 3 read as ONE composed operator: 70 % of the 4x box-downsampled pixels dropped
+    "cfg3_maskbox4_L64": (64, lambda p: p.MaskedBoxDownsampleOperator(FULL, 4, missing_fraction=0.7, seed=0),
+                          lambda: oops.OracleMaskedBox(FULL, 4, _coarse_keep(FULL, 4, 0.7, 0))),
 }
 
 

@@ -30,6 +30,9 @@ def _pairs(shape, seed=3):
     for f in (2, 3, 4, 8):
         if h % f == 0 and w % f == 0:
             out[f"box{f}"] = (pops.BoxDownsampleOperator(shape, f), oops.OracleBoxDownsample(shape, f))
+            cm = torch.rand(c, h // f, w // f, generator=g) < 0.7   # True = missing coarse pixel
+            out[f"maskbox{f}"] = (pops.MaskedBoxDownsampleOperator(shape, f, mask=cm),
+                                  oops.OracleMaskedBox(shape, f, (~cm).float()))
     return out
 
 

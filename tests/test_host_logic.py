@@ -53,7 +53,7 @@ def test_abi_argument_validation_without_gpu():
     assert lib.psx_op_destroy(h) == _native.PSX_OK
     taps3 = (C.c_float * 3)(0.25, 0.5, 0.25)
     assert lib.psx_op_create_sepblur(3, 8, 8, taps3, 3, taps3, 3, C.byref(h)) == _native.PSX_OK
-    assert lib.psx_op_workspace_bytes(h, 2) == 2 * 3 * 8 * 8 * 4
+    assert lib.psx_op_workspace_bytes(h, 2) == 2 * (2 * 3 * 8 * 8 * 4)   # h1 and h2 of the CUDA-core K1: two regions
     lib.psx_op_destroy(h)
 
 

@@ -21,6 +21,7 @@ def _ops():
         "motion_walk": oops.OracleConv2dBlur(shape, oops.motion_walk_kernel(13, 0.5, seed=1)),
         "box4": oops.OracleBoxDownsample(shape, 4),
         "box2": oops.OracleBoxDownsample(shape, 2),
+        "maskbox4": oops.OracleMaskedBox(shape, 4, (torch.rand(3, 5, 7, generator=g) >= 0.7).float()),
     }
 
 
@@ -56,3 +57,14 @@ def test_separable_equals_outer_product_2d():
 def test_motion_kernels_sum_to_one():
     assert abs(float(oops.motion_line_kernel(61, 45.0).sum()) - 1) < 1e-5
     assert abs(float(oops.motion_walk_kernel(61, 0.5).sum()) - 1) < 1e-5
+
+
+def test_masked_box_is_mask_after_box_and_has_its_pseudo_inverse():
+    shape = (3, 16, 24)
+    g = torch.Generator().manual_seed(5)
+    keep = (torch.rand(3, 4, 6, generator=g) >= 0.7).double()
+    op, box = oops.OracleMaskedBox(shape, 4, keep), oops.OracleBoxDownsample(shape, 4)
+    x = torch.randn(2, *shape, generator=g, dtype=torch.float64)
+    y = op.apply(x)
+    assert torch.equal(y, box.apply(x) * keep) and torch.all(y[:, keep == 0] == 0)
+    assert torch.allclose(op.apply(op.pinv(y)), y, atol=1e-12)          # A A^+ y = y on the range of A
