@@ -111,15 +111,19 @@ k1_pointwise_s(const float* __restrict__ x, const float* __restrict__ eps, const
 
 // ---- grid sizing: ONE wave.  A kernel this short (tens of microseconds) loses 10-25 % to a partial
 // second wave, so the per-sample part count is chosen such that parts * L <= resident CTA slots.
-static int g_sm_count = 0;
+// SM count of the CURRENT device (cached per device ordinal; the per-kernel occupancy figures cached at the launch
+// sites are blocks per SM times this and assume what the north star names: one process per GPU of a homogeneous box).
 int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cached[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
   }
-  return g_sm_count;
+  return cached[dev];
 }
 template <typename K>
 int resident_slots(K kernel) {
