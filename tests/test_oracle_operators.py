@@ -68,3 +68,45 @@ def test_masked_box_is_mask_after_box_and_has_its_pseudo_inverse():
     y = op.apply(x)
     assert torch.equal(y, box.apply(x) * keep) and torch.all(y[:, keep == 0] == 0)
     assert torch.allclose(op.apply(op.pinv(y)), y, atol=1e-12)          # A A^+ y = y on the range of A
+
+
+def test_oracle_blur_box_and_motion_against_independent_implementations():
+    """The blur / motion / box operators have no counterpart in the reference, so the oracle is their definition;
+    here it is cross-checked against implementations that share no code with it: scipy.ndimage (separable and 2-D
+    zero-padded correlation), a numpy reshape-mean (box) and the closed form of the sampled Gaussian."""
+    import numpy as np
+    from scipy import ndimage
+    shape = (2, 20, 28)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1, *shape, generator=g, dtype=torch.float64)
+    # taps: exp(-i^2 / (2 sigma^2)) normalised to sum 1
+    w = oops.gaussian_taps(9, 1.5).double().numpy()
+    i = np.arange(9) - 4
+    ref_w = np.exp(-i ** 2 / (2 * 1.5 ** 2))
+    assert np.allclose(w, ref_w / ref_w.sum(), atol=1e-7)
+    # separable blur: rows with taps_h, then columns with taps_v (asymmetric taps on purpose: correlation, not convolution)
+    th, tv = torch.rand(7, generator=g, dtype=torch.float64), torch.rand(5, generator=g, dtype=torch.float64)
+    sep = oops.OracleSeparableBlur(shape, th, tv)
+    sep.taps_h, sep.taps_v = th, tv
+    got = sep.apply(x)[0].numpy()
+    for c in range(shape[0]):
+        r = ndimage.correlate1d(x[0, c].numpy(), th.numpy(), axis=1, mode="constant", cval=0.0)
+        r = ndimage.correlate1d(r, tv.numpy(), axis=0, mode="constant", cval=0.0)
+        assert np.allclose(got[c], r, atol=1e-12)
+    # adjoint = correlation with the flipped taps = convolution
+    gt = sep.adjoint(x)[0].numpy()
+    for c in range(shape[0]):
+        r = ndimage.convolve1d(x[0, c].numpy(), tv.numpy(), axis=0, mode="constant", cval=0.0)
+        r = ndimage.convolve1d(r, th.numpy(), axis=1, mode="constant", cval=0.0)
+        assert np.allclose(gt[c], r, atol=1e-12)
+    # 2-D PSF
+    k2 = oops.motion_line_kernel(11, 30.0).double()
+    op2 = oops.OracleConv2dBlur(shape, k2)
+    op2.kernel2d = k2
+    got2 = op2.apply(x)[0].numpy()
+    for c in range(shape[0]):
+        assert np.allclose(got2[c], ndimage.correlate(x[0, c].numpy(), k2.numpy(), mode="constant", cval=0.0), atol=1e-12)
+    # box: mean over non-overlapping 4 x 4 blocks
+    box = oops.OracleBoxDownsample(shape, 4).apply(x)[0].numpy()
+    ref = x[0].numpy().reshape(shape[0], shape[1] // 4, 4, shape[2] // 4, 4).mean(axis=(2, 4))
+    assert np.allclose(box, ref, atol=1e-12)
