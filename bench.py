@@ -529,7 +529,7 @@ def multi_gpu_parity(device, rank: int, world: int) -> dict:
     """Run under torchrun after the timed region (tiny networks, < 2 s): (1) DPS reconstructions sharded over the ranks
     (sample_posterior: gather + moment all-reduce) equal the same reconstructions computed on one rank; (2) PSLD with
     `process_group` (batch-global norms all-reduced, one scalar per norm) equals the full-batch run of one rank,
-    sample for sample.  Errors are the max over ranks."""
+    sample for sample; (3) the same for ReSample.  Errors are the max over ranks."""
     import torch.distributed as dist
     from samplers_b200 import operators as P
     from samplers_b200.distributed import sample_posterior
@@ -599,6 +599,26 @@ def multi_gpu_parity(device, rank: int, world: int) -> dict:
         e = torch.tensor([float((mine[0] - fullb[rank]).abs().max() / fullb.abs().max())], device=device, dtype=torch.float64)
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         res["psld_process_group_vs_full_batch"] = {"batch": world, "rel_err": float(e[0])}
+        # ---- (3) ReSample, the same way (MSE / norm sums all-reduced per conditioning step and optimiser iteration)
+        from samplers_b200.samplers import ReSampleSampler
+        rkw = dict(num_sampling_steps=8, sigma_scale=40.0, max_optimization_iters=6, eta=1.0, inter_timesteps=2,
+                   time_travel_interval=2, stage_splits=3)
+
+        def run_resample(lo, hi, group):
+            count = [0]
+
+            def draw(sh, dev, dtype):   # draw i of the full batch, this rank's rows (every draw is batch-leading)
+                count[0] += 1
+                full = torch.randn((world,) + tuple(sh[1:]), generator=torch.Generator().manual_seed(300 + count[0]))
+                return full[lo:hi].to(dev)
+            s = ReSampleSampler(lnet, process_group=group)
+            s.draw = draw
+            return s(probl, num_reconstructions=hi - lo, condition=cond, **rkw)
+        mine = run_resample(rank, rank + 1, dist.group.WORLD).reshape(1, *xs)
+        fullb = run_resample(0, world, None).reshape(world, *xs)
+        e = torch.tensor([float((mine[0] - fullb[rank]).abs().max() / fullb.abs().max())], device=device, dtype=torch.float64)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        res["resample_process_group_vs_full_batch"] = {"batch": world, "rel_err": float(e[0])}
     except Exception as exc:   # reported, never silent
         res["error"] = f"{type(exc).__name__}: {exc}"[:300]
     finally:
