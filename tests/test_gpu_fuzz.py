@@ -18,7 +18,7 @@ def _cases(kind, count, seed):
     out = []
     for _ in range(count):
         c = rng.choice([1, 2, 3, 4])
-        if kind == "box":
+        if kind in ("box", "maskbox"):
             f = rng.choice([2, 3, 4, 8])
             h, w = f * rng.randint(1, 12), f * rng.randint(1, 12)
             extra = f
@@ -75,6 +75,9 @@ def _build(kind, shape, extra):
         return P.InpaintingOperator(shape, mask, flatten=True), oops.OracleMaskGather(shape, mask), None
     if kind == "box":
         return P.BoxDownsampleOperator(shape, extra), oops.OracleBoxDownsample(shape, extra), None
+    if kind == "maskbox":   # config 3 as one operator: mask on the coarse grid after the box average
+        op = P.MaskedBoxDownsampleOperator(shape, extra, missing_fraction=0.6, seed=shape[1] * 131 + shape[2])
+        return op, oops.OracleMaskedBox(shape, extra, (~op.mask).float()), None
     if kind == "blur":
         return P.GaussianBlurOperator(shape, extra[0], extra[1]), oops.OracleGaussianBlur(shape, extra[0], extra[1]), None
     if kind == "sep":
@@ -101,7 +104,7 @@ def test_blur_heights_between_128_and_256_regression():
         assert rel_err(op.apply_transpose(x).cpu(), ora.adjoint(x).cpu()) < 3e-6
 
 
-@pytest.mark.parametrize("kind,env", [("identity", None), ("mask", None), ("box", None), ("blur", None),
+@pytest.mark.parametrize("kind,env", [("identity", None), ("mask", None), ("box", None), ("maskbox", None), ("blur", None),
                                       ("blur", "PSX_NO_FAST16"), ("blur", "PSX_NO_PIPE"), ("blur", "PSX_SPLIT"),
                                       ("sep", None), ("sep", "PSX_NO_FAST16"), ("motion", None)])
 def test_random_geometries(psx_env, kind, env):
@@ -117,7 +120,7 @@ def test_random_geometries(psx_env, kind, env):
         shape = (c, h, w)
         op, ora, keep = _build(kind, shape, extra)
         op = op.to(DEV)
-        for name in ("taps_h", "taps_v", "kernel2d"):
+        for name in ("taps_h", "taps_v", "kernel2d", "kept"):
             if hasattr(ora, name):
                 setattr(ora, name, getattr(ora, name).to(DEV))
         nat = op._native_cached(torch.device(DEV))
