@@ -1539,12 +1539,40 @@ __device__ __forceinline__ void c2_chunk(float (&acc)[kC2Rows][8], float (&win)[
       for (int h = 0; h < kC2Rows; ++h) acc[h][q] = fmaf(tw[i], win[h][(q + i + 4 * R) % 12], acc[h][q]);
 }
 
+// The same chunk on 32-bit shared-memory addresses (tile row and tap group both in shared memory): explicit ld.shared,
+// so that no generic-to-shared window arithmetic is re-derived per segment.
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+template <int R>
+__device__ __forceinline__ void c2_chunk_s(float (&acc)[kC2Rows][8], float (&win)[kC2Rows][12], uint32_t row,
+                                           uint32_t row_step_b, uint32_t w4) {
+  constexpr int S = (8 + 4 * R) % 12;  // slot of the incoming columns
+#pragma unroll
+  for (int h = 0; h < kC2Rows; ++h) {
+    const float4 v = lds128(row + h * row_step_b);
+    win[h][S] = v.x; win[h][S + 1] = v.y; win[h][S + 2] = v.z; win[h][S + 3] = v.w;
+  }
+  const float4 t = lds128(w4);
+  const float tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int h = 0; h < kC2Rows; ++h) acc[h][q] = fmaf(tw[i], win[h][(q + i + 4 * R) % 12], acc[h][q]);
+}
+
 // 2-D (motion) PSFs.  The PSF is a list of row segments (psx_common.cuh: RowSeg): every PSF row is a short 1-D
 // correlation, evaluated as a sliding register window -- per chunk of 4 taps a thread issues 2 LDS.128 + one
 // broadcast tap load for 64 FMAs (8 outputs x 2 rows), against one load per FMA of a tap-by-tap gather.
 // grid = (tilesX, tilesY, planes).  Thread q: column group cg (8 columns) and rows rp, rp + 16 of the 32 x 64 tile;
 // a quarter-warp covers 4 column groups x 2 consecutive rows, conflict-free for LDS.128 because pitch / 4 is odd.
-template <int MODE>
+// STAB: the taps and segments were copied behind the tile (nw4 > 0): they are then read with shared-memory loads from
+// compile-time-known address space (a pointer that may be either costs generic LD.E plus a 16-bit load per field).
+template <int MODE, bool STAB>
 __global__ void __launch_bounds__(kC2Threads)
 conv2d_rowseg(const float* __restrict__ in, const float* __restrict__ eps, const float* __restrict__ y,
               float* __restrict__ out, float* __restrict__ err_part, const RowSeg* __restrict__ segs,
@@ -1560,13 +1588,11 @@ conv2d_rowseg(const float* __restrict__ in, const float* __restrict__ eps, const
   const int64_t plane = pl * H * W;
   // nw4 > 0: the launcher reserved room behind the tile for a copy of the taps and segments -- shared-memory
   // broadcasts (~30 cycles) instead of L1-hit global loads (~200) at the head of every chunk's FMA chain
-  if (nw4 > 0) {
-    float4* sw4 = reinterpret_cast<float4*>(smem + th * pitch);
-    RowSeg* ssg = reinterpret_cast<RowSeg*>(sw4 + nw4);
+  float4* const sw4 = reinterpret_cast<float4*>(smem + th * pitch);
+  RowSeg* const ssg = reinterpret_cast<RowSeg*>(sw4 + (STAB ? nw4 : 0));
+  if (STAB) {
     for (int i = threadIdx.x; i < nw4; i += kC2Threads) sw4[i] = w4[i];
     for (int i = threadIdx.x; i < nseg; i += kC2Threads) ssg[i] = segs[i];
-    w4 = sw4;
-    segs = ssg;
   }
 
   if ((W & 3) == 0) {
@@ -1616,30 +1642,84 @@ conv2d_rowseg(const float* __restrict__ in, const float* __restrict__ eps, const
   for (int h = 0; h < kC2Rows; ++h)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[h][j] = 0.f;
-  const float* base = smem + (rp - dy_lo) * pitch + (8 * cg - dx_lo);
-  RowSeg nxt = segs[0];
-  for (int sgi = 0; sgi < nseg; ++sgi) {
-    const RowSeg sg = nxt;
-    if (sgi + 1 < nseg) nxt = segs[sgi + 1];  // in flight while this segment computes
-    const float* row = base + sg.dy * pitch + sg.dx0;
-    const float4* wp = w4 + sg.w4_off;
-    float win[kC2Rows][12];
+  // The thread's tile offset takes a round trip through shared memory: left alone, ptxas re-derives it from %tid for
+  // every segment (S2R + 10 integer instructions of a ~50-instruction segment prologue; ncu source view), and an
+  // empty asm does not stop it.
+  int boff = (rp - dy_lo) * pitch + (8 * cg - dx_lo);
+  // (the same for the three shared-memory base addresses of the loop, which would otherwise be rebuilt per segment from
+  // %cluster_ctaid and the shared window base on the uniform datapath: ~25 instructions)
+  uint32_t base_s = (uint32_t)__cvta_generic_to_shared(smem) + 4u * (uint32_t)boff;
+  uint32_t wtab_s = (uint32_t)__cvta_generic_to_shared(sw4), seg_s = (uint32_t)__cvta_generic_to_shared(ssg);
+  {
+    __shared__ int spin[4 * kC2Threads];
+    volatile int* vb = spin;
+    vb[q] = boff;
+    vb[q + kC2Threads] = (int)base_s;
+    vb[q + 2 * kC2Threads] = (int)wtab_s;
+    vb[q + 3 * kC2Threads] = (int)seg_s;
+    boff = vb[q];
+    base_s = (uint32_t)vb[q + kC2Threads];
+    wtab_s = (uint32_t)vb[q + 2 * kC2Threads];
+    seg_s = (uint32_t)vb[q + 3 * kC2Threads];
+  }
+  static_assert(sizeof(RowSeg) == 8, "a segment is read as one 64-bit word");  // {dy | dx0 << 16, nch | w4_off << 16}
+  if (STAB) {
+    // everything the loop touches is in shared memory: 32-bit shared addresses, explicit ld.shared
+    const uint32_t row_step_b = 4u * (uint32_t)row_step;
+    int2 nxt;
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(nxt.x), "=r"(nxt.y) : "r"(seg_s));
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+      const int2 sg = nxt;
+      if (sgi + 1 < nseg)  // in flight while this segment computes
+        asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(nxt.x), "=r"(nxt.y) : "r"(seg_s + 8u * (uint32_t)(sgi + 1)));
+      const int sg_dy = (int)(short)(sg.x & 0xffff), sg_dx0 = sg.x >> 16;
+      uint32_t row = base_s + 4u * (uint32_t)(sg_dy * pitch + sg_dx0);
+      uint32_t wp = wtab_s + 16u * ((uint32_t)sg.y >> 16);
+      float win[kC2Rows][12];
 #pragma unroll
-    for (int h = 0; h < kC2Rows; ++h) {
-      const float4 a0 = *reinterpret_cast<const float4*>(row + h * row_step);
-      const float4 a1 = *reinterpret_cast<const float4*>(row + h * row_step + 4);
-      win[h][0] = a0.x; win[h][1] = a0.y; win[h][2] = a0.z; win[h][3] = a0.w;
-      win[h][4] = a1.x; win[h][5] = a1.y; win[h][6] = a1.z; win[h][7] = a1.w;
+      for (int h = 0; h < kC2Rows; ++h) {
+        const float4 a0 = lds128(row + h * row_step_b), a1 = lds128(row + h * row_step_b + 16);
+        win[h][0] = a0.x; win[h][1] = a0.y; win[h][2] = a0.z; win[h][3] = a0.w;
+        win[h][4] = a1.x; win[h][5] = a1.y; win[h][6] = a1.z; win[h][7] = a1.w;
+      }
+      row += 32;
+      int nch = (int)(short)(sg.y & 0xffff);
+      for (; nch >= 3; nch -= 3, row += 48, wp += 48) {  // the window rotation has period 3
+        c2_chunk_s<0>(acc, win, row, row_step_b, wp);
+        c2_chunk_s<1>(acc, win, row + 16, row_step_b, wp + 16);
+        c2_chunk_s<2>(acc, win, row + 32, row_step_b, wp + 32);
+      }
+      if (nch >= 1) c2_chunk_s<0>(acc, win, row, row_step_b, wp);
+      if (nch >= 2) c2_chunk_s<1>(acc, win, row + 16, row_step_b, wp + 16);
     }
-    row += 8;
-    int nch = sg.nch;
-    for (; nch >= 3; nch -= 3, row += 12, wp += 3) {  // the window rotation has period 3
-      c2_chunk<0>(acc, win, row, row_step, wp);
-      c2_chunk<1>(acc, win, row + 4, row_step, wp + 1);
-      c2_chunk<2>(acc, win, row + 8, row_step, wp + 2);
+  } else {
+    const float* base = smem + boff;
+    const int2* const seg2 = reinterpret_cast<const int2*>(segs);
+    int2 nxt = seg2[0];
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+      const int2 sg = nxt;
+      if (sgi + 1 < nseg) nxt = seg2[sgi + 1];  // in flight while this segment computes
+      const int sg_dy = (int)(short)(sg.x & 0xffff), sg_dx0 = sg.x >> 16;
+      const float* row = base + sg_dy * pitch + sg_dx0;
+      const float4* wp = w4 + ((unsigned)sg.y >> 16);
+      float win[kC2Rows][12];
+#pragma unroll
+      for (int h = 0; h < kC2Rows; ++h) {
+        const float4 a0 = *reinterpret_cast<const float4*>(row + h * row_step);
+        const float4 a1 = *reinterpret_cast<const float4*>(row + h * row_step + 4);
+        win[h][0] = a0.x; win[h][1] = a0.y; win[h][2] = a0.z; win[h][3] = a0.w;
+        win[h][4] = a1.x; win[h][5] = a1.y; win[h][6] = a1.z; win[h][7] = a1.w;
+      }
+      row += 8;
+      int nch = (int)(short)(sg.y & 0xffff);
+      for (; nch >= 3; nch -= 3, row += 12, wp += 3) {  // the window rotation has period 3
+        c2_chunk<0>(acc, win, row, row_step, wp);
+        c2_chunk<1>(acc, win, row + 4, row_step, wp + 1);
+        c2_chunk<2>(acc, win, row + 8, row_step, wp + 2);
+      }
+      if (nch >= 1) c2_chunk<0>(acc, win, row, row_step, wp);
+      if (nch >= 2) c2_chunk<1>(acc, win, row + 4, row_step, wp + 1);
     }
-    if (nch >= 1) c2_chunk<0>(acc, win, row, row_step, wp);
-    if (nch >= 2) c2_chunk<1>(acc, win, row + 4, row_step, wp + 1);
   }
 
   float e2 = 0.f;
@@ -1859,12 +1939,18 @@ static int run_conv2d(const psx_op* op, const float* in, const float* eps, const
   if (nw4) smem += tab;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(conv2d_rowseg<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2d_rowseg<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2d_rowseg<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  conv2d_rowseg<MODE><<<grid, kC2Threads, smem, st>>>(in, eps, y, out, err_part, psf.d_segs, psf.d_w4, psf.nseg, nw4,
-                                                       psf.dy_lo, psf.dy_hi, psf.dx_lo, psf.dx_hi, pitch, op->C, op->H,
-                                                       op->W, obs_repeat, sa, s1, wgt, dsc);
+  if (nw4)
+    conv2d_rowseg<MODE, true><<<grid, kC2Threads, smem, st>>>(in, eps, y, out, err_part, psf.d_segs, psf.d_w4, psf.nseg,
+                                                               nw4, psf.dy_lo, psf.dy_hi, psf.dx_lo, psf.dx_hi, pitch,
+                                                               op->C, op->H, op->W, obs_repeat, sa, s1, wgt, dsc);
+  else
+    conv2d_rowseg<MODE, false><<<grid, kC2Threads, smem, st>>>(in, eps, y, out, err_part, psf.d_segs, psf.d_w4, psf.nseg,
+                                                                nw4, psf.dy_lo, psf.dy_hi, psf.dx_lo, psf.dx_hi, pitch,
+                                                                op->C, op->H, op->W, obs_repeat, sa, s1, wgt, dsc);
   return check_cuda(cudaGetLastError(), "conv2d_rowseg launch");
 }
 
