@@ -1513,7 +1513,7 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
 
 // ------------------------------------------------------------------------------------------ sparse 2-D
 enum C2Mode { C2_PLAIN = 0, C2_RESIDUAL = 1, C2_COT = 2 };
-constexpr int kC2TH = 32;        // output tile: 32 rows x 64 columns, 128 threads
+constexpr int kC2TH = 64;        // output tile: 64 rows x 64 columns, 256 threads (32 / 48 / 128 rows measured: 141 / 158 / 136 us against 136 us at L = 16, 473 / 503 / 440 against 426 us at L = 64)
 constexpr int kC2TW = 64;
 constexpr int kC2Rows = 2;       // rows per thread: rp, rp + 16 (4 rows per thread measured slower: 194 vs 153 us)
 constexpr int kC2Threads = (kC2TH / kC2Rows) * (kC2TW / 8);
@@ -1633,8 +1633,11 @@ conv2d_rowseg(const float* __restrict__ in, const float* __restrict__ eps, const
   __syncthreads();
 
   const int q = threadIdx.x;
-  const int cg = (q & 3) | (((q >> 3) & 1) << 2);
-  const int rp = ((q >> 2) & 1) | ((q >> 4) << 1);  // 0 .. kC2TH / kC2Rows - 1
+  // q bits 0-1 and 3.. (kCgBits - 2 of them): column group; bit 2 and the rest: row pair
+  constexpr int kCgBits = kC2TW == 64 ? 3 : kC2TW == 128 ? 4 : kC2TW == 256 ? 5 : -1;
+  static_assert(kCgBits > 0, "tile width 64, 128 or 256");
+  const int cg = (q & 3) | (((q >> 3) & ((1 << (kCgBits - 2)) - 1)) << 2);
+  const int rp = ((q >> 2) & 1) | ((q >> (kCgBits + 1)) << 1);  // 0 .. kC2TH / kC2Rows - 1
   constexpr int kStepRows = kC2TH / kC2Rows;
   const int row_step = kStepRows * pitch;
   float acc[kC2Rows][8];
@@ -1853,7 +1856,7 @@ conv2d_colseg(const float* __restrict__ in, const float* __restrict__ eps, const
   }
   __syncthreads();
 
-  const int cp = threadIdx.x & 31, rg = threadIdx.x >> 5;  // columns 2cp, 2cp + 1; rows 8rg .. 8rg + 7
+  const int cp = threadIdx.x % (kC2TW / 2), rg = threadIdx.x / (kC2TW / 2);  // columns 2cp, 2cp + 1; rows 8rg .. 8rg + 7
   float2 acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
