@@ -96,7 +96,7 @@ void read_env() {
   e.no_pipe = getenv("PSX_NO_PIPE") != nullptr;
   e.no_fast16 = getenv("PSX_NO_FAST16") != nullptr;
   e.no_tc = getenv("PSX_NO_TC") != nullptr;
-  e.tc_one_plane = getenv("PSX_TC_ONE_PLANE") != nullptr;
+  e.tc_persist = getenv("PSX_TC_PERSIST") != nullptr;
   e.fused = getenv("PSX_FUSED") != nullptr;
   const char* sp = getenv("PSX_SPLIT");
   e.split = sp ? atoi(sp) : 0;

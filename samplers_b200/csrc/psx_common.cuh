@@ -259,7 +259,7 @@ int conv2d_err_parts(const psx_op* op);
 // Kernel-selection switches of the environment, read once (psx_reload_env re-reads them).
 struct EnvOpts {
   bool no_pipe, no_fast16, no_tc, fused;
-  bool tc_one_plane;  // PSX_TC_ONE_PLANE: blur_k1_tc with one cluster pair per plane (no persistent loop)
+  bool tc_persist;    // PSX_TC_PERSIST: blur_k1_tc as one wave of persistent cluster pairs when the planes exceed it
   int split;  // PSX_SPLIT: forced number of K1 sample groups, 0 = automatic
 };
 const EnvOpts& env_opts();

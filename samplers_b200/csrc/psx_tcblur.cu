@@ -212,6 +212,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   PSX_TCTICK(1, 0)
   PSX_TCCLOCK(30)
 
+  float4 xe0, xe1, ee0, ee1;  // LOOP = false: chunk 0 of the plane, requested before the set-up
   if (warp == kTcWarps) {
     if (lane == 0) {
       mbar_init(bars + kBImg, 1);
@@ -239,11 +240,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   } else if (warp < kTcWarps) {
     reinterpret_cast<uint4*>(zsm)[tid] = make_uint4(0, 0, 0, 0);  // 512 x 16 B
     fence_async_smem();
+    // Chunk 0 of the (first) plane is requested HERE: its latency then runs under the set-up of the other warps (TMEM
+    // allocation, barrier initialisation, Toeplitz block).  For that, nothing the loader warps execute between here and
+    // the chunk loop may wait for a load in flight: the proxy fence is above, they skip the tcgen05 fences around the
+    // block barrier (their first tcgen05 operation, the TMEM read of E1, follows an mbarrier wait and its own
+    // fence::after_thread_sync), and they arrive RELAXED on the cluster barrier (the release belongs to the warps that
+    // initialised the mbarriers).  Measured: set-up 0.92 -> 0.53 us, all chunks in 9.15 -> 7.7 us, CTA 19.7 -> 17.9 us.
+    // (One chunk only, and only without the plane loop: more early registers spill across the role branches.)
+    if (!LOOP) {
+      const int r_ = lane & 7, cg_ = 4 * (warp & 3) + (lane >> 3), kb_ = warp >> 2;
+      const int64_t off_ = plane0 * (int64_t)(kTcN * kTcN) + (int64_t)(8 * kb_ + r_) * kTcN + j0 + 8 * cg_;
+      ld_nc8_v(x + off_, xe0, xe1);
+      ld_nc8_v(eps + off_, ee0, ee1);
+    }
   }
-  tc_fence_before();
+  if (warp >= kTcWarps) tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  cluster_arrive_release();  // #0: this CTA's barriers are initialised
+  if (warp >= kTcWarps) {
+    tc_fence_after();
+    cluster_arrive_release();  // #0: this CTA's barriers are initialised
+  } else {
+    cluster_arrive_relaxed();
+  }
   const uint32_t tb = *tslot;
   PSX_TCTICK(0, 1)
   PSX_TCTICK(1, 1)
@@ -440,8 +458,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     constexpr int kAhead = LOOP ? kTcAhead : 4;
     float4 xa[4], xb[4], ea[4], eb[4];
     // the first chunks of the first plane (those of every further plane are requested ahead of E4 of the plane before)
+    if (!LOOP) {
+      xa[0] = xe0; xb[0] = xe1; ea[0] = ee0; eb[0] = ee1;
+    }
 #pragma unroll
-    for (int u = 0; u < kAhead; ++u) {
+    for (int u = LOOP ? 0 : 1; u < kAhead; ++u) {
       ld_nc8_v(x + plane0 * (int64_t)(kTcN * kTcN) + ld_off + u * 32 * kTcN, xa[u], xb[u]);
       ld_nc8_v(eps + plane0 * (int64_t)(kTcN * kTcN) + ld_off + u * 32 * kTcN, ea[u], eb[u]);
     }
@@ -791,10 +812,11 @@ int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, co
   const int64_t planes = L * op->C;
   PSX_REQUIRE(planes <= INT32_MAX / 2, "blur_k1_tc: too many planes");
   const float coef = (float)((double)w / (double)sa);
-  // up to one resident wave of cluster pairs (74 on a 148-SM part): a pair per plane; beyond: one resident wave of
-  // persistent pairs, each looping over its planes (PSX_TC_ONE_PLANE=1 keeps a pair per plane: several waves)
+  // A cluster pair per plane, in as many waves as it takes.  PSX_TC_PERSIST=1 selects, beyond one resident wave (74
+  // pairs on a 148-SM part), ONE wave of persistent pairs that loop over their planes: it was 3 % faster at L = 64
+  // until chunk 0 moved ahead of the set-up, which the loop kernel cannot afford in registers (62.9 against 65.1 us).
   const int64_t resident = tc_resident_clusters();
-  if (planes <= resident || env_opts().tc_one_plane)
+  if (planes <= resident || !env_opts().tc_persist)
     blur_k1_tc<false><<<(unsigned)(planes * 2), kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
                                                                             op->tc_inv_scale, op->C, obs_repeat,
                                                                             op->err_parts / op->C, sa, s1, coef, dsc,

@@ -184,16 +184,16 @@ def test_posterior_moments_of_many_samples_match_torch():
 
 
 @pytest.mark.parametrize("L,obs_repeat", [(64, 64), (64, 1), (30, 1), (50, 5)])
-@pytest.mark.parametrize("path", ["tc", "tc_one_plane", "cuda_core_1", "cuda_core_2"])
+@pytest.mark.parametrize("path", ["tc", "tc_persist", "cuda_core_1", "cuda_core_2"])
 def test_blur_k1_large_batches_every_path(L, obs_repeat, path, monkeypatch):
-    """K1 of config 2's blur at batches with MORE planes than resident CTA groups -- the persistent loop of the
-    tensor-core kernel (74 cluster pairs; 90 / 150 / 192 planes) and the persistent strip kernels of the CUDA-core
+    """K1 of config 2's blur at batches with MORE planes than resident CTA groups -- the tensor-core kernel in several
+    waves and as one wave of persistent cluster pairs (74 pairs; 90 / 150 / 192 planes) and the persistent strip kernels of the CUDA-core
     path (whose in-place interleaved h2 once raced with unfetched strips from L = 32 on) -- against the oracle's
     operator evaluated in fp64 on the device, per sample, twice (repeatability)."""
     from samplers_b200 import _native, operators as pops
-    env = {"tc": {}, "tc_one_plane": {"PSX_TC_ONE_PLANE": "1"}, "cuda_core_1": {"PSX_NO_TC": "1", "PSX_SPLIT": "1"},
+    env = {"tc": {}, "tc_persist": {"PSX_TC_PERSIST": "1"}, "cuda_core_1": {"PSX_NO_TC": "1", "PSX_SPLIT": "1"},
            "cuda_core_2": {"PSX_NO_TC": "1", "PSX_SPLIT": "2"}}[path]
-    for k in ("PSX_TC_ONE_PLANE", "PSX_NO_TC", "PSX_SPLIT"):
+    for k in ("PSX_TC_PERSIST", "PSX_NO_TC", "PSX_SPLIT"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)

@@ -102,13 +102,13 @@ def main():
              for _ in range(nsets)]
         y = torch.randn(1, nat.n_y, device=dev)
         res = {"L": L, "nsets": nsets}
-        for name, env in (("cuda_core", "1"), ("tc", None), ("tc_one_plane", "one"), ("tc", None)):
+        for name, env in (("cuda_core", "1"), ("tc", None), ("tc_persist", "one"), ("tc", None)):
             os.environ.pop("PSX_NO_TC", None)
-            os.environ.pop("PSX_TC_ONE_PLANE", None)
+            os.environ.pop("PSX_TC_PERSIST", None)
             if env == "1":
                 os.environ["PSX_NO_TC"] = env
             elif env == "one":
-                os.environ["PSX_TC_ONE_PLANE"] = "1"
+                os.environ["PSX_TC_PERSIST"] = "1"
             _native.reload_env()
 
             def k1(i):
