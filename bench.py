@@ -190,6 +190,19 @@ def run_own(args):
 
     dps_mod._native.dps_pre_dev = timed_dev("k1", real_pre_dev)
     dps_mod._native.dps_post_dev = timed_dev("k2", real_post_dev)
+    # the tensor-core blur runs the pair with the bridge mean written by K1 (psx_dps_pre_mean / psx_dps_post_mean):
+    # one wrapper for both launch modes
+    real_pre_mean, real_post_mean = _native.dps_pre_mean, _native.dps_post_mean
+
+    def timed_any(name, fn):
+        graph_wrap, eager_wrap = timed_dev(name, fn), timed(name, fn)
+
+        def wrap(*a, **k):
+            return (graph_wrap if torch.cuda.is_current_stream_capturing() else eager_wrap)(*a, **k)
+        return wrap
+
+    dps_mod._native.dps_pre_mean = timed_any("k1", real_pre_mean)
+    dps_mod._native.dps_post_mean = timed_any("k2", real_post_mean)
 
     try:
         if use_graph:
@@ -280,6 +293,7 @@ def run_own(args):
         sampler.release()
         dps_mod._native.dps_pre, dps_mod._native.dps_post = real_pre, real_post
         dps_mod._native.dps_pre_dev, dps_mod._native.dps_post_dev = real_pre_dev, real_post_dev
+        dps_mod._native.dps_pre_mean, dps_mod._native.dps_post_mean = real_pre_mean, real_post_mean
 
     t = torch.tensor([ms, ms_e2e, k1_ms, k2_ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -418,8 +432,30 @@ def roofline_by_config(device, peak: float) -> list:
         for i in range(nsets):
             k1(i); k2(i)
         m1, m2 = _rotate_time(k1, nsets, 10), _rotate_time(k2, nsets, 10)
+        classic = {}
+        if nat.fuses_mean(L):
+            # the pair the sampler runs for this operator at this batch: CTAs on the SMs K1 leaves idle write the bridge
+            # mean, K2 reads it instead of x_t and eps (bit-identical results)
+            classic = {"k1_us_classic_pair": m1 * 1e3, "k2_us_classic_pair": m2 * 1e3, "pair": "K1 + bridge mean / K2 "
+                       "on the mean (psx_dps_pre_mean / psx_dps_post_mean); *_classic_pair = psx_dps_pre / psx_dps_post"}
+            for d in S:
+                d["mean"] = torch.empty(L, n, device=device)
+
+            def k1m(i):
+                d = S[i]
+                _native.dps_pre_mean(nat, d["x"], d["eps"], y, L, 0.8, 0.6, 400.0, 0.99, 0.01, d["cot"], d["part"],
+                                     d["mean"], d["ws"])
+
+            def k2m(i):
+                d = S[i]
+                _native.dps_post_mean(d["mean"], d["cot"], d["v"], d["z"], d["part"], nat.err_parts, n, 0.6, 0.05,
+                                      1.0, d["out"], None)
+
+            for i in range(nsets):
+                k1m(i); k2m(i)
+            m1, m2 = _rotate_time(k1m, nsets, 10), _rotate_time(k2m, nsets, 10)
         b1, b2 = 16 * L * n, 24 * L * n
-        out.append({"operator": kind, "L": L, "k1_us": m1 * 1e3, "k2_us": m2 * 1e3,
+        out.append({"operator": kind, "L": L, "k1_us": m1 * 1e3, "k2_us": m2 * 1e3, **classic,
                     "k1_frac": b1 / m1 / 1e6 / peak, "k2_frac": b2 / m2 / 1e6 / peak,
                     "fused_gbs": (b1 + b2) / (m1 + m2) / 1e6, "fused_frac": (b1 + b2) / (m1 + m2) / 1e6 / peak,
                     "timing": f"ring of {nsets} cold buffer sets, the ring pass replayed as one CUDA graph; the L "

@@ -41,7 +41,7 @@ extern "C" {
 #define PSX_ERR_UNSUPPORTED 3 /* valid request this build has no kernel for  */
 
 #define PSX_MAX_TAPS 127  /* longest 1-D tap vector of a separable blur       */
-#define PSX_ABI_VERSION 4
+#define PSX_ABI_VERSION 5
 
 /* Operator kinds (psx_op_kind). */
 #define PSX_OP_IDENTITY 0
@@ -204,6 +204,34 @@ PSX_API int psx_dps_pre_dev(const psx_op* op, const float* d_x_t, const float* d
 PSX_API int psx_dps_post_dev(const float* d_x_t, const float* d_eps, const float* d_cot, const float* d_vjp,
                              const float* d_z, const float* d_err_part, int err_parts, int64_t L, int64_t n,
                              const float* d_step_row, float* d_x_next, float* d_err_out, void* stream);
+
+/* ------------------------------------------------------------------ K1 that also emits the bridge mean
+ * The bridge mean  mean = c_ell * x_t + c_s * x0  (samplers/samplers/utils/bridge_kernels.py:41) depends on x_t and
+ * eps only.  Where K1 is not HBM-bound AND leaves SMs idle -- the tensor-core blur at small batches (config 2: 96 of
+ * 148 SMs hold planes): psx_op_fuses_mean(op, L) == 1 -- the same launch carries extra CTAs on the idle SMs that
+ * write the mean under K1's span, and K2 then reads ONE array instead of x_t and eps: 4 B per element leave the
+ * HBM-bound kernel (K2 24 -> 20 B per element).
+ *   psx_dps_pre_mean[_dev]   = psx_dps_pre[_dev] + d_mean_out (L, n); c_ell / c_s by value or from row entries 3-4
+ *   psx_dps_post_mean[_dev]  = psx_dps_post[_dev] with d_mean in place of (d_x_t, d_eps); d_x_next is usually the
+ *                              state x_t itself (in-place step)
+ * The roundings are those of psx_dps_post (Tweedie, mul, mul, add; then + std*z; then + scale*grad), so the pair is
+ * bit-identical to psx_dps_pre + psx_dps_post.  Other operators / larger batches: PSX_ERR_UNSUPPORTED (their K1 is
+ * HBM-bound or fills the GPU; moving the 4 bytes would gain nothing). */
+PSX_API int psx_op_fuses_mean(const psx_op* op, int64_t L);
+PSX_API int psx_dps_pre_mean(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y, int64_t L,
+                             int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight, float c_ell,
+                             float c_s, float* d_cot, float* d_err_part, float* d_mean_out, void* d_workspace,
+                             size_t workspace_bytes, void* stream);
+PSX_API int psx_dps_pre_mean_dev(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y,
+                                 int64_t L, int64_t obs_repeat, const float* d_step_row, float* d_cot,
+                                 float* d_err_part, float* d_mean_out, void* d_workspace, size_t workspace_bytes,
+                                 void* stream);
+PSX_API int psx_dps_post_mean(const float* d_mean, const float* d_cot, const float* d_vjp, const float* d_z,
+                              const float* d_err_part, int err_parts, int64_t L, int64_t n, float sqrt_1m_acp,
+                              float std, float gamma, float* d_x_next, float* d_err_out, void* stream);
+PSX_API int psx_dps_post_mean_dev(const float* d_mean, const float* d_cot, const float* d_vjp, const float* d_z,
+                                  const float* d_err_part, int err_parts, int64_t L, int64_t n,
+                                  const float* d_step_row, float* d_x_next, float* d_err_out, void* stream);
 
 /* ------------------------------------------------------------------ K2 with in-kernel noise (production mode)
  * Same update as psx_dps_post, but the N(0,1) field is drawn inside the kernel instead of being read: no noise

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libpsx.so")
 
 PSX_OK, PSX_ERR_INVALID, PSX_ERR_CUDA, PSX_ERR_UNSUPPORTED = 0, 1, 2, 3
 OP_IDENTITY, OP_MASK, OP_BOX, OP_SEPBLUR, OP_CONV2D = range(5)
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # name -> (restype, argtypes); must list every prototype of include/psx.h
 _f32p, _i64, _vp, _f = C.c_void_p, C.c_int64, C.c_void_p, C.c_float
@@ -55,6 +55,15 @@ PROTOTYPES = {
                                   C.c_size_t, _vp]),
     "psx_dps_post_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _f32p,
                                    _f32p, _vp]),
+    "psx_op_fuses_mean": (C.c_int, [_opp, _i64]),
+    "psx_dps_pre_mean": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f, _f, _f, _f, _f, _f32p, _f32p, _f32p,
+                                   _vp, C.c_size_t, _vp]),
+    "psx_dps_pre_mean_dev": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _vp,
+                                       C.c_size_t, _vp]),
+    "psx_dps_post_mean": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f, _f, _f, _f32p,
+                                    _f32p, _vp]),
+    "psx_dps_post_mean_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _f32p,
+                                        _f32p, _vp]),
     "psx_dps_post_philox": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f, _f, _f, _f, _f, _f,
                                       C.c_uint64, C.c_uint64, _f32p, _f32p, _vp]),
     "psx_dps_post_philox_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _vp, _f32p,
@@ -161,6 +170,11 @@ class NativeOp:
         self.n = lib.psx_op_x_numel(self.handle)
         self.n_y = lib.psx_op_y_numel(self.handle)
         self.err_parts = lib.psx_op_err_parts(self.handle)
+
+    def fuses_mean(self, L: int) -> bool:
+        """True when this operator's K1 can also write the bridge mean for L samples (psx_dps_pre_mean): the
+        tensor-core blur at batches that leave SMs idle."""
+        return bool(load().psx_op_fuses_mean(self.handle, L))
 
     def workspace_bytes(self, L: int) -> int:
         return load().psx_op_workspace_bytes(self.handle, L)
@@ -297,6 +311,43 @@ def dps_post_dev(x_t, eps, cot, vjp, z, err_part, err_parts: int, n: int, step_r
                                       ptr(err_part), err_parts if err_part is not None else 0, L, n,
                                       step_row.data_ptr(), x_next.data_ptr(), ptr(err_out),
                                       stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def dps_pre_mean(op: NativeOp, x_t, eps, y, obs_repeat: int, sa: float, s1: float, weight: float, c_ell: float,
+                 c_s: float, cot, err_part, mean, ws, step_row=None) -> None:
+    """psx_dps_pre that also writes the bridge mean c_ell x_t + c_s x0 (``op.fuses_mean`` operators only); with
+    ``step_row`` the scalars come from the device row (psx_dps_pre_mean_dev)."""
+    global launch_count
+    L = x_t.shape[0]
+    wsb = 0 if ws is None else ws.numel() * 4
+    with torch.cuda.device(x_t.device):
+        if step_row is None:
+            check(load().psx_dps_pre_mean(op.handle, x_t.data_ptr(), eps.data_ptr(), y.data_ptr(), L, obs_repeat, sa,
+                                          s1, weight, c_ell, c_s, cot.data_ptr(), err_part.data_ptr(),
+                                          mean.data_ptr(), ptr(ws), wsb, stream_ptr(x_t.device)))
+        else:
+            check(load().psx_dps_pre_mean_dev(op.handle, x_t.data_ptr(), eps.data_ptr(), y.data_ptr(), L, obs_repeat,
+                                              step_row.data_ptr(), cot.data_ptr(), err_part.data_ptr(),
+                                              mean.data_ptr(), ptr(ws), wsb, stream_ptr(x_t.device)))
+    launch_count += 1
+
+
+def dps_post_mean(mean, cot, vjp, z, err_part, err_parts: int, n: int, s1: float, std: float, gamma: float, x_next,
+                  err_out=None, step_row=None) -> None:
+    """psx_dps_post behind psx_dps_pre_mean: reads the bridge mean instead of x_t and eps."""
+    global launch_count
+    L = mean.shape[0]
+    with torch.cuda.device(mean.device):
+        if step_row is None:
+            check(load().psx_dps_post_mean(mean.data_ptr(), cot.data_ptr(), vjp.data_ptr(), ptr(z), ptr(err_part),
+                                           err_parts if err_part is not None else 0, L, n, s1, std, gamma,
+                                           x_next.data_ptr(), ptr(err_out), stream_ptr(mean.device)))
+        else:
+            check(load().psx_dps_post_mean_dev(mean.data_ptr(), cot.data_ptr(), vjp.data_ptr(), z.data_ptr(),
+                                               ptr(err_part), err_parts if err_part is not None else 0, L, n,
+                                               step_row.data_ptr(), x_next.data_ptr(), ptr(err_out),
+                                               stream_ptr(mean.device)))
     launch_count += 1
 
 

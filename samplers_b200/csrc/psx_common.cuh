@@ -239,9 +239,17 @@ int launch_pre_pointwise(const psx_op* op, const float* x, const float* eps, con
 int launch_pre_box(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                    int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                    float* x0_out, cudaStream_t st);
+// mean_out != nullptr: K1 also writes the bridge mean c_ell x_t + c_s x0 (tensor-core blur at small batches, see
+// fuses_mean)
 int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                        int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
-                       float* x0_out, float* ws, cudaStream_t st, bool half = false);
+                       float* x0_out, float* ws, cudaStream_t st, bool half = false, float* mean_out = nullptr,
+                       float c_ell = 0.f, float c_s = 0.f);
+bool fuses_mean(const psx_op* op, int64_t L);
+bool tcblur_mean_fits(const psx_op* op, int64_t L);
+int launch_post_mean(const float* mean, const float* cot, const float* vjp, const float* z, const float* err_part,
+                     int err_parts, int64_t L, int64_t n, float s1, float sd, float gamma, const float* dsc,
+                     float* x_next, float* err_out, cudaStream_t st);
 int launch_pre_conv2d(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                       int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                       float* x0_out, float* ws, cudaStream_t st);
@@ -253,7 +261,7 @@ void tcblur_release(psx_op* op);
 bool tcblur_available(const psx_op* op);
 int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                           int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot,
-                          float* err_part, cudaStream_t st);
+                          float* err_part, float* mean_out, float c_ell, float c_s, cudaStream_t st);
 int conv2d_err_parts(const psx_op* op);
 
 // Kernel-selection switches of the environment, read once (psx_reload_env re-reads them).

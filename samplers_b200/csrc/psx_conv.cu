@@ -1423,15 +1423,27 @@ static int run_fast_tail(const psx_op* op, const float* y, float* ws, float* ws2
   return check_cuda(cudaGetLastError(), "conv_rows_il launch");
 }
 
+// K1 launches that can emit the bridge mean for K2 (psx_dps_pre_mean): the tensor-core blur at batches that leave
+// SMs idle
+bool fuses_mean(const psx_op* op, int64_t L) {
+  return op->kind == PSX_OP_SEPBLUR && tcblur_available(op) && !env_opts().no_tc && tcblur_mean_fits(op, L);
+}
+
 // half: x, eps and cot are bf16 arrays (passed through the float* parameters); the intermediates in ws stay fp32.
 int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                        int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
-                       float* x0_out, float* ws, cudaStream_t st, bool half) {
+                       float* x0_out, float* ws, cudaStream_t st, bool half, float* mean_out, float c_ell,
+                       float c_s) {
   if (x0_out) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: d_x0_out is not produced for blur operators");
   const int64_t planes = L * op->C;
   // tensor-core single launch (psx_tcblur.cu): 256 x 256 planes, symmetric taps shared by rows and columns
+  if (mean_out && (half || !fuses_mean(op, L)))
+    return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre_mean: this operator's K1 does not emit the bridge mean at this "
+                                     "batch size (psx_op_fuses_mean)");
   if (!half && tcblur_available(op) && !env_opts().no_tc)
-    return launch_pre_sepblur_tc(op, x, eps, y, L, obs_repeat, sa, s1, w, dsc, cot, err_part, st);
+    return launch_pre_sepblur_tc(op, x, eps, y, L, obs_repeat, sa, s1, w, dsc, cot, err_part, mean_out, c_ell, c_s,
+                                 st);
+
   // cluster-fused single launch for 256 x 256 planes
   if (op->H == kFusedCL * kFusedRB && op->W == kFusedW && op->fh.k == 40 && op->fv.k == 40 && op->ah.k == 40 &&
       op->av.k == 40 && op->fh.lo == op->ah.lo && op->fv.lo == op->av.lo && -op->fv.lo <= kFusedRB &&

@@ -492,6 +492,84 @@ int launch_post(const float* x, const float* eps, const float* cot, const float*
   return check_cuda(cudaGetLastError(), "k2_post launch");
 }
 
+// K2 behind a K1 that has already written the bridge mean (psx_dps_pre_mean: the tensor-core blur):
+//     x_next = (mean + std*z) + scale * (cot - s1*vjp)
+// -- the arithmetic and roundings of k2_post_v4 from `m` on, so the pair (K1 with mean, this) is bit-identical to
+// (K1, k2_post_v4).  20 instead of 24 B per element through the HBM-bound kernel.  ZMODE: 0 = no noise term, 1 = z read.
+template <int ZMODE>
+__global__ void __launch_bounds__(kThreads)
+k2_post_mean(const float* __restrict__ mean, const float* __restrict__ cot, const float* __restrict__ vjp,
+             const float* __restrict__ z, const float* __restrict__ err_part, int err_parts, int64_t n,
+             int64_t chunk4, float s1, float sd, float gamma, float* __restrict__ x_next,
+             float* __restrict__ err_out, const float* __restrict__ dsc) {
+  if (dsc != nullptr) {
+    s1 = __ldg(dsc + 1);
+    sd = __ldg(dsc + 5);
+    gamma = __ldg(dsc + 6);
+  }
+  __shared__ float red[32];
+  const int64_t l = blockIdx.y;
+  float scale = gamma;
+  if (err_parts > 0) {
+    const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
+    const float err = sqrtf(e2);
+    scale = __fdiv_rn(gamma, __fadd_rn(err, 1e-9f));
+    if (err_out && blockIdx.x == 0 && threadIdx.x == 0) err_out[l] = err;
+  }
+  const int64_t n4 = n >> 2;
+  const int64_t beg = (int64_t)blockIdx.x * chunk4, end = min(beg + chunk4, n4);
+  const int64_t so = l * n;
+  constexpr int U = 2;
+  for (int64_t base = beg + threadIdx.x; base < end; base += (int64_t)kThreads * U) {
+    float4 mv[U], dv[U], vv[U], zv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * kThreads;
+      if (i < end) {
+        mv[u] = ld_stream4(mean + so + 4 * i);
+        dv[u] = ld_stream4(cot + so + 4 * i);
+        vv[u] = ld_stream4(vjp + so + 4 * i);
+        if (ZMODE == 1) zv[u] = ld_stream4(z + so + 4 * i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * kThreads;
+      if (i < end) {
+        float4 o;
+#define PSX_K2M_LANE(c)                                                        \
+  {                                                                            \
+    float m = mv[u].c;                                                         \
+    if (ZMODE != 0) m = __fadd_rn(m, __fmul_rn(sd, zv[u].c));                  \
+    const float g = __fadd_rn(dv[u].c, __fmul_rn(-s1, vv[u].c));               \
+    o.c = __fadd_rn(m, __fmul_rn(scale, g));                                   \
+  }
+        PSX_K2M_LANE(x) PSX_K2M_LANE(y) PSX_K2M_LANE(z) PSX_K2M_LANE(w)
+#undef PSX_K2M_LANE
+        st_stream4(x_next + so + 4 * i, o);
+      }
+    }
+  }
+}
+
+int launch_post_mean(const float* mean, const float* cot, const float* vjp, const float* z, const float* err_part,
+                     int err_parts, int64_t L, int64_t n, float s1, float sd, float gamma, const float* dsc,
+                     float* x_next, float* err_out, cudaStream_t st) {
+  if (n % 4 != 0) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_post_mean: n must be a multiple of 4");
+#define PSX_POSTM(KERNEL)                                                                                   \
+  {                                                                                                         \
+    static int rs = 0;                                                                                      \
+    if (!rs) rs = resident_slots(KERNEL);                                                                   \
+    const int parts = one_wave_parts(rs, L, n / 4, 1 << 20);                                                \
+    const int64_t chunk = (n / 4 + parts - 1) / parts;                                                      \
+    KERNEL<<<dim3(parts, (unsigned)L), kThreads, 0, st>>>(mean, cot, vjp, z, err_part, err_parts, n, chunk, \
+                                                          s1, sd, gamma, x_next, err_out, dsc);             \
+  }
+  if (z != nullptr) PSX_POSTM(k2_post_mean<1>) else PSX_POSTM(k2_post_mean<0>)
+#undef PSX_POSTM
+  return check_cuda(cudaGetLastError(), "k2_post_mean launch");
+}
+
 // =========================================================================== final Tweedie (+ posterior moments)
 // One thread per pixel (quad), looping over the L local samples: x0 goes to the gather slot, the
 // per-pixel sum / sum of squares are the all-reduce send buffers for the posterior mean / variance.

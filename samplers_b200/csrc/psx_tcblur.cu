@@ -188,12 +188,21 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
 
 // LOOP = false: one cluster pair per plane (grid = 2 x planes; all of them resident: up to 74 planes), straight-line
 // code.  LOOP = true: one resident wave of cluster pairs, each looping over its planes.
-template <bool LOOP>
+//
+// MEAN = true (LOOP = false only): the grid carries EXTRA cluster pairs beyond the planes -- the SMs a small batch
+// leaves idle (config 2: 96 of 148 SMs hold planes) -- and those CTAs stream x_t and eps once more (second readers:
+// L2 hits) and write the bridge mean
+//     mean = c_ell x_t + c_s x0            (bridge_kernels.py:41, the roundings of K2: tweedie(), mul, mul, add)
+// so that K2 reads ONE array instead of x_t and eps (psx_dps_post_mean): 4 B per element leave the HBM-bound K2 and
+// are produced under K1's span by SMs that had nothing to do.  (Writing the mean from the loader warps, which hold
+// x_t and eps in registers, was measured first: the stores share the SM <-> L2 path that bounds the load phase --
+// K1 20.4 -> 23.7 us for K2 15.1 -> 12.9 us, a net loss; profiles/r02d_inloader_mean_bench_line.json.)
+template <bool LOOP, bool MEAN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     blur_k1_tc(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
                float* __restrict__ cot, float* __restrict__ err_part, const uint8_t* __restrict__ bimg, float inv_scale,
                int C, int64_t obs_repeat, int pp, float sa, float s1, float coef, const float* __restrict__ dsc,
-               int planes) {
+               int planes, float* __restrict__ mean_out, float c_ell, float c_s) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* op = smem;
   uint8_t* bsm = smem + kOpBytes;
@@ -203,6 +212,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   float* red = reinterpret_cast<float*>(bars + kBCount + 1);  // [kTcWarps]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (MEAN && (int)(blockIdx.x >> 1) >= planes) {
+    // ================================================================ bridge-mean role (extra cluster pairs; no barriers,
+    // no TMEM: both CTAs of such a pair take this branch and leave)
+    if (dsc != nullptr) {
+      sa = __ldg(dsc);
+      s1 = __ldg(dsc + 1);
+      c_ell = __ldg(dsc + 3);
+      c_s = __ldg(dsc + 4);
+    }
+    const TweedieC tw = make_tc(s1, sa);
+    // Tiles of 4096 elements: x_t and eps arrive by bulk copies (the LSU path of one SM streams ~50 GB/s, the copy
+    // engine more than twice that), the 16 compute warps overwrite the x_t stage with the mean, a bulk copy stores it.
+    // full[s]: both arrays of the stage have landed (bytes); done[s]: the 16 warps have written the stage (and fenced
+    // their writes towards the async proxy).  Warp 18's lane 0 is the producer.
+    constexpr int kMT = 4096, kMS = 5;                       // tile elements, stages (5 x 32 KB)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* done = full + kMS;
+    float* stage = reinterpret_cast<float*>(smem + 1024);    // [kMS][x: kMT | eps: kMT]
+    const int64_t tiles = (int64_t)planes * (kTcN * kTcN / kMT);
+    const int64_t E = (int64_t)gridDim.x - 2 * planes, e = (int64_t)blockIdx.x - 2 * planes;
+    const int nt = (int)((tiles - e + E - 1) / E);           // this CTA's tiles: e, e + E, ...
+    if (tid == 0) {
+      for (int i = 0; i < kMS; ++i) {
+        mbar_init(full + i, 1);
+        mbar_init(done + i, kTcWarps);
+      }
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == kTcWarps + 2) {
+      if (lane == 0) {
+        auto request = [&](int k) {
+          const int st_ = k % kMS;
+          const int64_t off = (e + (int64_t)k * E) * kMT;
+          mbar_expect_tx(full + st_, 2 * kMT * 4);
+          bulk_g2s(stage + st_ * 2 * kMT, x + off, kMT * 4, full + st_);
+          bulk_g2s(stage + st_ * 2 * kMT + kMT, eps + off, kMT * 4, full + st_);
+        };
+        for (int k = 0; k < kMS && k < nt; ++k) request(k);
+        for (int k = 0; k < nt; ++k) {
+          const int st_ = k % kMS;
+          mbar_wait(done + st_, (uint32_t)(k / kMS) & 1u);
+          bulk_s2g(mean_out + (e + (int64_t)k * E) * kMT, stage + st_ * 2 * kMT, kMT * 4);
+          bulk_commit();
+          if (k + kMS < nt) {
+            bulk_wait_read_all();  // the store has read the stage: it may be refilled
+            request(k + kMS);
+          }
+        }
+        bulk_wait_all();
+      }
+    } else if (warp < kTcWarps) {
+      for (int k = 0; k < nt; ++k) {
+        const int st_ = k % kMS;
+        float4* xs = reinterpret_cast<float4*>(stage + st_ * 2 * kMT);
+        const float4* es = reinterpret_cast<const float4*>(stage + st_ * 2 * kMT + kMT);
+        mbar_wait(full + st_, (uint32_t)(k / kMS) & 1u);
+#pragma unroll
+        for (int u = 0; u < kMT / 4 / kTcEpi; ++u) {
+          const float4 xv = xs[tid + u * kTcEpi], ev = es[tid + u * kTcEpi];
+          float4 m;
+          m.x = __fadd_rn(__fmul_rn(c_ell, xv.x), __fmul_rn(c_s, tweedie(xv.x, ev.x, tw)));
+          m.y = __fadd_rn(__fmul_rn(c_ell, xv.y), __fmul_rn(c_s, tweedie(xv.y, ev.y, tw)));
+          m.z = __fadd_rn(__fmul_rn(c_ell, xv.z), __fmul_rn(c_s, tweedie(xv.z, ev.z, tw)));
+          m.w = __fadd_rn(__fmul_rn(c_ell, xv.w), __fmul_rn(c_s, tweedie(xv.w, ev.w, tw)));
+          xs[tid + u * kTcEpi] = m;
+        }
+        fence_async_smem();
+        warp_arrive(done + st_, lane);
+      }
+    }
+    return;
+  }
   const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
   // persistent: cluster c works on planes c, c + (clusters in the grid), ...; every mbarrier completes exactly one
   // phase per plane, so the parity every wait uses is the low bit of the plane iteration `it`
@@ -784,7 +866,7 @@ static int tc_resident_clusters() {
     cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = kTcSmem;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, blur_k1_tc<true>, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, blur_k1_tc<true, false>, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       n = sm_count() / 2;
     }
@@ -793,20 +875,27 @@ static int tc_resident_clusters() {
   return cached[dev];
 }
 
+// The bridge-mean role needs idle SMs: the pairs the planes leave free must stream 12 B per element (x_t and eps in,
+// the mean out) within K1's span -- measured ~50 GB/s per SM against ~20 us: at most 2.2 planes per free pair.
+bool tcblur_mean_fits(const psx_op* op, int64_t L) {
+  const int64_t planes = L * op->C, resident = tc_resident_clusters();
+  return planes < resident && 10 * planes <= 22 * (resident - planes);
+}
+
 int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                           int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot,
-                          float* err_part, cudaStream_t st) {
+                          float* err_part, float* mean_out, float c_ell, float c_s, cudaStream_t st) {
   static bool attr[64] = {};  // function attributes are per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!attr[dev]) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(blur_k1_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem),
-                            "blur_k1_tc attribute"))
-      return rc;
-    if (int rc = check_cuda(cudaFuncSetAttribute(blur_k1_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem),
-                            "blur_k1_tc attribute"))
-      return rc;
+    const void* fns[3] = {(const void*)blur_k1_tc<false, false>, (const void*)blur_k1_tc<true, false>,
+                          (const void*)blur_k1_tc<false, true>};
+    for (const void* f : fns)
+      if (int rc = check_cuda(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem),
+                              "blur_k1_tc attribute"))
+        return rc;
     attr[dev] = true;
   }
   const int64_t planes = L * op->C;
@@ -816,16 +905,18 @@ int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, co
   // pairs on a 148-SM part), ONE wave of persistent pairs that loop over their planes: it was 3 % faster at L = 64
   // until chunk 0 moved ahead of the set-up, which the loop kernel cannot afford in registers (62.9 against 65.1 us).
   const int64_t resident = tc_resident_clusters();
-  if (planes <= resident || !env_opts().tc_persist)
-    blur_k1_tc<false><<<(unsigned)(planes * 2), kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
-                                                                            op->tc_inv_scale, op->C, obs_repeat,
-                                                                            op->err_parts / op->C, sa, s1, coef, dsc,
-                                                                            (int)planes);
-  else
-    blur_k1_tc<true><<<(unsigned)(resident * 2), kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img,
-                                                                             op->tc_inv_scale, op->C, obs_repeat,
-                                                                             op->err_parts / op->C, sa, s1, coef, dsc,
-                                                                             (int)planes);
+  const bool loop = planes > resident && env_opts().tc_persist;
+  PSX_REQUIRE(!mean_out || tcblur_mean_fits(op, L), "blur_k1_tc: no idle SMs for the bridge-mean role at this batch");
+  // with the mean: every pair the planes leave free carries the bridge-mean role
+  const unsigned grid = (unsigned)((loop ? resident : (mean_out ? resident : planes)) * 2);
+#define PSX_TC_LAUNCH(LOOP_, MEAN_)                                                                                  \
+  blur_k1_tc<LOOP_, MEAN_><<<grid, kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img, op->tc_inv_scale, \
+                                                              op->C, obs_repeat, op->err_parts / op->C, sa, s1, coef, \
+                                                              dsc, (int)planes, mean_out, c_ell, c_s)
+  if (mean_out) PSX_TC_LAUNCH(false, true);
+  else if (loop) PSX_TC_LAUNCH(true, false);
+  else PSX_TC_LAUNCH(false, false);
+#undef PSX_TC_LAUNCH
   return check_cuda(cudaGetLastError(), "blur_k1_tc launch");
 }
 

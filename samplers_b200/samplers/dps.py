@@ -98,6 +98,11 @@ class DPSRun:
         wsb = self.op.workspace_bytes(self.L)
         self.ws = torch.empty(wsb // 4, device=self.device, dtype=torch.float32) if wsb else None
         self._graph: torch.cuda.CUDAGraph | None = None
+        # K1 of the tensor-core blur, at batches that leave SMs idle (config 2), also writes the bridge mean
+        # c_ell x_t + c_s x0 (into the idle half of the state's double buffer) and K2 reads that one array instead of
+        # x_t and eps: bit-identical, 4 B per element less through the HBM-bound kernel (include/psx.h,
+        # psx_dps_pre_mean).  Philox draws keep the classic pair.
+        self._fused_mean = (not self._bf16) and self.philox_seed is None and self.op.fuses_mean(self.L)
 
     def _network_eps(self, t):
         """(leaf over the state, eps in the network's dtype with its graph, eps as contiguous (L, n) in the state dtype)."""
@@ -139,6 +144,17 @@ class DPSRun:
                                   None if fixed else self.err_part, 0 if fixed else self.op.err_parts, self.n,
                                   1.0, 0.0, 0.0, 0.0, 0.0, 0.0, self.x, None if fixed else self.err, step_row=self.row,
                                   seed_step=self.seed_step if philox else None)
+            self.k_dev.add_(1)
+            return
+        if self._fused_mean:
+            _native.dps_pre_mean(self.op, self.x, eps_flat, self.y, self.obs_repeat, 1.0, 0.0, 1.0, 0.0, 0.0,
+                                 self.cot, self.err_part, self.x_next, self.ws, step_row=self.row)
+            v = self._network_vjp(eps, x_in)
+            if self._draw_in_graph:
+                self.z.normal_()
+            _native.dps_post_mean(self.x_next, self.cot, v, self.z, None if fixed else self.err_part,
+                                  0 if fixed else self.op.err_parts, self.n, 0.0, 0.0, 0.0, self.x,
+                                  None if fixed else self.err, step_row=self.row)
             self.k_dev.add_(1)
             return
         _native.dps_pre_dev(self.op, self.x, eps_flat, self.y, self.obs_repeat, self.row, self.cot, self.err_part,
@@ -233,6 +249,8 @@ class DPSRun:
         x_in, eps, eps_flat = self._network_eps(sc.t)                        # graph kept for the VJP
         if self._bf16:
             return self._step_bf16(k, sc, x_in, eps, eps_flat, z)
+        if self._fused_mean:
+            return self._step_fused_mean(sc, x_in, eps, eps_flat, z)
         _native.dps_pre(self.op, self.x, eps_flat, self.y, self.obs_repeat, sc.sqrt_acp, sc.sqrt_1m_acp,
                         self.weight, self.cot, self.err_part, self.ws)
         v = self._network_vjp(eps, x_in)
@@ -255,6 +273,20 @@ class DPSRun:
             _native.dps_post(self.x, eps_flat, self.cot, v, z, None, 0, self.n, sc.sqrt_acp, sc.sqrt_1m_acp,
                              sc.c_ell, sc.c_s, sc.std, self._fixed_scale(sc), self.x_next, None)
         self.x, self.x_next = self.x_next, self.x
+
+    def _step_fused_mean(self, sc: StepScalars, x_in, eps, eps_flat, z) -> None:
+        """The eager timestep with the bridge mean written by K1 (psx_dps_pre_mean / psx_dps_post_mean), in place."""
+        _native.dps_pre_mean(self.op, self.x, eps_flat, self.y, self.obs_repeat, sc.sqrt_acp, sc.sqrt_1m_acp,
+                             self.weight, sc.c_ell, sc.c_s, self.cot, self.err_part, self.x_next, self.ws)
+        v = self._network_vjp(eps, x_in)
+        if sc.std != 0.0 and z is None:
+            z = self.draw(self.view.flat_shape, self.device, self.dtype)
+        if z is not None:
+            z = z.reshape(self.L, self.n)
+        fixed = self._fixed_scale is not None
+        _native.dps_post_mean(self.x_next, self.cot, v, z, None if fixed else self.err_part,
+                              0 if fixed else self.op.err_parts, self.n, sc.sqrt_1m_acp, sc.std,
+                              self._fixed_scale(sc) if fixed else self.gamma, self.x, None if fixed else self.err)
 
     def _step_bf16(self, k: int, sc: StepScalars, x_in, eps, eps_flat, z) -> None:
         """The eager timestep on the bf16 state (psx_dps_pre_bf16 / psx_dps_post_bf16)."""
