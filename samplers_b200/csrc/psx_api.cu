@@ -97,6 +97,8 @@ void read_env() {
   e.no_fast16 = getenv("PSX_NO_FAST16") != nullptr;
   e.no_tc = getenv("PSX_NO_TC") != nullptr;
   e.tc_persist = getenv("PSX_TC_PERSIST") != nullptr;
+  const char* lag = getenv("PSX_MEAN_LAG_NS");
+  e.mean_lag_ns = lag ? atoi(lag) : 8000;
   e.fused = getenv("PSX_FUSED") != nullptr;
   const char* sp = getenv("PSX_SPLIT");
   e.split = sp ? atoi(sp) : 0;

@@ -268,6 +268,8 @@ int conv2d_err_parts(const psx_op* op);
 struct EnvOpts {
   bool no_pipe, no_fast16, no_tc, fused;
   bool tc_persist;    // PSX_TC_PERSIST: blur_k1_tc as one wave of persistent cluster pairs when the planes exceed it
+  int mean_lag_ns;    // PSX_MEAN_LAG_NS: the bridge-mean CTAs of blur_k1_tc start this long after the kernel (default 8000:
+                      // behind the plane CTAs' load phase, see psx_tcblur.cu)
   int split;  // PSX_SPLIT: forced number of K1 sample groups, 0 = automatic
 };
 const EnvOpts& env_opts();

@@ -202,7 +202,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     blur_k1_tc(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
                float* __restrict__ cot, float* __restrict__ err_part, const uint8_t* __restrict__ bimg, float inv_scale,
                int C, int64_t obs_repeat, int pp, float sa, float s1, float coef, const float* __restrict__ dsc,
-               int planes, float* __restrict__ mean_out, float c_ell, float c_s) {
+               int planes, float* __restrict__ mean_out, float c_ell, float c_s, int mean_lag_ns) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* op = smem;
   uint8_t* bsm = smem + kOpBytes;
@@ -222,10 +222,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       c_s = __ldg(dsc + 4);
     }
     const TweedieC tw = make_tc(s1, sa);
-    // Tiles of 4096 elements: x_t and eps arrive by bulk copies (the LSU path of one SM streams ~50 GB/s, the copy
-    // engine more than twice that), the 16 compute warps overwrite the x_t stage with the mean, a bulk copy stores it.
-    // full[s]: both arrays of the stage have landed (bytes); done[s]: the 16 warps have written the stage (and fenced
-    // their writes towards the async proxy).  Warp 18's lane 0 is the producer.
+    // Tiles of 4096 elements: x_t and eps arrive by bulk copies, the mean leaves through the LSU -- the load / store
+    // path of one SM streams ~50 GB/s, the copy engine more than twice that, so the 12 B per element are split 8 / 4
+    // between them.  (Measured: everything through the LSU, or the mean stored by bulk copies whose smem reads the
+    // producer has to await: 14 us per 725 KB either way.)  full[s]: both arrays of the stage have landed (bytes);
+    // done[s]: the 16 warps hold the stage's values in registers.  Warp 18's lane 0 is the producer.
     constexpr int kMT = 4096, kMS = 5;                       // tile elements, stages (5 x 32 KB)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* done = full + kMS;
@@ -243,44 +244,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     __syncthreads();
     if (warp == kTcWarps + 2) {
       if (lane == 0) {
+        // Tile order: 16-row band t of every plane before band t + 1 of any -- the order in which the plane CTAs
+        // stream their chunks in, so that the two readers of a line ask for it at about the same time (one DRAM
+        // fetch) instead of competing for different lines.
+        auto tile_off = [&](int k) -> int64_t {
+          const int g = (int)e + k * (int)E;  // < 16 x 74 tiles
+          return (int64_t)((g % planes) * (kTcN * kTcN / kMT) + g / planes) * kMT;
+        };
         auto request = [&](int k) {
           const int st_ = k % kMS;
-          const int64_t off = (e + (int64_t)k * E) * kMT;
+          const int64_t off = tile_off(k);
           mbar_expect_tx(full + st_, 2 * kMT * 4);
           bulk_g2s(stage + st_ * 2 * kMT, x + off, kMT * 4, full + st_);
           bulk_g2s(stage + st_ * 2 * kMT + kMT, eps + off, kMT * 4, full + st_);
         };
-        for (int k = 0; k < kMS && k < nt; ++k) request(k);
-        for (int k = 0; k < nt; ++k) {
-          const int st_ = k % kMS;
-          mbar_wait(done + st_, (uint32_t)(k / kMS) & 1u);
-          bulk_s2g(mean_out + (e + (int64_t)k * E) * kMT, stage + st_ * 2 * kMT, kMT * 4);
-          bulk_commit();
-          if (k + kMS < nt) {
-            bulk_wait_read_all();  // the store has read the stage: it may be refilled
-            request(k + kMS);
-          }
+        // Start BEHIND the plane CTAs' load phase (~8 us): that phase is bound by the SM <-> L2 path and gives way to
+        // any other traffic (K1 +1.0 us when both start together), the ~10 us of UMMA chain after it leave the memory
+        // system idle, and by then x_t / eps are L2 hits.  Measured at L = 16 (profiles/r02i_mean_ab.txt): lag 0 ->
+        // K1 21.6 us, 6-10 us -> 20.9-21.1 us (classic 20.7), from 11 us on the mean CTAs (10.5 us) end after the planes.
+        if (mean_lag_ns > 0) {
+          uint64_t t0, t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+          do {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          } while (t1 - t0 < (uint64_t)mean_lag_ns);
         }
-        bulk_wait_all();
+        for (int k = 0; k < kMS && k < nt; ++k) request(k);
+        for (int k = 0; k + kMS < nt; ++k) {
+          mbar_wait(done + k % kMS, (uint32_t)(k / kMS) & 1u);  // the 16 warps have read the stage out
+          request(k + kMS);
+        }
       }
     } else if (warp < kTcWarps) {
       for (int k = 0; k < nt; ++k) {
         const int st_ = k % kMS;
-        float4* xs = reinterpret_cast<float4*>(stage + st_ * 2 * kMT);
-        const float4* es = reinterpret_cast<const float4*>(stage + st_ * 2 * kMT + kMT);
+        const float4* xs = reinterpret_cast<const float4*>(stage + st_ * 2 * kMT);
+        const float4* es = xs + kMT / 4;
+        const int g = (int)e + k * (int)E;
+        float* mp = mean_out + (int64_t)((g % planes) * (kTcN * kTcN / kMT) + g / planes) * kMT;
         mbar_wait(full + st_, (uint32_t)(k / kMS) & 1u);
+        float4 xv[kMT / 4 / kTcEpi], ev[kMT / 4 / kTcEpi];
 #pragma unroll
         for (int u = 0; u < kMT / 4 / kTcEpi; ++u) {
-          const float4 xv = xs[tid + u * kTcEpi], ev = es[tid + u * kTcEpi];
-          float4 m;
-          m.x = __fadd_rn(__fmul_rn(c_ell, xv.x), __fmul_rn(c_s, tweedie(xv.x, ev.x, tw)));
-          m.y = __fadd_rn(__fmul_rn(c_ell, xv.y), __fmul_rn(c_s, tweedie(xv.y, ev.y, tw)));
-          m.z = __fadd_rn(__fmul_rn(c_ell, xv.z), __fmul_rn(c_s, tweedie(xv.z, ev.z, tw)));
-          m.w = __fadd_rn(__fmul_rn(c_ell, xv.w), __fmul_rn(c_s, tweedie(xv.w, ev.w, tw)));
-          xs[tid + u * kTcEpi] = m;
+          xv[u] = xs[tid + u * kTcEpi];
+          ev[u] = es[tid + u * kTcEpi];
         }
-        fence_async_smem();
-        warp_arrive(done + st_, lane);
+        warp_arrive(done + st_, lane);  // the values are in registers: the stage may be refilled
+#pragma unroll
+        for (int u = 0; u < kMT / 4 / kTcEpi; ++u) {
+          float4 m;
+          m.x = __fadd_rn(__fmul_rn(c_ell, xv[u].x), __fmul_rn(c_s, tweedie(xv[u].x, ev[u].x, tw)));
+          m.y = __fadd_rn(__fmul_rn(c_ell, xv[u].y), __fmul_rn(c_s, tweedie(xv[u].y, ev[u].y, tw)));
+          m.z = __fadd_rn(__fmul_rn(c_ell, xv[u].z), __fmul_rn(c_s, tweedie(xv[u].z, ev[u].z, tw)));
+          m.w = __fadd_rn(__fmul_rn(c_ell, xv[u].w), __fmul_rn(c_s, tweedie(xv[u].w, ev[u].w, tw)));
+          st_stream4(mp + 4 * (tid + u * kTcEpi), m);
+        }
       }
     }
     return;
@@ -912,7 +930,7 @@ int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, co
 #define PSX_TC_LAUNCH(LOOP_, MEAN_)                                                                                  \
   blur_k1_tc<LOOP_, MEAN_><<<grid, kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img, op->tc_inv_scale, \
                                                               op->C, obs_repeat, op->err_parts / op->C, sa, s1, coef, \
-                                                              dsc, (int)planes, mean_out, c_ell, c_s)
+                                                              dsc, (int)planes, mean_out, c_ell, c_s, env_opts().mean_lag_ns)
   if (mean_out) PSX_TC_LAUNCH(false, true);
   else if (loop) PSX_TC_LAUNCH(true, false);
   else PSX_TC_LAUNCH(false, false);
