@@ -35,7 +35,7 @@ BATCH_PER_GPU = 16
 SAMPLING_STEPS = 1000
 GUIDED_STEPS = SAMPLING_STEPS - 2        # range(len(ts)-1, 1, -1)
 SIGMA_Y = 0.05
-NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_ncu_dram_bytes.json")   # written from the ncu --set full capture
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02k_ncu_dram_bytes.json")   # written from the ncu --set full capture
 METRIC = "dps_posterior_samples_per_s_256"
 WORKLOAD = "cfg2: DPS gaussian-blur 61x61 sigma3, ddpm-celebahq-256 UNet, 1000 steps, batch 16/GPU, 3x256x256"
 
@@ -343,7 +343,13 @@ def run_own(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic if (L, n) == (16, 3 * 256 * 256) else None, "traffic_source": traffic_src,
                      "peak_source": peak_src,
-                     "kernel": "fused DPS step = K1 (blur_k1_tc: tcgen05 / TMEM, one launch) + K2 (k2_post_v4)",
+                     "kernel": ("fused DPS step = K1 (blur_k1_tc<0, 1>: tcgen05 / TMEM, one launch; its spare CTAs on the "
+                                "SMs the planes leave idle write the bridge mean) + K2 (k2_post_mean, on that mean)"
+                                if getattr(run, "_fused_mean", False) else
+                                "fused DPS step = K1 (blur_k1_tc: tcgen05 / TMEM, one launch) + K2 (k2_post_v4)"),
+                     "algorithmic_bytes_note": "40 B per element: x_t, eps, y in / cot out (K1), x_t, eps, cot, vjp, z "
+                                               "in / x_next out (K2) -- the reference's data flow; the bridge-mean pair "
+                                               "moves 4 of K2's bytes under K1 and is charged the same 40",
                      "algorithmic_bytes": alg_bytes, "k1_ms": k1_ms, "k2_ms": k2_ms,
                      "kernel_timing": ("external CUDA events inside the replayed graph, mean of K replays read "
                                        "one by one right after the timed region; last timed step: "

@@ -97,6 +97,7 @@ void read_env() {
   e.no_fast16 = getenv("PSX_NO_FAST16") != nullptr;
   e.no_tc = getenv("PSX_NO_TC") != nullptr;
   e.tc_persist = getenv("PSX_TC_PERSIST") != nullptr;
+  e.no_c2v2 = getenv("PSX_NO_C2V2") != nullptr;
   const char* lag = getenv("PSX_MEAN_LAG_NS");
   e.mean_lag_ns = lag ? atoi(lag) : 8000;
   e.fused = getenv("PSX_FUSED") != nullptr;
@@ -290,6 +291,20 @@ static int make_psf2d(const float* k, int kh, int kw, int sign, Psf2D* out) {
   out->nseg = (int)b.segs.size();
   out->nw4 = (int)(b.w.size() / 4);
   out->dy_lo = b.dy_lo; out->dy_hi = b.dy_hi; out->dx_lo = b.dx_lo; out->dx_hi = b.dx_hi;
+  out->h_v2 = nullptr;
+  if (!use_cols && b.segs.size() <= (size_t)kC2MaxSeg && b.w.size() <= (size_t)kC2MaxTap) {
+    C2Params* v2 = new (std::nothrow) C2Params();
+    if (v2) {
+      v2->nseg = (int)b.segs.size();
+      v2->pad = 0;
+      for (size_t i = 0; i < b.segs.size(); ++i) {
+        const RowSeg& sg = b.segs[i];
+        v2->seg[i] = make_int2((int)(uint16_t)sg.dy | ((int)sg.dx0 << 16), (int)(uint16_t)sg.nch | ((int)sg.w4_off * 4 << 16));
+      }
+      for (size_t i = 0; i < b.w.size(); ++i) v2->ww[i] = make_float2(b.w[i], b.w[i]);
+      out->h_v2 = v2;
+    }
+  }
   int rc = check_cuda(cudaMalloc(&out->d_segs, b.segs.size() * sizeof(RowSeg)), "cudaMalloc PSF segments");
   if (!rc) rc = check_cuda(cudaMalloc(&out->d_w4, b.w.size() * sizeof(float)), "cudaMalloc PSF taps");
   if (!rc) rc = check_cuda(cudaMemcpy(out->d_segs, b.segs.data(), b.segs.size() * sizeof(RowSeg), cudaMemcpyHostToDevice), "copy PSF segments");
@@ -300,6 +315,8 @@ static int make_psf2d(const float* k, int kh, int kw, int sign, Psf2D* out) {
 static void free_psf2d(Psf2D* p) {
   if (p->d_segs) cudaFree(p->d_segs);
   if (p->d_w4) cudaFree(p->d_w4);
+  delete p->h_v2;
+  p->h_v2 = nullptr;
   p->d_segs = nullptr;
   p->d_w4 = nullptr;
 }

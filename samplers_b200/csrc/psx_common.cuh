@@ -41,7 +41,17 @@ struct RowSeg {
   int16_t nch;
   uint16_t w4_off;
 };
+// The same row-segment PSF as a kernel parameter (conv2d_rowseg2): segments and DUPLICATED taps (w, w) live in the
+// parameter constant bank, so that the tap pairs reach packed FFMA2 through uniform registers.
+constexpr int kC2MaxSeg = 80, kC2MaxTap = 368;
+struct C2Params {
+  int nseg, pad;
+  int2 seg[kC2MaxSeg];      // {dy | dx0 << 16, nch | first tap << 16}
+  float2 ww[kC2MaxTap];     // (w, w), 4 per chunk
+};
+static_assert(sizeof(C2Params) <= 3712, "kernel parameter space (4 KB with the other arguments)");
 struct Psf2D {              // one direction (forward or adjoint = flipped PSF)
+  C2Params* h_v2;           // host, owned: parameter image for conv2d_rowseg2, or null (column form / too large)
   RowSeg* d_segs;           // device, owned
   float4* d_w4;             // device, owned: zero-padded taps, 4 per chunk
   int nseg, nw4;            // segments, float4 tap groups
@@ -267,6 +277,7 @@ int conv2d_err_parts(const psx_op* op);
 // Kernel-selection switches of the environment, read once (psx_reload_env re-reads them).
 struct EnvOpts {
   bool no_pipe, no_fast16, no_tc, fused;
+  bool no_c2v2;       // PSX_NO_C2V2: 2-D row-segment PSFs on the scalar-FFMA kernel (conv2d_rowseg) instead of conv2d_rowseg2
   bool tc_persist;    // PSX_TC_PERSIST: blur_k1_tc as one wave of persistent cluster pairs when the planes exceed it
   int mean_lag_ns;    // PSX_MEAN_LAG_NS: the bridge-mean CTAs of blur_k1_tc start this long after the kernel (default 8000:
                       // behind the plane CTAs' load phase, see psx_tcblur.cu)

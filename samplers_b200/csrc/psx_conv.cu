@@ -1770,6 +1770,148 @@ conv2d_rowseg(const float* __restrict__ in, const float* __restrict__ eps, const
   }
 }
 
+// ---- row segments on packed FFMA2 (conv2d_rowseg2).  Same tiling and the same sliding 12-column window as
+// conv2d_rowseg, but (i) the tile is stored as ROW PAIRS P[r][c] = (T[r][c], T[r + 32][c]) -- a thread's two output rows
+// rp, rp + 32 read the two halves of one float2, so one FFMA2 advances both rows and one LDS.128 brings 2 columns x 2
+// rows; (ii) the segments and the duplicated taps (w, w) are a kernel PARAMETER: they are read through the constant
+// bank with warp-uniform indices into uniform registers, which is what keeps FFMA2 at full rate (FFMA2 R, R, UR, R;
+// three vector-register pairs cost a third register-file cycle).  Per chunk of 4 taps: 2 LDS.128 + 32 FFMA2 for 64 FMAs
+// (conv2d_rowseg: 3 LDS.128 + 64 FFMA).
+template <int R>
+__device__ __forceinline__ void c2v2_chunk(float2 (&acc)[8], float2 (&win)[12], uint32_t row, const float2* __restrict__ ww) {
+  constexpr int S = (8 + 4 * R) % 12;  // slot of the incoming columns
+  const float4 a = lds128(row), b = lds128(row + 16);
+  win[S] = make_float2(a.x, a.y); win[S + 1] = make_float2(a.z, a.w);
+  win[S + 2] = make_float2(b.x, b.y); win[S + 3] = make_float2(b.z, b.w);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 w = ww[i];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = __ffma2_rn(w, win[(q + i + 4 * R) % 12], acc[q]);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kC2Threads)
+conv2d_rowseg2(const float* __restrict__ in, const float* __restrict__ eps, const float* __restrict__ y,
+               float* __restrict__ out, float* __restrict__ err_part, const __grid_constant__ C2Params prm, int dy_lo,
+               int dy_hi, int dx_lo, int dx_hi, int pitch2, int C, int H, int W, int64_t obs_repeat, float sa, float s1,
+               float wgt, const float* __restrict__ dsc) {
+  static_assert(kC2TH == 64 && kC2TW == 64 && kC2Threads == 256, "row pairs (r, r + 32), 8 column groups x 32 pairs");
+  step_scalars_k1(dsc, sa, s1, wgt);
+  const TweedieC tc = make_tc(s1, sa);
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[32];
+  const int pr = 32 + dy_hi - dy_lo, tw4 = (kC2TW + dx_hi - dx_lo) >> 2;  // pair rows, float4 groups per tile row
+  const int r0 = blockIdx.y * kC2TH, c0 = blockIdx.x * kC2TW;
+  const int64_t pl = blockIdx.z;
+  const int64_t plane = pl * H * W;
+  {
+    // fill: a warp owns pair rows warp, warp + 8, ...; W, c0 + dx_lo are multiples of 4, so a float4 is inside the image
+    // or outside; both rows of a pair are loaded by the same lane and stored as two 16-byte pieces (x0 y0 x1 y1)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 2   // (unroll 4 with three resident CTAs pinned: 132 / 420 us against 124 / 389 us at L = 16 / 64)
+    for (int r = warp; r < pr; r += kC2Threads / 32) {
+      const int gr0 = r0 + dy_lo + r, gr1 = gr0 + 32;
+      const bool ok0 = gr0 >= 0 && gr0 < H, ok1 = gr1 >= 0 && gr1 < H;
+      for (int c4 = lane; c4 < tw4; c4 += 32) {
+        const int gc = c0 + dx_lo + 4 * c4;
+        const bool cok = gc >= 0 && gc < W;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (ok0 && cok) {
+          const int64_t g = plane + (int64_t)gr0 * W + gc;
+          a = *reinterpret_cast<const float4*>(in + g);
+          if (MODE == C2_RESIDUAL) {
+            const float4 e = *reinterpret_cast<const float4*>(eps + g);
+            a.x = tweedie(a.x, e.x, tc); a.y = tweedie(a.y, e.y, tc);
+            a.z = tweedie(a.z, e.z, tc); a.w = tweedie(a.w, e.w, tc);
+          }
+        }
+        if (ok1 && cok) {
+          const int64_t g = plane + (int64_t)gr1 * W + gc;
+          b = *reinterpret_cast<const float4*>(in + g);
+          if (MODE == C2_RESIDUAL) {
+            const float4 e = *reinterpret_cast<const float4*>(eps + g);
+            b.x = tweedie(b.x, e.x, tc); b.y = tweedie(b.y, e.y, tc);
+            b.z = tweedie(b.z, e.z, tc); b.w = tweedie(b.w, e.w, tc);
+          }
+        }
+        float4* d = reinterpret_cast<float4*>(smem + 2 * (r * pitch2 + 4 * c4));
+        d[0] = make_float4(a.x, b.x, a.y, b.y);
+        d[1] = make_float4(a.z, b.z, a.w, b.w);
+      }
+    }
+  }
+  __syncthreads();
+
+  // thread -> (column group cg: 8 columns, row pair rp: rows rp, rp + 32).  A quarter-warp = 8 consecutive pair rows
+  // of one column group: conflict-free LDS.128 because pitch2 / 2 is odd.
+  const int q = threadIdx.x;
+  const int rp = (q & 7) | ((q >> 6) << 3), cg = (q >> 3) & 7;
+  float2 acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+  const uint32_t base_s = (uint32_t)__cvta_generic_to_shared(smem) +
+                          8u * (uint32_t)((rp - dy_lo) * pitch2 + (8 * cg - dx_lo));
+  const int nseg = prm.nseg;
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    const int2 sg = prm.seg[sgi];
+    const int sg_dy = (int)(short)(sg.x & 0xffff), sg_dx0 = sg.x >> 16;
+    uint32_t row = base_s + 8u * (uint32_t)(sg_dy * pitch2 + sg_dx0);
+    const float2* wp = prm.ww + ((unsigned)sg.y >> 16);
+    float2 win[12];
+    {
+      const float4 a0 = lds128(row), a1 = lds128(row + 16), a2 = lds128(row + 32), a3 = lds128(row + 48);
+      win[0] = make_float2(a0.x, a0.y); win[1] = make_float2(a0.z, a0.w);
+      win[2] = make_float2(a1.x, a1.y); win[3] = make_float2(a1.z, a1.w);
+      win[4] = make_float2(a2.x, a2.y); win[5] = make_float2(a2.z, a2.w);
+      win[6] = make_float2(a3.x, a3.y); win[7] = make_float2(a3.z, a3.w);
+    }
+    row += 64;
+    int nch = sg.y & 0xffff;
+    for (; nch >= 3; nch -= 3, row += 96, wp += 12) {  // the window rotation has period 3
+      c2v2_chunk<0>(acc, win, row, wp);
+      c2v2_chunk<1>(acc, win, row + 32, wp + 4);
+      c2v2_chunk<2>(acc, win, row + 64, wp + 8);
+    }
+    if (nch >= 1) c2v2_chunk<0>(acc, win, row, wp);
+    if (nch >= 2) c2v2_chunk<1>(acc, win, row + 32, wp + 4);
+  }
+
+  float e2 = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int gr = r0 + rp + 32 * h;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gc = c0 + 8 * cg + j;
+      const float av = h ? acc[j].y : acc[j].x;
+      if (gr < H && gc < W) {
+        const int64_t g = plane + (int64_t)gr * W + gc;
+        if (MODE == C2_RESIDUAL) {
+          const int64_t yo = ((pl / C) / obs_repeat * C + pl % C) * (int64_t)H * W + (int64_t)gr * W + gc;
+          const float r = __fsub_rn(__ldg(y + yo), av);
+          e2 = fmaf(r, r, e2);
+          out[g] = r;
+        } else if (MODE == C2_COT) {
+          out[g] = __fmul_rn(wgt, av);
+        } else {
+          out[g] = av;
+        }
+      }
+    }
+  }
+  if (MODE == C2_RESIDUAL) {
+    const float tot = block_sum(e2, red);
+    if (threadIdx.x == 0) {
+      const int tiles = gridDim.x * gridDim.y;
+      const int64_t l = pl / C;
+      const int ch = (int)(pl % C);
+      err_part[l * (int64_t)(C * tiles) + (int64_t)ch * tiles + blockIdx.y * gridDim.x + blockIdx.x] = tot;
+    }
+  }
+}
+
 // One chunk of a COLUMN segment: 4 taps x (8 output rows x 2 columns).  The window holds 12 consecutive rows of the
 // thread's column pair and rotates by 4 rows per chunk (R = chunk index modulo 3, as in c2_chunk).  ODD: the pair
 // starts at an odd tile column, i.e. it is not 8-byte aligned and is read as two LDS.32.
@@ -1945,6 +2087,23 @@ static int run_conv2d(const psx_op* op, const float* in, const float* eps, const
                                                          psf.dy_lo, psf.dy_hi, dx_lo4, tw, pitch, op->C, op->H, op->W,
                                                          obs_repeat, sa, s1, wgt, dsc);
     return check_cuda(cudaGetLastError(), "conv2d_colseg launch");
+  }
+  if (psf.h_v2 && (op->W & 3) == 0 && !env_opts().no_c2v2) {
+    // packed-FFMA2 kernel: row-pair tile, segments / taps in the parameter bank
+    int pitch2 = kC2TW + psf.dx_hi - psf.dx_lo;  // multiple of 4 -> + 2: even with pitch2 / 2 odd
+    pitch2 += 2;
+    const size_t smem2 = (size_t)(32 + psf.dy_hi - psf.dy_lo) * pitch2 * sizeof(float2);
+    if (smem2 <= 200 * 1024) {
+      static bool attr2 = false;
+      if (!attr2) {
+        cudaFuncSetAttribute(conv2d_rowseg2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr2 = true;
+      }
+      conv2d_rowseg2<MODE><<<grid, kC2Threads, smem2, st>>>(in, eps, y, out, err_part, *psf.h_v2, psf.dy_lo, psf.dy_hi,
+                                                           psf.dx_lo, psf.dx_hi, pitch2, op->C, op->H, op->W,
+                                                           obs_repeat, sa, s1, wgt, dsc);
+      return check_cuda(cudaGetLastError(), "conv2d_rowseg2 launch");
+    }
   }
   const int tw = kC2TW + psf.dx_hi - psf.dx_lo;
   int pitch = tw;                      // multiple of 4 with pitch / 4 odd: conflict-free LDS.128 (see the kernel)

@@ -49,6 +49,12 @@ def k2m(i):
     _native.dps_post_mean(d["mean"], d["cot"], d["v"], d["z"], d["part"], nat.err_parts, n, 0.6, 0.05, 1.0, d["out"], None)
 
 
+if os.environ.get("ONCE"):  # one launch of each kernel of the pair (for ncu)
+    for i in range(nsets):
+        k1m(i); k2m(i)
+    torch.cuda.synchronize()
+    sys.exit(0)
+
 for rep in range(2):
     print(f"classic: K1 {bench._rotate_time(k1, nsets, 10) * 1e3:.2f} us  K2 {bench._rotate_time(k2, nsets, 10) * 1e3:.2f} us")
     for lag in [int(v) for v in os.environ.get("LAGS", "0,2000,6000,8000,9000,10000,11000,12000,14000").split(",")]:
