@@ -305,6 +305,7 @@ def run_own(args):
     fused_s = (k1_ms + k2_ms) / 1e3
     achieved = alg_bytes / fused_s / 1e9
     # ---------------- everything below is outside the timed regions; the UNet and its buffers are gone by now
+    fused_mean = bool(getattr(run, "_fused_mean", False))
     del run, sampler, net, problem, summary, gathered
     torch.cuda.empty_cache()
     extra = {}
@@ -345,7 +346,7 @@ def run_own(args):
                      "peak_source": peak_src,
                      "kernel": ("fused DPS step = K1 (blur_k1_tc<0, 1>: tcgen05 / TMEM, one launch; its spare CTAs on the "
                                 "SMs the planes leave idle write the bridge mean) + K2 (k2_post_mean, on that mean)"
-                                if getattr(run, "_fused_mean", False) else
+                                if fused_mean else
                                 "fused DPS step = K1 (blur_k1_tc: tcgen05 / TMEM, one launch) + K2 (k2_post_v4)"),
                      "algorithmic_bytes_note": "40 B per element: x_t, eps, y in / cot out (K1), x_t, eps, cot, vjp, z "
                                                "in / x_next out (K2) -- the reference's data flow; the bridge-mean pair "

@@ -375,6 +375,27 @@ k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const flo
   const TweedieC tc = make_tc(s1, sa);
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
+  const int64_t n4 = n >> 2;
+  const int64_t beg = (int64_t)blockIdx.x * chunk4, end = min(beg + chunk4, n4);
+  const int64_t so = l * n;
+  constexpr int U = 2;
+  constexpr int64_t kStride = (int64_t)kThreads * U;
+  float4 xv[U], ev[U], dv[U], vv[U], zv[U];
+#define PSX_K2_LOAD(BASE)                                         \
+  _Pragma("unroll") for (int u = 0; u < U; ++u) {                 \
+    const int64_t i = (BASE) + (int64_t)u * kThreads;             \
+    if (i < end) {                                                \
+      xv[u] = ld_stream4(x + so + 4 * i);                         \
+      ev[u] = ld_stream4(eps + so + 4 * i);                       \
+      dv[u] = ld_stream4(cot + so + 4 * i);                       \
+      vv[u] = ld_stream4(vjp + so + 4 * i);                       \
+      if (ZMODE == 1) zv[u] = ld_stream4(z + so + 4 * i);         \
+    }                                                             \
+  }
+  // The first batch is requested BEFORE the reduction of the partial sums (a dependent global round trip plus a block
+  // barrier): the guidance scale is only needed by the last operation of an element.
+  int64_t base = beg + threadIdx.x;
+  PSX_K2_LOAD(base)
   float scale = gamma;  // err_parts == 0: fixed guidance scale (PGDM); otherwise DPS: gamma / (|r| + 1e-9)
   if (err_parts > 0) {
     const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
@@ -382,25 +403,8 @@ k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const flo
     scale = __fdiv_rn(gamma, __fadd_rn(err, 1e-9f));
     if (err_out && blockIdx.x == 0 && threadIdx.x == 0) err_out[l] = err;
   }
-
-  const int64_t n4 = n >> 2;
-  const int64_t beg = (int64_t)blockIdx.x * chunk4, end = min(beg + chunk4, n4);
-  const int64_t so = l * n;
-  constexpr int U = 2;
-  for (int64_t base = beg + threadIdx.x; base < end; base += (int64_t)kThreads * U) {
-    float4 xv[U], ev[U], dv[U], vv[U], zv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t i = base + (int64_t)u * kThreads;
-      if (i < end) {
-        xv[u] = ld_stream4(x + so + 4 * i);
-        ev[u] = ld_stream4(eps + so + 4 * i);
-        dv[u] = ld_stream4(cot + so + 4 * i);
-        vv[u] = ld_stream4(vjp + so + 4 * i);
-        if (ZMODE == 1) zv[u] = ld_stream4(z + so + 4 * i);
-      }
-    }
-    if (ZMODE == 2) {  // generated while the loads above are in flight
+  for (; base < end; base += kStride) {
+    if (ZMODE == 2) {  // generated while the loads are in flight
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t i = base + (int64_t)u * kThreads;
@@ -425,7 +429,9 @@ k2_post_v4(const float* __restrict__ x, const float* __restrict__ eps, const flo
         st_stream4(x_next + so + 4 * i, o);
       }
     }
+    PSX_K2_LOAD(base + kStride)
   }
+#undef PSX_K2_LOAD
 }
 
 template <int ZMODE>
@@ -509,6 +515,24 @@ k2_post_mean(const float* __restrict__ mean, const float* __restrict__ cot, cons
   }
   __shared__ float red[32];
   const int64_t l = blockIdx.y;
+  const int64_t n4 = n >> 2;
+  const int64_t beg = (int64_t)blockIdx.x * chunk4, end = min(beg + chunk4, n4);
+  const int64_t so = l * n;
+  constexpr int U = 2;
+  constexpr int64_t kStride = (int64_t)kThreads * U;
+  float4 mv[U], dv[U], vv[U], zv[U];
+#define PSX_K2M_LOAD(BASE)                                        \
+  _Pragma("unroll") for (int u = 0; u < U; ++u) {                 \
+    const int64_t i = (BASE) + (int64_t)u * kThreads;             \
+    if (i < end) {                                                \
+      mv[u] = ld_stream4(mean + so + 4 * i);                      \
+      dv[u] = ld_stream4(cot + so + 4 * i);                       \
+      vv[u] = ld_stream4(vjp + so + 4 * i);                       \
+      if (ZMODE == 1) zv[u] = ld_stream4(z + so + 4 * i);         \
+    }                                                             \
+  }
+  int64_t base = beg + threadIdx.x;
+  PSX_K2M_LOAD(base)  // ahead of the partial-sum reduction, as in k2_post_v4
   float scale = gamma;
   if (err_parts > 0) {
     const float e2 = sum_parts(err_part + l * err_parts, err_parts, red);
@@ -516,22 +540,7 @@ k2_post_mean(const float* __restrict__ mean, const float* __restrict__ cot, cons
     scale = __fdiv_rn(gamma, __fadd_rn(err, 1e-9f));
     if (err_out && blockIdx.x == 0 && threadIdx.x == 0) err_out[l] = err;
   }
-  const int64_t n4 = n >> 2;
-  const int64_t beg = (int64_t)blockIdx.x * chunk4, end = min(beg + chunk4, n4);
-  const int64_t so = l * n;
-  constexpr int U = 2;
-  for (int64_t base = beg + threadIdx.x; base < end; base += (int64_t)kThreads * U) {
-    float4 mv[U], dv[U], vv[U], zv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t i = base + (int64_t)u * kThreads;
-      if (i < end) {
-        mv[u] = ld_stream4(mean + so + 4 * i);
-        dv[u] = ld_stream4(cot + so + 4 * i);
-        vv[u] = ld_stream4(vjp + so + 4 * i);
-        if (ZMODE == 1) zv[u] = ld_stream4(z + so + 4 * i);
-      }
-    }
+  for (; base < end; base += kStride) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t i = base + (int64_t)u * kThreads;
@@ -549,7 +558,9 @@ k2_post_mean(const float* __restrict__ mean, const float* __restrict__ cot, cons
         st_stream4(x_next + so + 4 * i, o);
       }
     }
+    PSX_K2M_LOAD(base + kStride)
   }
+#undef PSX_K2M_LOAD
 }
 
 int launch_post_mean(const float* mean, const float* cot, const float* vjp, const float* z, const float* err_part,
