@@ -442,7 +442,7 @@ def roofline_by_config(device, peak: float) -> list:
         classic = {}
         if nat.fuses_mean(L):
             # the pair the sampler runs for this operator at this batch: CTAs on the SMs K1 leaves idle write the bridge
-            # mean, K2 reads it instead of x_t and eps (bit-identical results)
+            # mean + std z, K2 reads it instead of x_t, eps and z (bit-identical results)
             classic = {"k1_us_classic_pair": m1 * 1e3, "k2_us_classic_pair": m2 * 1e3, "pair": "K1 + bridge mean / K2 "
                        "on the mean (psx_dps_pre_mean / psx_dps_post_mean); *_classic_pair = psx_dps_pre / psx_dps_post"}
             for d in S:
@@ -451,11 +451,11 @@ def roofline_by_config(device, peak: float) -> list:
             def k1m(i):
                 d = S[i]
                 _native.dps_pre_mean(nat, d["x"], d["eps"], y, L, 0.8, 0.6, 400.0, 0.99, 0.01, d["cot"], d["part"],
-                                     d["mean"], d["ws"])
+                                     d["mean"], d["ws"], z=d["z"], std=0.05)
 
             def k2m(i):
                 d = S[i]
-                _native.dps_post_mean(d["mean"], d["cot"], d["v"], d["z"], d["part"], nat.err_parts, n, 0.6, 0.05,
+                _native.dps_post_mean(d["mean"], d["cot"], d["v"], None, d["part"], nat.err_parts, n, 0.6, 0.0,
                                       1.0, d["out"], None)
 
             for i in range(nsets):

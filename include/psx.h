@@ -211,21 +211,24 @@ PSX_API int psx_dps_post_dev(const float* d_x_t, const float* d_eps, const float
  * 148 SMs hold planes): psx_op_fuses_mean(op, L) == 1 -- the same launch carries extra CTAs on the idle SMs that
  * write the mean under K1's span, and K2 then reads ONE array instead of x_t and eps: 4 B per element leave the
  * HBM-bound kernel (K2 24 -> 20 B per element).
- *   psx_dps_pre_mean[_dev]   = psx_dps_pre[_dev] + d_mean_out (L, n); c_ell / c_s by value or from row entries 3-4
- *   psx_dps_post_mean[_dev]  = psx_dps_post[_dev] with d_mean in place of (d_x_t, d_eps); d_x_next is usually the
- *                              state x_t itself (in-place step)
+ *   psx_dps_pre_mean[_dev]   = psx_dps_pre[_dev] + d_mean_out (L, n); c_ell / c_s / std by value or from row entries
+ *                              3-5.  d_z (the step's N(0,1) field, drawn before K1) may be NULL; when given,
+ *                              d_mean_out = mean + std * z (bridge_kernels.py:59) and K2 takes d_z = NULL
+ *   psx_dps_post_mean[_dev]  = psx_dps_post[_dev] with d_mean in place of (d_x_t, d_eps); d_z = NULL: no noise term
+ *                              (std == 0, or already folded into d_mean); d_x_next is usually the state x_t itself
+ *                              (in-place step).  K2 then moves 16 (z folded) or 20 B per element instead of 24
  * The roundings are those of psx_dps_post (Tweedie, mul, mul, add; then + std*z; then + scale*grad), so the pair is
  * bit-identical to psx_dps_pre + psx_dps_post.  Other operators / larger batches: PSX_ERR_UNSUPPORTED (their K1 is
  * HBM-bound or fills the GPU; moving the 4 bytes would gain nothing). */
 PSX_API int psx_op_fuses_mean(const psx_op* op, int64_t L);
 PSX_API int psx_dps_pre_mean(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y, int64_t L,
                              int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight, float c_ell,
-                             float c_s, float* d_cot, float* d_err_part, float* d_mean_out, void* d_workspace,
-                             size_t workspace_bytes, void* stream);
+                             float c_s, const float* d_z, float std, float* d_cot, float* d_err_part,
+                             float* d_mean_out, void* d_workspace, size_t workspace_bytes, void* stream);
 PSX_API int psx_dps_pre_mean_dev(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y,
-                                 int64_t L, int64_t obs_repeat, const float* d_step_row, float* d_cot,
-                                 float* d_err_part, float* d_mean_out, void* d_workspace, size_t workspace_bytes,
-                                 void* stream);
+                                 int64_t L, int64_t obs_repeat, const float* d_step_row, const float* d_z,
+                                 float* d_cot, float* d_err_part, float* d_mean_out, void* d_workspace,
+                                 size_t workspace_bytes, void* stream);
 PSX_API int psx_dps_post_mean(const float* d_mean, const float* d_cot, const float* d_vjp, const float* d_z,
                               const float* d_err_part, int err_parts, int64_t L, int64_t n, float sqrt_1m_acp,
                               float std, float gamma, float* d_x_next, float* d_err_out, void* stream);

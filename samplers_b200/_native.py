@@ -56,9 +56,9 @@ PROTOTYPES = {
     "psx_dps_post_dev": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f32p, _f32p,
                                    _f32p, _vp]),
     "psx_op_fuses_mean": (C.c_int, [_opp, _i64]),
-    "psx_dps_pre_mean": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f, _f, _f, _f, _f, _f32p, _f32p, _f32p,
-                                   _vp, C.c_size_t, _vp]),
-    "psx_dps_pre_mean_dev": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _vp,
+    "psx_dps_pre_mean": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f, _f, _f, _f, _f, _f32p, _f, _f32p, _f32p,
+                                   _f32p, _vp, C.c_size_t, _vp]),
+    "psx_dps_pre_mean_dev": (C.c_int, [_opp, _f32p, _f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _vp,
                                        C.c_size_t, _vp]),
     "psx_dps_post_mean": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _i64, _i64, _f, _f, _f, _f32p,
                                     _f32p, _vp]),
@@ -315,20 +315,21 @@ def dps_post_dev(x_t, eps, cot, vjp, z, err_part, err_parts: int, n: int, step_r
 
 
 def dps_pre_mean(op: NativeOp, x_t, eps, y, obs_repeat: int, sa: float, s1: float, weight: float, c_ell: float,
-                 c_s: float, cot, err_part, mean, ws, step_row=None) -> None:
-    """psx_dps_pre that also writes the bridge mean c_ell x_t + c_s x0 (``op.fuses_mean`` operators only); with
-    ``step_row`` the scalars come from the device row (psx_dps_pre_mean_dev)."""
+                 c_s: float, cot, err_part, mean, ws, step_row=None, z=None, std: float = 0.0) -> None:
+    """psx_dps_pre that also writes the bridge mean c_ell x_t + c_s x0 (``op.fuses_mean`` operators only) -- plus
+    std * z when the step's noise ``z`` is given; with ``step_row`` the scalars come from the device row
+    (psx_dps_pre_mean_dev)."""
     global launch_count
     L = x_t.shape[0]
     wsb = 0 if ws is None else ws.numel() * 4
     with torch.cuda.device(x_t.device):
         if step_row is None:
             check(load().psx_dps_pre_mean(op.handle, x_t.data_ptr(), eps.data_ptr(), y.data_ptr(), L, obs_repeat, sa,
-                                          s1, weight, c_ell, c_s, cot.data_ptr(), err_part.data_ptr(),
+                                          s1, weight, c_ell, c_s, ptr(z), std, cot.data_ptr(), err_part.data_ptr(),
                                           mean.data_ptr(), ptr(ws), wsb, stream_ptr(x_t.device)))
         else:
             check(load().psx_dps_pre_mean_dev(op.handle, x_t.data_ptr(), eps.data_ptr(), y.data_ptr(), L, obs_repeat,
-                                              step_row.data_ptr(), cot.data_ptr(), err_part.data_ptr(),
+                                              step_row.data_ptr(), ptr(z), cot.data_ptr(), err_part.data_ptr(),
                                               mean.data_ptr(), ptr(ws), wsb, stream_ptr(x_t.device)))
     launch_count += 1
 
@@ -344,7 +345,7 @@ def dps_post_mean(mean, cot, vjp, z, err_part, err_parts: int, n: int, s1: float
                                            err_parts if err_part is not None else 0, L, n, s1, std, gamma,
                                            x_next.data_ptr(), ptr(err_out), stream_ptr(mean.device)))
         else:
-            check(load().psx_dps_post_mean_dev(mean.data_ptr(), cot.data_ptr(), vjp.data_ptr(), z.data_ptr(),
+            check(load().psx_dps_post_mean_dev(mean.data_ptr(), cot.data_ptr(), vjp.data_ptr(), ptr(z),
                                                ptr(err_part), err_parts if err_part is not None else 0, L, n,
                                                step_row.data_ptr(), x_next.data_ptr(), ptr(err_out),
                                                stream_ptr(mean.device)))

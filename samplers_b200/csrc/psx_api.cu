@@ -99,7 +99,7 @@ void read_env() {
   e.tc_persist = getenv("PSX_TC_PERSIST") != nullptr;
   e.no_c2v2 = getenv("PSX_NO_C2V2") != nullptr;
   const char* lag = getenv("PSX_MEAN_LAG_NS");
-  e.mean_lag_ns = lag ? atoi(lag) : 8000;
+  e.mean_lag_ns = lag ? atoi(lag) : 5000;
   e.fused = getenv("PSX_FUSED") != nullptr;
   const char* sp = getenv("PSX_SPLIT");
   e.split = sp ? atoi(sp) : 0;
@@ -438,7 +438,7 @@ static int dps_pre_impl(const char* who, const psx_op* op, const float* d_x_t, c
                         int64_t L, int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight,
                         const float* d_row, float* d_cot, float* d_err_part, float* d_x0_out, void* ws,
                         size_t ws_bytes, void* stream, float* d_mean_out = nullptr, float c_ell = 0.f,
-                        float c_s = 0.f) {
+                        float c_s = 0.f, const float* d_z = nullptr, float sd = 0.f) {
   if (!(op && d_x_t && d_eps && d_y && d_cot && d_err_part)) return fail(PSX_ERR_INVALID, std::string(who) + ": null pointer");
   if (!(L > 0 && L <= 65535)) return fail(PSX_ERR_INVALID, std::string(who) + ": L must be in [1, 65535]");
   if (!(obs_repeat > 0)) return fail(PSX_ERR_INVALID, std::string(who) + ": obs_repeat must be positive");
@@ -457,7 +457,7 @@ static int dps_pre_impl(const char* who, const psx_op* op, const float* d_x_t, c
                             d_err_part, d_x0_out, st);
     case PSX_OP_SEPBLUR:
       return launch_pre_sepblur(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight, d_row,
-                                d_cot, d_err_part, d_x0_out, (float*)ws, st, false, d_mean_out, c_ell, c_s);
+                                d_cot, d_err_part, d_x0_out, (float*)ws, st, false, d_mean_out, c_ell, c_s, d_z, sd);
     case PSX_OP_CONV2D:
       return launch_pre_conv2d(op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight, d_row,
                                d_cot, d_err_part, d_x0_out, (float*)ws, st);
@@ -488,22 +488,23 @@ PSX_API int psx_op_fuses_mean(const psx_op* op, int64_t L) {
 
 PSX_API int psx_dps_pre_mean(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y, int64_t L,
                              int64_t obs_repeat, float sqrt_acp, float sqrt_1m_acp, float lik_weight, float c_ell,
-                             float c_s, float* d_cot, float* d_err_part, float* d_mean_out, void* ws,
-                             size_t ws_bytes, void* stream) {
+                             float c_s, const float* d_z, float std_, float* d_cot, float* d_err_part,
+                             float* d_mean_out, void* ws, size_t ws_bytes, void* stream) {
   PSX_REQUIRE(d_mean_out != nullptr, "psx_dps_pre_mean: null d_mean_out");
   PSX_REQUIRE(sqrt_acp > 0.f && std::isfinite(sqrt_acp) && std::isfinite(sqrt_1m_acp) && std::isfinite(lik_weight) &&
-                  std::isfinite(c_ell) && std::isfinite(c_s),
+                  std::isfinite(c_ell) && std::isfinite(c_s) && std::isfinite(std_),
               "psx_dps_pre_mean: non-finite or non-positive schedule scalar");
   return dps_pre_impl("psx_dps_pre_mean", op, d_x_t, d_eps, d_y, L, obs_repeat, sqrt_acp, sqrt_1m_acp, lik_weight,
-                      nullptr, d_cot, d_err_part, nullptr, ws, ws_bytes, stream, d_mean_out, c_ell, c_s);
+                      nullptr, d_cot, d_err_part, nullptr, ws, ws_bytes, stream, d_mean_out, c_ell, c_s, d_z, std_);
 }
 
 PSX_API int psx_dps_pre_mean_dev(const psx_op* op, const float* d_x_t, const float* d_eps, const float* d_y,
-                                 int64_t L, int64_t obs_repeat, const float* d_step_row, float* d_cot,
-                                 float* d_err_part, float* d_mean_out, void* ws, size_t ws_bytes, void* stream) {
+                                 int64_t L, int64_t obs_repeat, const float* d_step_row, const float* d_z,
+                                 float* d_cot, float* d_err_part, float* d_mean_out, void* ws, size_t ws_bytes,
+                                 void* stream) {
   PSX_REQUIRE(d_step_row != nullptr && d_mean_out != nullptr, "psx_dps_pre_mean_dev: null step row / d_mean_out");
   return dps_pre_impl("psx_dps_pre_mean_dev", op, d_x_t, d_eps, d_y, L, obs_repeat, 1.f, 0.f, 1.f, d_step_row, d_cot,
-                      d_err_part, nullptr, ws, ws_bytes, stream, d_mean_out, 0.f, 0.f);
+                      d_err_part, nullptr, ws, ws_bytes, stream, d_mean_out, 0.f, 0.f, d_z, 0.f);
 }
 
 PSX_API int psx_dps_post_mean(const float* d_mean, const float* d_cot, const float* d_vjp, const float* d_z,
@@ -512,7 +513,6 @@ PSX_API int psx_dps_post_mean(const float* d_mean, const float* d_cot, const flo
   PSX_REQUIRE(d_mean && d_cot && d_vjp && d_x_next, "psx_dps_post_mean: null pointer");
   PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts >= 0, "psx_dps_post_mean: bad sizes");
   PSX_REQUIRE((err_parts > 0) == (d_err_part != nullptr), "psx_dps_post_mean: d_err_part and err_parts must agree");
-  PSX_REQUIRE(d_z || std_ == 0.f, "psx_dps_post_mean: d_z may be NULL only when std == 0");
   PSX_REQUIRE(std::isfinite(sqrt_1m_acp) && std::isfinite(std_) && std::isfinite(gamma),
               "psx_dps_post_mean: non-finite scalar");
   return launch_post_mean(d_mean, d_cot, d_vjp, std_ == 0.f ? nullptr : d_z, d_err_part, err_parts, L, n,
@@ -522,7 +522,7 @@ PSX_API int psx_dps_post_mean(const float* d_mean, const float* d_cot, const flo
 PSX_API int psx_dps_post_mean_dev(const float* d_mean, const float* d_cot, const float* d_vjp, const float* d_z,
                                   const float* d_err_part, int err_parts, int64_t L, int64_t n,
                                   const float* d_step_row, float* d_x_next, float* d_err_out, void* stream) {
-  PSX_REQUIRE(d_mean && d_cot && d_vjp && d_z && d_x_next && d_step_row, "psx_dps_post_mean_dev: null pointer");
+  PSX_REQUIRE(d_mean && d_cot && d_vjp && d_x_next && d_step_row, "psx_dps_post_mean_dev: null pointer");
   PSX_REQUIRE(L > 0 && L <= 65535 && n > 0 && err_parts >= 0, "psx_dps_post_mean_dev: bad sizes");
   PSX_REQUIRE((err_parts > 0) == (d_err_part != nullptr),
               "psx_dps_post_mean_dev: d_err_part and err_parts must agree");

@@ -254,7 +254,7 @@ int launch_pre_box(const psx_op* op, const float* x, const float* eps, const flo
 int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                        int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                        float* x0_out, float* ws, cudaStream_t st, bool half = false, float* mean_out = nullptr,
-                       float c_ell = 0.f, float c_s = 0.f);
+                       float c_ell = 0.f, float c_s = 0.f, const float* zn = nullptr, float sd = 0.f);
 bool fuses_mean(const psx_op* op, int64_t L);
 bool tcblur_mean_fits(const psx_op* op, int64_t L);
 int launch_post_mean(const float* mean, const float* cot, const float* vjp, const float* z, const float* err_part,
@@ -271,7 +271,8 @@ void tcblur_release(psx_op* op);
 bool tcblur_available(const psx_op* op);
 int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                           int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot,
-                          float* err_part, float* mean_out, float c_ell, float c_s, cudaStream_t st);
+                          float* err_part, float* mean_out, float c_ell, float c_s, const float* zn, float sd,
+                          cudaStream_t st);
 int conv2d_err_parts(const psx_op* op);
 
 // Kernel-selection switches of the environment, read once (psx_reload_env re-reads them).
@@ -279,7 +280,7 @@ struct EnvOpts {
   bool no_pipe, no_fast16, no_tc, fused;
   bool no_c2v2;       // PSX_NO_C2V2: 2-D row-segment PSFs on the scalar-FFMA kernel (conv2d_rowseg) instead of conv2d_rowseg2
   bool tc_persist;    // PSX_TC_PERSIST: blur_k1_tc as one wave of persistent cluster pairs when the planes exceed it
-  int mean_lag_ns;    // PSX_MEAN_LAG_NS: the bridge-mean CTAs of blur_k1_tc start this long after the kernel (default 8000:
+  int mean_lag_ns;    // PSX_MEAN_LAG_NS: the bridge-mean CTAs of blur_k1_tc start this long after the kernel (default 5000:
                       // behind the plane CTAs' load phase, see psx_tcblur.cu)
   int split;  // PSX_SPLIT: forced number of K1 sample groups, 0 = automatic
 };

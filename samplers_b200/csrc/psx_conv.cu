@@ -1433,7 +1433,7 @@ bool fuses_mean(const psx_op* op, int64_t L) {
 int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                        int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot, float* err_part,
                        float* x0_out, float* ws, cudaStream_t st, bool half, float* mean_out, float c_ell,
-                       float c_s) {
+                       float c_s, const float* zn, float sd) {
   if (x0_out) return fail(PSX_ERR_UNSUPPORTED, "psx_dps_pre: d_x0_out is not produced for blur operators");
   const int64_t planes = L * op->C;
   // tensor-core single launch (psx_tcblur.cu): 256 x 256 planes, symmetric taps shared by rows and columns
@@ -1442,7 +1442,7 @@ int launch_pre_sepblur(const psx_op* op, const float* x, const float* eps, const
                                      "batch size (psx_op_fuses_mean)");
   if (!half && tcblur_available(op) && !env_opts().no_tc)
     return launch_pre_sepblur_tc(op, x, eps, y, L, obs_repeat, sa, s1, w, dsc, cot, err_part, mean_out, c_ell, c_s,
-                                 st);
+                                 zn, sd, st);
 
   // cluster-fused single launch for 256 x 256 planes
   if (op->H == kFusedCL * kFusedRB && op->W == kFusedW && op->fh.k == 40 && op->fv.k == 40 && op->ah.k == 40 &&

@@ -202,7 +202,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     blur_k1_tc(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ y,
                float* __restrict__ cot, float* __restrict__ err_part, const uint8_t* __restrict__ bimg, float inv_scale,
                int C, int64_t obs_repeat, int pp, float sa, float s1, float coef, const float* __restrict__ dsc,
-               int planes, float* __restrict__ mean_out, float c_ell, float c_s, int mean_lag_ns) {
+               int planes, float* __restrict__ mean_out, float c_ell, float c_s, int mean_lag_ns,
+               const float* __restrict__ zn, float sd) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* op = smem;
   uint8_t* bsm = smem + kOpBytes;
@@ -220,17 +221,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       s1 = __ldg(dsc + 1);
       c_ell = __ldg(dsc + 3);
       c_s = __ldg(dsc + 4);
+      sd = __ldg(dsc + 5);
     }
     const TweedieC tw = make_tc(s1, sa);
+    const bool has_z = zn != nullptr;  // the step's noise is known: the stored array is mean + std z (K2's roundings)
     // Tiles of 4096 elements: x_t and eps arrive by bulk copies, the mean leaves through the LSU -- the load / store
     // path of one SM streams ~50 GB/s, the copy engine more than twice that, so the 12 B per element are split 8 / 4
     // between them.  (Measured: everything through the LSU, or the mean stored by bulk copies whose smem reads the
     // producer has to await: 14 us per 725 KB either way.)  full[s]: both arrays of the stage have landed (bytes);
     // done[s]: the 16 warps hold the stage's values in registers.  Warp 18's lane 0 is the producer.
-    constexpr int kMT = 4096, kMS = 5;                       // tile elements, stages (5 x 32 KB)
+    constexpr int kMT = 4096, kMS = 3, kMA = 3;              // tile elements, stages (3 x 48 KB), arrays per stage
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* done = full + kMS;
-    float* stage = reinterpret_cast<float*>(smem + 1024);    // [kMS][x: kMT | eps: kMT]
+    float* stage = reinterpret_cast<float*>(smem + 1024);    // [kMS][x: kMT | eps: kMT | z: kMT]
+    static_assert(1024 + kMS * kMA * kMT * 4 <= kTcSmem, "mean-role stages");
     const int64_t tiles = (int64_t)planes * (kTcN * kTcN / kMT);
     const int64_t E = (int64_t)gridDim.x - 2 * planes, e = (int64_t)blockIdx.x - 2 * planes;
     const int nt = (int)((tiles - e + E - 1) / E);           // this CTA's tiles: e, e + E, ...
@@ -254,11 +258,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         auto request = [&](int k) {
           const int st_ = k % kMS;
           const int64_t off = tile_off(k);
-          mbar_expect_tx(full + st_, 2 * kMT * 4);
-          bulk_g2s(stage + st_ * 2 * kMT, x + off, kMT * 4, full + st_);
-          bulk_g2s(stage + st_ * 2 * kMT + kMT, eps + off, kMT * 4, full + st_);
+          mbar_expect_tx(full + st_, (has_z ? 3 : 2) * kMT * 4);
+          bulk_g2s(stage + st_ * kMA * kMT, x + off, kMT * 4, full + st_);
+          bulk_g2s(stage + st_ * kMA * kMT + kMT, eps + off, kMT * 4, full + st_);
+          if (has_z) bulk_g2s(stage + st_ * kMA * kMT + 2 * kMT, zn + off, kMT * 4, full + st_);
         };
-        // Start BEHIND the plane CTAs' load phase (~8 us): that phase is bound by the SM <-> L2 path and gives way to
+        // Start BEHIND most of the plane CTAs' load phase (~8 us; default delay 5 us since the z stage made this role 14.5 us long): that phase is bound by the SM <-> L2 path and gives way to
         // any other traffic (K1 +1.0 us when both start together), the ~10 us of UMMA chain after it leave the memory
         // system idle, and by then x_t / eps are L2 hits.  Measured at L = 16 (profiles/r02i_mean_ab.txt): lag 0 ->
         // K1 21.6 us, 6-10 us -> 20.9-21.1 us (classic 20.7), from 11 us on the mean CTAs (10.5 us) end after the planes.
@@ -278,16 +283,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     } else if (warp < kTcWarps) {
       for (int k = 0; k < nt; ++k) {
         const int st_ = k % kMS;
-        const float4* xs = reinterpret_cast<const float4*>(stage + st_ * 2 * kMT);
+        const float4* xs = reinterpret_cast<const float4*>(stage + st_ * kMA * kMT);
         const float4* es = xs + kMT / 4;
+        const float4* zs = es + kMT / 4;
         const int g = (int)e + k * (int)E;
         float* mp = mean_out + (int64_t)((g % planes) * (kTcN * kTcN / kMT) + g / planes) * kMT;
         mbar_wait(full + st_, (uint32_t)(k / kMS) & 1u);
-        float4 xv[kMT / 4 / kTcEpi], ev[kMT / 4 / kTcEpi];
+        float4 xv[kMT / 4 / kTcEpi], ev[kMT / 4 / kTcEpi], zv[kMT / 4 / kTcEpi];
 #pragma unroll
         for (int u = 0; u < kMT / 4 / kTcEpi; ++u) {
           xv[u] = xs[tid + u * kTcEpi];
           ev[u] = es[tid + u * kTcEpi];
+          zv[u] = has_z ? zs[tid + u * kTcEpi] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         warp_arrive(done + st_, lane);  // the values are in registers: the stage may be refilled
 #pragma unroll
@@ -297,6 +304,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
           m.y = __fadd_rn(__fmul_rn(c_ell, xv[u].y), __fmul_rn(c_s, tweedie(xv[u].y, ev[u].y, tw)));
           m.z = __fadd_rn(__fmul_rn(c_ell, xv[u].z), __fmul_rn(c_s, tweedie(xv[u].z, ev[u].z, tw)));
           m.w = __fadd_rn(__fmul_rn(c_ell, xv[u].w), __fmul_rn(c_s, tweedie(xv[u].w, ev[u].w, tw)));
+          if (has_z) {  // bridge_kernels.py:59: mean + std * z, one rounding per operation
+            m.x = __fadd_rn(m.x, __fmul_rn(sd, zv[u].x));
+            m.y = __fadd_rn(m.y, __fmul_rn(sd, zv[u].y));
+            m.z = __fadd_rn(m.z, __fmul_rn(sd, zv[u].z));
+            m.w = __fadd_rn(m.w, __fmul_rn(sd, zv[u].w));
+          }
           st_stream4(mp + 4 * (tid + u * kTcEpi), m);
         }
       }
@@ -902,7 +915,8 @@ bool tcblur_mean_fits(const psx_op* op, int64_t L) {
 
 int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, const float* y, int64_t L,
                           int64_t obs_repeat, float sa, float s1, float w, const float* dsc, float* cot,
-                          float* err_part, float* mean_out, float c_ell, float c_s, cudaStream_t st) {
+                          float* err_part, float* mean_out, float c_ell, float c_s, const float* zn, float sd,
+                          cudaStream_t st) {
   static bool attr[64] = {};  // function attributes are per device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -930,7 +944,7 @@ int launch_pre_sepblur_tc(const psx_op* op, const float* x, const float* eps, co
 #define PSX_TC_LAUNCH(LOOP_, MEAN_)                                                                                  \
   blur_k1_tc<LOOP_, MEAN_><<<grid, kTcThreads, kTcSmem, st>>>(x, eps, y, cot, err_part, op->d_tc_img, op->tc_inv_scale, \
                                                               op->C, obs_repeat, op->err_parts / op->C, sa, s1, coef, \
-                                                              dsc, (int)planes, mean_out, c_ell, c_s, env_opts().mean_lag_ns)
+                                                              dsc, (int)planes, mean_out, c_ell, c_s, env_opts().mean_lag_ns, zn, sd)
   if (mean_out) PSX_TC_LAUNCH(false, true);
   else if (loop) PSX_TC_LAUNCH(true, false);
   else PSX_TC_LAUNCH(false, false);

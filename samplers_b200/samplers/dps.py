@@ -147,12 +147,14 @@ class DPSRun:
             self.k_dev.add_(1)
             return
         if self._fused_mean:
-            _native.dps_pre_mean(self.op, self.x, eps_flat, self.y, self.obs_repeat, 1.0, 0.0, 1.0, 0.0, 0.0,
-                                 self.cot, self.err_part, self.x_next, self.ws, step_row=self.row)
-            v = self._network_vjp(eps, x_in)
+            # the step's noise is drawn BEFORE K1 (the network consumes no random numbers, so the draw order of the
+            # run is unchanged) and folded into the mean: K2 reads mean + std z, cot and the VJP only
             if self._draw_in_graph:
                 self.z.normal_()
-            _native.dps_post_mean(self.x_next, self.cot, v, self.z, None if fixed else self.err_part,
+            _native.dps_pre_mean(self.op, self.x, eps_flat, self.y, self.obs_repeat, 1.0, 0.0, 1.0, 0.0, 0.0,
+                                 self.cot, self.err_part, self.x_next, self.ws, step_row=self.row, z=self.z)
+            v = self._network_vjp(eps, x_in)
+            _native.dps_post_mean(self.x_next, self.cot, v, None, None if fixed else self.err_part,
                                   0 if fixed else self.op.err_parts, self.n, 0.0, 0.0, 0.0, self.x,
                                   None if fixed else self.err, step_row=self.row)
             self.k_dev.add_(1)
@@ -275,17 +277,21 @@ class DPSRun:
         self.x, self.x_next = self.x_next, self.x
 
     def _step_fused_mean(self, sc: StepScalars, x_in, eps, eps_flat, z) -> None:
-        """The eager timestep with the bridge mean written by K1 (psx_dps_pre_mean / psx_dps_post_mean), in place."""
-        _native.dps_pre_mean(self.op, self.x, eps_flat, self.y, self.obs_repeat, sc.sqrt_acp, sc.sqrt_1m_acp,
-                             self.weight, sc.c_ell, sc.c_s, self.cot, self.err_part, self.x_next, self.ws)
-        v = self._network_vjp(eps, x_in)
+        """The eager timestep with the bridge mean (+ std z) written by K1 (psx_dps_pre_mean / psx_dps_post_mean), in
+        place.  The noise is drawn before K1 instead of after the VJP; the network draws nothing in between."""
         if sc.std != 0.0 and z is None:
             z = self.draw(self.view.flat_shape, self.device, self.dtype)
         if z is not None:
             z = z.reshape(self.L, self.n)
+            if not z.is_contiguous():
+                z = z.contiguous()
+        _native.dps_pre_mean(self.op, self.x, eps_flat, self.y, self.obs_repeat, sc.sqrt_acp, sc.sqrt_1m_acp,
+                             self.weight, sc.c_ell, sc.c_s, self.cot, self.err_part, self.x_next, self.ws,
+                             z=z if sc.std != 0.0 else None, std=sc.std)
+        v = self._network_vjp(eps, x_in)
         fixed = self._fixed_scale is not None
-        _native.dps_post_mean(self.x_next, self.cot, v, z, None if fixed else self.err_part,
-                              0 if fixed else self.op.err_parts, self.n, sc.sqrt_1m_acp, sc.std,
+        _native.dps_post_mean(self.x_next, self.cot, v, None, None if fixed else self.err_part,
+                              0 if fixed else self.op.err_parts, self.n, sc.sqrt_1m_acp, 0.0,
                               self._fixed_scale(sc) if fixed else self.gamma, self.x, None if fixed else self.err)
 
     def _step_bf16(self, k: int, sc: StepScalars, x_in, eps, eps_flat, z) -> None:

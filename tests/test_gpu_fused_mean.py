@@ -76,6 +76,18 @@ def test_pair_with_mean_is_bit_identical(L, persist, sc):
         _native.dps_post_mean(mean_c, cot_c, v, z, ep_c, parts, N, 0.0, 0.0, 0.0, state, None, step_row=row)
         torch.cuda.synchronize()
         assert torch.equal(mean_c, mean) and torch.equal(cot_c, cot_b) and torch.equal(state, out_b)
+        # the step's noise folded into the mean by K1 (mean + std z): K2 then reads mean, cot and the VJP only
+        cot_d, ep_d, mean_z, out_d = torch.empty_like(x), torch.empty_like(ep_a), torch.empty_like(x), torch.empty_like(x)
+        _native.dps_pre_mean(op, x, eps, y, L, sa, s1, weight, c_ell, c_s, cot_d, ep_d, mean_z, ws, z=z, std=std)
+        _native.dps_post_mean(mean_z, cot_d, v, None, ep_d, parts, N, s1, 0.0, gamma, out_d, None)
+        torch.cuda.synchronize()
+        assert torch.equal(mean_z, mean + f32(std) * z) and torch.equal(cot_d, cot_a) and torch.equal(out_d, out_a)
+        mean_z.fill_(float("nan"))
+        _native.dps_pre_mean(op, x, eps, y, L, 1.0, 0.0, 1.0, 0.0, 0.0, cot_d, ep_d, mean_z, ws, step_row=row, z=z)
+        state = x.clone()
+        _native.dps_post_mean(mean_z, cot_d, v, None, ep_d, parts, N, 0.0, 0.0, 0.0, state, None, step_row=row)
+        torch.cuda.synchronize()
+        assert torch.equal(state, out_a)
     finally:
         if persist:
             del os.environ["PSX_TC_PERSIST"]

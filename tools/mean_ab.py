@@ -41,12 +41,14 @@ def k2(i):
 
 def k1m(i):
     d = S[i]
-    _native.dps_pre_mean(nat, d["x"], d["eps"], y, L, 0.8, 0.6, 400.0, 0.99, 0.01, d["cot"], d["part"], d["mean"], d["ws"])
+    _native.dps_pre_mean(nat, d["x"], d["eps"], y, L, 0.8, 0.6, 400.0, 0.99, 0.01, d["cot"], d["part"], d["mean"], d["ws"],
+                         **({} if os.environ.get("NO_Z") else dict(z=d["z"], std=0.05)))
 
 
 def k2m(i):
     d = S[i]
-    _native.dps_post_mean(d["mean"], d["cot"], d["v"], d["z"], d["part"], nat.err_parts, n, 0.6, 0.05, 1.0, d["out"], None)
+    _native.dps_post_mean(d["mean"], d["cot"], d["v"], d["z"] if os.environ.get("NO_Z") else None, d["part"], nat.err_parts, n,
+                          0.6, 0.05 if os.environ.get("NO_Z") else 0.0, 1.0, d["out"], None)
 
 
 if os.environ.get("ONCE"):  # one launch of each kernel of the pair (for ncu)
