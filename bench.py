@@ -35,7 +35,7 @@ BATCH_PER_GPU = 16
 SAMPLING_STEPS = 1000
 GUIDED_STEPS = SAMPLING_STEPS - 2        # range(len(ts)-1, 1, -1)
 SIGMA_Y = 0.05
-NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02k_ncu_dram_bytes.json")   # written from the ncu --set full capture
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02q_ncu_dram_bytes.json")   # written from the ncu --set full capture
 METRIC = "dps_posterior_samples_per_s_256"
 WORKLOAD = "cfg2: DPS gaussian-blur 61x61 sigma3, ddpm-celebahq-256 UNet, 1000 steps, batch 16/GPU, 3x256x256"
 
