@@ -270,9 +270,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         if (mean_lag_ns > 0) {
           uint64_t t0, t1;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-          do {
+          for (int poll = 0; poll < 8192; ++poll) {  // bounded: a timer that does not advance must not hang the launch
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-          } while (t1 - t0 < (uint64_t)mean_lag_ns);
+            if (t1 - t0 >= (uint64_t)mean_lag_ns) break;
+          }
         }
         for (int k = 0; k < kMS && k < nt; ++k) request(k);
         for (int k = 0; k + kMS < nt; ++k) {

@@ -50,6 +50,14 @@ def test_abi_argument_validation_without_gpu():
     assert lib.psx_op_workspace_bytes(h, 4) == 0 and lib.psx_op_err_parts(h) >= 1
     assert lib.psx_dps_pre(h, None, None, None, 1, 1, 1.0, 0.0, 1.0, None, None, None, None, 0, None) == \
         _native.PSX_ERR_INVALID
+    # the bridge-mean pair (ABI 5): offered by the tensor-core blur only; argument checks come before any CUDA call
+    assert lib.psx_op_fuses_mean(h, 16) == 0 and lib.psx_op_fuses_mean(None, 16) == 0
+    assert lib.psx_dps_pre_mean(h, None, None, None, 1, 1, 1.0, 0.0, 1.0, 0.5, 0.5, None, 0.0, None, None, None, None,
+                                0, None) == _native.PSX_ERR_INVALID
+    assert lib.psx_dps_post_mean(None, None, None, None, None, 0, 1, 48, 0.6, 0.0, 1.0, None, None, None) == \
+        _native.PSX_ERR_INVALID
+    assert lib.psx_dps_post_mean_dev(None, None, None, None, None, 0, 1, 48, None, None, None, None) == \
+        _native.PSX_ERR_INVALID
     assert lib.psx_op_destroy(h) == _native.PSX_OK
     taps3 = (C.c_float * 3)(0.25, 0.5, 0.25)
     assert lib.psx_op_create_sepblur(3, 8, 8, taps3, 3, taps3, 3, C.byref(h)) == _native.PSX_OK
