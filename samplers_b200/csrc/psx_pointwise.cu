@@ -7,6 +7,9 @@
 
 #include "psx_common.cuh"
 
+#ifndef PSX_K2M_U
+#define PSX_K2M_U 4  // float4 groups per thread and batch in k2_post_mean (L <= 16: 1 / 2 / 4 -> 10.6 / 10.45 / 10.0 us)
+#endif
 namespace psx {
 
 // =========================================================================== K1: identity / mask
@@ -518,7 +521,7 @@ k2_post_mean(const float* __restrict__ mean, const float* __restrict__ cot, cons
   const int64_t n4 = n >> 2;
   const int64_t beg = (int64_t)blockIdx.x * chunk4, end = min(beg + chunk4, n4);
   const int64_t so = l * n;
-  constexpr int U = 2;
+  constexpr int U = PSX_K2M_U;
   constexpr int64_t kStride = (int64_t)kThreads * U;
   float4 mv[U], dv[U], vv[U], zv[U];
 #define PSX_K2M_LOAD(BASE)                                        \
