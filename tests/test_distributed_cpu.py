@@ -27,6 +27,35 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _run_world(target, world, make_args):
+    """Spawn `world` gloo ranks of `target(rank, world, port, *make_args(q))` and return their queue results sorted by
+    rank.  The rendezvous port is probed and released before the ranks bind it, so another process can take it in
+    between: a failed rendezvous is retried on a fresh port (twice) instead of failing the suite."""
+    import queue
+    import time
+    ctx = mp.get_context("spawn")
+    for _ in range(3):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, world, port, *make_args(q))) for r in range(world)]
+        for p in procs:
+            p.start()
+        results, deadline = [], time.time() + 120
+        while len(results) < world and time.time() < deadline:
+            try:
+                results.append(q.get(timeout=1))
+            except queue.Empty:
+                if any(p.exitcode not in (None, 0) for p in procs):
+                    break
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.terminate()
+        if len(results) == world and all(p.exitcode == 0 for p in procs):
+            return sorted(results, key=lambda t: t[0])
+    raise AssertionError("gloo world did not complete in three attempts")
+
+
 def _draw(rank, count, n, offset, scale):
     return offset + scale * torch.randn(count, n, generator=torch.Generator().manual_seed(100 + rank))
 
@@ -49,16 +78,7 @@ def _worker(rank, world, port, counts, n, q, offset=0.0, scale=1.0):
 @pytest.mark.parametrize("counts", [[3, 3], [4, 3]])
 def test_terminal_gather_and_moments_world2(counts):
     world, n = 2, 48
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, counts, n, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    results = _run_world(_worker, world, lambda q: (counts, n, q))
     expected = torch.cat([_draw(r, counts[r], n, 0.0, 1.0) for r in range(world)])
     for _, samples, mean, var in results:  # every rank ends with the same, complete answer
         assert torch.equal(samples, expected)
@@ -70,16 +90,7 @@ def test_posterior_variance_of_a_converged_posterior_world2():
     """256 samples with mean 0.9 and standard deviation 1e-3: sum(x^2) - R mean^2 has no correct digit left in fp32
     (0.81 * 256 against a spread of 2.6e-4); the two-pass form keeps 4+ digits."""
     world, n, counts = 2, 32, [128, 128]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, counts, n, q, 0.9, 1e-3)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    results = _run_world(_worker, world, lambda q: (counts, n, q, 0.9, 1e-3))
     expected = torch.cat([_draw(r, counts[r], n, 0.9, 1e-3) for r in range(world)]).double()
     ref = expected.var(0, unbiased=True)
     for _, samples, mean, var in results:
@@ -131,16 +142,7 @@ def test_global_norms_over_two_ranks_equal_the_full_batch():
     """Sharding a batch over 2 ranks with all-reduced sums of squares reproduces the reference's batch-global
     norms (psld.py:130,138; resample_kernels.py:27): same loss on both ranks, gradient = slice of the full one."""
     world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_norm_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    results = _run_world(_norm_worker, world, lambda q: (q,))
     g = torch.Generator().manual_seed(7)
     z_all, y_all = torch.randn(6, 8, generator=g), torch.randn(6, 12, generator=g)
     dec_w, enc_w = torch.randn(8, 12, generator=g) * 0.3, torch.randn(12, 8, generator=g) * 0.3
